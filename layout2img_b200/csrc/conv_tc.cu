@@ -1,0 +1,504 @@
+// 3x3 (pad 1) and 1x1 convolution as an implicit GEMM on the sm_100a tensor cores.
+//
+// Replaces the cuDNN calls behind nn.Conv2d on the hot path (reference
+// model/resnet_generator_app_v2.py:633-639,659-669 and model/rcnn_discriminator_app.py:297-326).
+//
+// Numerics: every fp32 operand x is carried as a bf16 pair (hi, lo) with x ~= hi + lo
+// (16 significant bits, fp32 exponent range).  A product a*b is accumulated in fp32 TMEM as
+// a_hi*b_hi + a_lo*b_hi + a_hi*b_lo -- three bf16 tcgen05.mma per K step.  Measured against
+// the fp32 reference this is ~60x more accurate than single-pass TF32.
+//
+// Data layout: activations NHWC (channel count padded to a multiple of 8), one tensor per
+// half of the pair.  Forward / data-gradient:
+//   GEMM M = 128 output pixels (a TW x TH x TN patch), N = BN output channels,
+//   K = taps x Cin, walked as (tap, 64-channel chunk).  The A tile of a tap is ONE 4-D TMA box
+//   at spatially shifted coordinates; the zero padding of the convolution is TMA's
+//   out-of-bounds fill.  Weights are pre-arranged [Cout][tap][Cin] (K-major).
+// Weight gradient:
+//   GEMM M = 128 output channels, N = BN input channels, K = pixels (64 per stage), both
+//   operands MN-major straight out of the NHWC tensors; one tap per CTA, split-K over pixels.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> global).
+#include "common.cuh"
+#include "conv_tc.h"
+
+namespace l2i {
+
+static constexpr int kThreads = 192;
+static constexpr int kBK = 64;          // bf16 elements per smem row (128 B, SWIZZLE_128B)
+static constexpr int kTileBytes = 128 * kBK * 2;   // one 128-row operand tile: 16 KB
+
+// ------------------------------------------------------------------------------------------
+// forward / dgrad
+// ------------------------------------------------------------------------------------------
+template <int BN>
+struct FwdCfg {
+  static constexpr int kStages = (BN == 128) ? 3 : 4;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = 2 * kTileBytes + 2 * kBBytes;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                const ConvFwdParams p) {
+  using Cfg = FwdCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* accum_bar = empty_bar + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int mt = blockIdx.x;
+  const int tw_i = mt % p.tiles_w;
+  const int th_i = (mt / p.tiles_w) % p.tiles_h;
+  const int tn_i = mt / (p.tiles_w * p.tiles_h);
+  const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
+  const int co0 = blockIdx.y * BN;
+  const int k_iters = p.taps * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_b_hi);
+    tma_prefetch_desc(&tm_b_lo);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < k_iters; ++it) {
+        const int s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int tap = it / p.kchunks;
+        const int kc = it - tap * p.kchunks;
+        const int dr = (p.taps == 9) ? (tap / 3 - 1) : 0;
+        const int ds = (p.taps == 9) ? (tap % 3 - 1) : 0;
+        uint8_t* st = smem + s * Cfg::kStageBytes;
+        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        tma_load_4d(st, &tm_a_hi, &full_bar[s], kc * kBK, w0 + ds, h0 + dr, n0);
+        tma_load_4d(st + kTileBytes, &tm_a_lo, &full_bar[s], kc * kBK, w0 + ds, h0 + dr, n0);
+        tma_load_2d(st + 2 * kTileBytes, &tm_b_hi, &full_bar[s], tap * p.cin_pad + kc * kBK, co0);
+        tma_load_2d(st + 2 * kTileBytes + Cfg::kBBytes, &tm_b_lo, &full_bar[s], tap * p.cin_pad + kc * kBK, co0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      for (int it = 0; it < k_iters; ++it) {
+        const int s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint32_t a_lo = a_hi + kTileBytes;
+        const uint32_t b_hi = a_hi + 2 * kTileBytes;
+        const uint32_t b_lo = b_hi + Cfg::kBBytes;
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          const uint64_t dah = umma_desc_sw128(a_hi + k * 32, 16, 1024);
+          const uint64_t dal = umma_desc_sw128(a_lo + k * 32, 16, 1024);
+          const uint64_t dbh = umma_desc_sw128(b_hi + k * 32, 16, 1024);
+          const uint64_t dbl = umma_desc_sw128(b_lo + k * 32, 16, 1024);
+          umma_bf16(tmem_base, dal, dbh, idesc, (it > 0 || k > 0) ? 1u : 0u);  // small terms first
+          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+          umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(accum_bar);         // accumulator complete
+    }
+  } else {
+    // ---- epilogue: warp q owns TMEM lanes [32q, 32q+32) = GEMM rows
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int tw = m % p.TW;
+    const int th = (m / p.TW) % p.TH;
+    const int tn = m / (p.TW * p.TH);
+    const int n_img = n0 + tn;
+    const bool row_ok = n_img < p.N;
+    const size_t pix = (static_cast<size_t>(n_img) * p.H + (h0 + th)) * p.W + (w0 + tw);
+    size_t rpix = pix;
+    if (p.res_shift) rpix = (static_cast<size_t>(n_img) * (p.H >> 1) + ((h0 + th) >> 1)) * (p.W >> 1) + ((w0 + tw) >> 1);
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const bool vec_ok = (p.cout & 3) == 0;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+      tmem_ld_wait();
+      const int cbase = co0 + c;
+      if (!row_ok || cbase >= p.cout) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int co = cbase + j;
+        float x = __uint_as_float(r[j]);
+        if (co < p.cout) {
+          if (p.bias) x += __ldg(p.bias + co);
+          if (p.residual) x += __ldg(p.residual + rpix * p.cout + co);
+        } else {
+          x = 0.f;
+        }
+        v[j] = x * p.out_scale;
+      }
+      if (p.out) {
+        float* o = p.out + pix * p.cout + cbase;
+        if (vec_ok && cbase + 32 <= p.cout) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 32 && cbase + j < p.cout; ++j) o[j] = v[j];
+        }
+      }
+      if (p.out_hi) {
+        // split (optionally ReLU'd) copy for a following convolution; channel stride cout_pad
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float a = v[j], b = v[j + 1];
+          if (p.relu_split) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          __nv_bfloat16 ah, al, bh, bl;
+          split_bf16(a, ah, al);
+          split_bf16(b, bh, bl);
+          hi[j >> 1] = pack_bf16x2(ah, bh);
+          lo[j >> 1] = pack_bf16x2(al, bl);
+        }
+        __nv_bfloat16* oh = p.out_hi + pix * p.cout_pad + cbase;
+        __nv_bfloat16* ol = p.out_lo + pix * p.cout_pad + cbase;
+        // cout_pad is a multiple of 8 and cbase a multiple of 32: 16-byte groups of 8 channels
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (cbase + g * 8 < p.cout_pad) {
+            *reinterpret_cast<uint4*>(oh + g * 8) = make_uint4(hi[g * 4], hi[g * 4 + 1], hi[g * 4 + 2], hi[g * 4 + 3]);
+            *reinterpret_cast<uint4*>(ol + g * 8) = make_uint4(lo[g * 4], lo[g * 4 + 1], lo[g * 4 + 2], lo[g * 4 + 3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient
+// ------------------------------------------------------------------------------------------
+template <int BN>
+struct WgCfg {
+  static constexpr int kStages = 3;
+  static constexpr int kABytes = 128 * 64 * 2;      // 128 channels x 64 pixels (two 64-channel boxes)
+  static constexpr int kBBytes = BN * 64 * 2;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_constant__ CUtensorMap tm_dy_lo,
+                  const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+                  const ConvWgradParams p) {
+  using Cfg = WgCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* accum_bar = empty_bar + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int co_t = blockIdx.x / p.cin_tiles;
+  const int ci_t = blockIdx.x - co_t * p.cin_tiles;
+  const int co0 = co_t * 128, ci0 = ci_t * BN;
+  const int tap = blockIdx.y;
+  const int dr = (p.taps == 9) ? (tap / 3 - 1) : 0;
+  const int ds = (p.taps == 9) ? (tap % 3 - 1) : 0;
+  const int pb_begin = blockIdx.z * p.blocks_per_split;
+  const int pb_end = min(pb_begin + p.blocks_per_split, p.pix_blocks);
+  const int k_iters = pb_end - pb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_dy_hi);
+    tma_prefetch_desc(&tm_dy_lo);
+    tma_prefetch_desc(&tm_x_hi);
+    tma_prefetch_desc(&tm_x_lo);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (k_iters > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int it = 0; it < k_iters; ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const int pb = pb_begin + it;
+          const int w0 = (pb % p.tiles_w) * p.TW;
+          const int h0 = ((pb / p.tiles_w) % p.tiles_h) * p.TH;
+          const int n0 = (pb / (p.tiles_w * p.tiles_h)) * p.TN;
+          uint8_t* st = smem + s * Cfg::kStageBytes;
+          mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            tma_load_4d(st + j * 8192, &tm_dy_hi, &full_bar[s], co0 + j * 64, w0, h0, n0);
+            tma_load_4d(st + Cfg::kABytes + j * 8192, &tm_dy_lo, &full_bar[s], co0 + j * 64, w0, h0, n0);
+          }
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) {
+            tma_load_4d(st + 2 * Cfg::kABytes + j * 8192, &tm_x_hi, &full_bar[s], ci0 + j * 64, w0 + ds, h0 + dr, n0);
+            tma_load_4d(st + 2 * Cfg::kABytes + Cfg::kBBytes + j * 8192, &tm_x_lo, &full_bar[s], ci0 + j * 64,
+                        w0 + ds, h0 + dr, n0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+        for (int it = 0; it < k_iters; ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t a_lo = a_hi + Cfg::kABytes;
+          const uint32_t b_hi = a_hi + 2 * Cfg::kABytes;
+          const uint32_t b_lo = b_hi + Cfg::kBBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {   // 16 pixels per MMA
+            const uint64_t dah = umma_desc_sw128(a_hi + k * 2048, 8192, 1024);
+            const uint64_t dal = umma_desc_sw128(a_lo + k * 2048, 8192, 1024);
+            const uint64_t dbh = umma_desc_sw128(b_hi + k * 2048, 8192, 1024);
+            const uint64_t dbl = umma_desc_sw128(b_lo + k * 2048, 8192, 1024);
+            umma_bf16(tmem_base, dal, dbh, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+            umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(accum_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      const int co = co0 + q * 32 + lane;
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+        tmem_ld_wait();
+        if (co >= p.cout) continue;
+        float* o = p.dw + (static_cast<size_t>(co) * p.taps + tap) * p.cin + ci0 + c;
+        if (p.atomic) {
+          for (int j = 0; j < 32 && ci0 + c + j < p.cin; ++j) atomicAdd(o + j, __uint_as_float(r[j]));
+        } else {
+          for (int j = 0; j < 32 && ci0 + c + j < p.cin; ++j) o[j] = __uint_as_float(r[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// NHWC bf16 activation map: dims (C, W, H, N), box (64, bw, bh, bn), 128B swizzle, zero OOB fill
+static int make_act_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int Cpad, int bw, int bh, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return L2I_ERR_DRIVER; }
+  cuuint64_t dims[4] = {(cuuint64_t)Cpad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)Cpad * 2, (cuuint64_t)W * Cpad * 2, (cuuint64_t)H * W * Cpad * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(act N=%d H=%d W=%d C=%d box=%d,%d,%d) failed: %d", N, H, W, Cpad, bw, bh, bn, (int)r);
+    return L2I_ERR_DRIVER;
+  }
+  return L2I_OK;
+}
+
+// weight map: [rows][K] bf16 K-major, box (64, box_rows)
+static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return L2I_ERR_DRIVER; }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(weight rows=%d K=%d) failed: %d", rows, K, (int)r);
+    return L2I_ERR_DRIVER;
+  }
+  return L2I_OK;
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// pick a (tw, th, tn) patch of exactly `pixels` pixels
+static int pick_tile(int H, int W, int pixels, int* tw, int* th, int* tn) {
+  if (!is_pow2(H) || !is_pow2(W)) return L2I_ERR_UNSUPPORTED;
+  int w = W < 16 ? W : 16;
+  int h = pixels / w;
+  if (h > H) h = H;
+  *tw = w; *th = h; *tn = pixels / (w * h);
+  return L2I_OK;
+}
+
+template <int BN>
+static int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                      const CUtensorMap& b_lo, const ConvFwdParams& p, dim3 grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<BN>::kSmem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_fwd): %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
+    configured = true;
+  }
+  conv_fwd_kernel<BN><<<grid, kThreads, FwdCfg<BN>::kSmem, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  return check_launch("conv_fwd_kernel");
+}
+
+int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream) {
+  if (a.taps != 9 && a.taps != 1) { set_error("conv: taps must be 9 (3x3 pad 1) or 1 (1x1), got %d", a.taps); return L2I_ERR_UNSUPPORTED; }
+  if (a.cin_pad % 8 || a.cin_pad <= 0 || a.cout <= 0 || a.N <= 0) { set_error("conv: bad channel/batch sizes (cin_pad=%d cout=%d N=%d)", a.cin_pad, a.cout, a.N); return L2I_ERR_BAD_ARG; }
+  if (!a.x_hi || !a.x_lo || !a.w_hi || !a.w_lo || (!a.out && !a.out_hi)) { set_error("conv: null operand pointer"); return L2I_ERR_BAD_ARG; }
+  if (a.out_hi && (a.cout_pad % 8 || a.cout_pad < a.cout)) { set_error("conv: cout_pad must be a multiple of 8 >= cout"); return L2I_ERR_BAD_ARG; }
+  if (a.res_shift && ((a.H | a.W) & 1)) { set_error("conv: upsampled residual needs even H, W"); return L2I_ERR_BAD_ARG; }
+  ConvFwdParams p;
+  p.N = a.N; p.H = a.H; p.W = a.W; p.cin_pad = a.cin_pad; p.cout = a.cout; p.taps = a.taps;
+  if (pick_tile(a.H, a.W, 128, &p.TW, &p.TH, &p.TN) != L2I_OK) { set_error("conv: H=%d W=%d must be powers of two", a.H, a.W); return L2I_ERR_UNSUPPORTED; }
+  p.tiles_w = a.W / p.TW; p.tiles_h = a.H / p.TH;
+  const int tiles_n = (a.N + p.TN - 1) / p.TN;
+  p.kchunks = (a.cin_pad + kBK - 1) / kBK;
+  p.bias = a.bias; p.residual = a.residual; p.res_shift = a.res_shift; p.out = a.out;
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(a.out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(a.out_lo);
+  p.cout_pad = a.cout_pad; p.relu_split = a.relu_split; p.out_scale = a.out_scale;
+  const int BN = (a.cout > 64) ? 128 : 64;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  if ((rc = make_act_map(&ta_hi, a.x_hi, a.N, a.H, a.W, a.cin_pad, p.TW, p.TH, p.TN))) return rc;
+  if ((rc = make_act_map(&ta_lo, a.x_lo, a.N, a.H, a.W, a.cin_pad, p.TW, p.TH, p.TN))) return rc;
+  if ((rc = make_w_map(&tb_hi, a.w_hi, a.cout, a.taps * a.cin_pad, BN))) return rc;
+  if ((rc = make_w_map(&tb_lo, a.w_lo, a.cout, a.taps * a.cin_pad, BN))) return rc;
+  dim3 grid(p.tiles_w * p.tiles_h * tiles_n, (a.cout + BN - 1) / BN);
+  if (BN == 128) return launch_fwd<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
+  return launch_fwd<64>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                        const CUtensorMap& b_lo, const ConvWgradParams& p, dim3 grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<BN>::kSmem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_wgrad): %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
+    configured = true;
+  }
+  conv_wgrad_kernel<BN><<<grid, kThreads, WgCfg<BN>::kSmem, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  return check_launch("conv_wgrad_kernel");
+}
+
+int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t stream) {
+  if (a.taps != 9 && a.taps != 1) { set_error("wgrad: taps must be 9 or 1"); return L2I_ERR_UNSUPPORTED; }
+  if (a.cin_pad % 8 || a.cout_pad % 8 || a.cin > a.cin_pad || a.cout > a.cout_pad || a.N <= 0) { set_error("wgrad: bad sizes"); return L2I_ERR_BAD_ARG; }
+  if (!a.dy_hi || !a.dy_lo || !a.x_hi || !a.x_lo || !a.dw) { set_error("wgrad: null pointer"); return L2I_ERR_BAD_ARG; }
+  ConvWgradParams p;
+  p.N = a.N; p.H = a.H; p.W = a.W; p.cin = a.cin; p.cout = a.cout; p.taps = a.taps;
+  if (pick_tile(a.H, a.W, 64, &p.TW, &p.TH, &p.TN) != L2I_OK) { set_error("wgrad: H=%d W=%d must be powers of two", a.H, a.W); return L2I_ERR_UNSUPPORTED; }
+  p.tiles_w = a.W / p.TW; p.tiles_h = a.H / p.TH;
+  const int tiles_n = (a.N + p.TN - 1) / p.TN;
+  p.pix_blocks = p.tiles_w * p.tiles_h * tiles_n;
+  const int BN = (a.cin > 64) ? 128 : 64;
+  p.cin_tiles = (a.cin + BN - 1) / BN;
+  const int co_tiles = (a.cout + 127) / 128;
+  const int base_ctas = co_tiles * p.cin_tiles * a.taps;
+  // split-K over pixel blocks until the grid covers ~2 waves of 148 SMs (>= 8 blocks per split)
+  int splits = (2 * 148 + base_ctas - 1) / base_ctas;
+  int max_splits = (p.pix_blocks + 7) / 8;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.blocks_per_split = (p.pix_blocks + splits - 1) / splits;
+  splits = (p.pix_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
+  p.atomic = splits > 1;
+  p.dw = a.dw;
+  if (p.atomic) {
+    cudaError_t e = cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.cout * a.taps * a.cin, stream);
+    if (e != cudaSuccess) { set_error("wgrad: memset failed: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
+  }
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  if ((rc = make_act_map(&ta_hi, a.dy_hi, a.N, a.H, a.W, a.cout_pad, p.TW, p.TH, p.TN))) return rc;
+  if ((rc = make_act_map(&ta_lo, a.dy_lo, a.N, a.H, a.W, a.cout_pad, p.TW, p.TH, p.TN))) return rc;
+  if ((rc = make_act_map(&tb_hi, a.x_hi, a.N, a.H, a.W, a.cin_pad, p.TW, p.TH, p.TN))) return rc;
+  if ((rc = make_act_map(&tb_lo, a.x_lo, a.N, a.H, a.W, a.cin_pad, p.TW, p.TH, p.TN))) return rc;
+  dim3 grid(co_tiles * p.cin_tiles, a.taps, splits);
+  if (BN == 128) return launch_wgrad<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
+  return launch_wgrad<64>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
+}
+
+}  // namespace l2i

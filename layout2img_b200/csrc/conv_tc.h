@@ -1,0 +1,50 @@
+// Internal (C++) interface of the tensor-core convolution kernels; the C ABI lives in api.cu.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace l2i {
+
+struct ConvFwdParams {          // device-side view
+  int N, H, W, cin_pad, cout, taps;
+  int TW, TH, TN, tiles_w, tiles_h, kchunks;
+  const float* bias;            // [cout] or null
+  const float* residual;        // [N,H,W,cout] (res_shift=0) or [N,H/2,W/2,cout] nearest-x2 (res_shift=1), or null
+  int res_shift;
+  float* out;                   // [N,H,W,cout] fp32 or null
+  __nv_bfloat16* out_hi;        // [N,H,W,cout_pad] split copy (optionally ReLU'd) or null
+  __nv_bfloat16* out_lo;
+  int cout_pad, relu_split;
+  float out_scale;
+};
+
+struct ConvFwdArgs {            // host-side call
+  int N, H, W, cin_pad, cout, taps;
+  const void *x_hi, *x_lo;      // [N,H,W,cin_pad] bf16
+  const void *w_hi, *w_lo;      // [cout][taps][cin_pad] bf16
+  const float* bias;
+  const float* residual;
+  int res_shift;
+  float* out;
+  void *out_hi, *out_lo;
+  int cout_pad, relu_split;
+  float out_scale;
+};
+
+struct ConvWgradParams {
+  int N, H, W, cin, cout, taps;
+  int TW, TH, TN, tiles_w, tiles_h, pix_blocks, blocks_per_split, cin_tiles, atomic;
+  float* dw;                    // [cout][taps][cin] fp32
+};
+
+struct ConvWgradArgs {
+  int N, H, W, cin, cin_pad, cout, cout_pad, taps;
+  const void *dy_hi, *dy_lo;    // [N,H,W,cout_pad] bf16
+  const void *x_hi, *x_lo;      // [N,H,W,cin_pad] bf16
+  float* dw;
+};
+
+int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream);
+int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t stream);
+
+}  // namespace l2i
