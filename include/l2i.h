@@ -54,6 +54,75 @@ int l2i_conv2d_fwd(int N, int H, int W, int cin_pad, int cout, int taps, const v
 int l2i_conv2d_wgrad(int N, int H, int W, int cin, int cin_pad, int cout, int cout_pad, int taps, const void* dy_hi,
                      const void* dy_lo, const void* x_hi, const void* x_lo, float* dw, void* stream);
 
+/* ---- batch-norm statistics + ISLA modulation (reference model/norm_module.py:152-189,
+ *      model/sync_batchnorm/batchnorm.py:48-53,113-125) ------------------------------------------- */
+
+/* sums[2c] = sum x, sums[2c+1] = sum x^2 over `pixels` rows of x [pixels, C] (fp64 accumulators). */
+int l2i_bn_stats(const float* x, long long pixels, int C, double* sums, void* stream);
+/* mean_invstd [2C] = (mean, 1/sqrt(biased var + eps)); running stats (nullable) updated with
+ * momentum and the unbiased variance, as F.batch_norm does in training mode. */
+int l2i_bn_finalize(const double* sums, double count, int C, float eps, float momentum, float* running_mean,
+                    float* running_var, float* mean_invstd, void* stream);
+/* eval mode: mean_invstd from the running statistics. */
+int l2i_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean_invstd,
+                      void* stream);
+/* out = (sum_o m_o gamma_o/(sum_o m_o + 1e-6) + 1) * xhat + sum_o m_o beta_o/(sum_o m_o + 1e-6).
+ * x [B,H,W,C]; mask [B,H,W,O] (pixel-major); gamma, beta [B,O,C].  O == 0: plain batch norm with the
+ * optional affine (aff_w, aff_b).  Outputs: out fp32 [B,H,W,C] (nullable) and/or the pair
+ * [B,H<<up2,W<<up2,cpad] of relu ? relu(out) : out, nearest-upsampled when up2. */
+int l2i_isla_fwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
+                 const float* aff_w, const float* aff_b, int B, int H, int W, int C, int O, float* out, void* hi,
+                 void* lo, int cpad, int relu, int up2, void* stream);
+/* Backward of l2i_isla_fwd followed by (relu) and (nearest x2): dout [B,H<<up2,W<<up2,C].
+ * Writes dx [B,H,W,C]; for O > 0 dmask [B,H,W,O], dgamma, dbeta [B,O,C]; csum [2C] fp64 receives
+ * (sum dxhat, sum dxhat*xhat) for O > 0 or (dbias, dweight) of the affine form for O == 0.
+ * gbuf [B,H,W,C] is scratch.  train = 0 skips the batch-statistics terms (eval-mode BN). */
+int l2i_isla_bwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
+                 const float* aff_w, const float* aff_b, const float* dout, int B, int H, int W, int C, int O,
+                 int relu, int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum,
+                 float* dx, void* stream);
+
+/* ---- layout maps (reference model/resnet_generator_app_v2.py:466-470,697-721, utils/bilinear.py:137-192)
+ *      bbox [B*O,4] xywh in [0,1]; maps are [B,O,S,S] unless stated ------------------------------- */
+int l2i_bbox_mask(const float* bbox, int BO, int H, int W, float* out, void* stream);
+int l2i_masks_to_layout_fwd(const float* bbox, const float* masks, int BO, int M, int S, float* out, void* stream);
+int l2i_masks_to_layout_bwd(const float* bbox, const float* dout, int BO, int M, int S, float* dmasks, void* stream);
+/* bilinear (align_corners=False) resize of [B,O,hi,wi] to [B,O,h,w] (pixel_major = 0) or [B,h,w,O]
+ * (pixel_major = 1); identity copy/transpose when sizes match.  bwd is a deterministic gather. */
+int l2i_mask_resize_fwd(const float* in, int B, int O, int hi, int wi, int h, int w, int pixel_major, float* out,
+                        void* stream);
+int l2i_mask_resize_bwd(const float* dout, int B, int O, int hi, int wi, int h, int w, int pixel_major, float* din,
+                        void* stream);
+/* out[b,o] = bilinear(bmask -> h) * (1 - a) + sigmoid(stage[b,:,:,y]) * nearest(hard -> h) * a,
+ * a = sigmoid(alpha[y]); stage [B,h,w,NC] NHWC, y [B,O] int64, alpha [NC]. */
+int l2i_stage_mix_fwd(const float* stage, const int64_t* y, const float* alpha, const float* bmask, const float* hard,
+                      int B, int O, int h, int w, int NC, int S, float* out, void* stream);
+/* dstage [B,h,w,NC] and dalpha [NC] must be zero-initialised; dsoft [B,O,h,w] = dout * (1 - a). */
+int l2i_stage_mix_bwd(const float* stage, const int64_t* y, const float* alpha, const float* bmask, const float* hard,
+                      const float* dout, int B, int O, int h, int w, int NC, int S, float* dstage, float* dalpha,
+                      float* dsoft, void* stream);
+
+/* ---- ROIAlign (the operator of the reference's setup.py:46-54 extension `model.roi_layers._C`;
+ *      call sites model/rcnn_discriminator_app.py:98-99,139,143; torchvision semantics, aligned=False,
+ *      sampling_ratio=0).  feat [N,H,W,C]; rois [K,5] = (image, x0, y0, x1, y1) px; out [K,P,P,C]. */
+int l2i_roi_align_fwd(const float* feat, const float* rois, int K, int N, int H, int W, int C, int P, float scale,
+                      float* out, void* stream);
+int l2i_roi_align_bwd(const float* dout, const float* rois, int K, int N, int H, int W, int C, int P, float scale,
+                      float* dfeat, void* stream);
+/* 2x2 average pooling, NHWC (F.avg_pool2d(x, 2) in the discriminator blocks). */
+int l2i_avgpool2_fwd(const float* x, int N, int H, int W, int C, float* out, void* stream);
+int l2i_avgpool2_bwd(const float* dout, int N, int H, int W, int C, float* dx, void* stream);
+
+/* ---- object-context attention (reference model/resnet_generator_app_v2.py:17-120,172-192), one head.
+ *      q, k, v, out [B,O,D]; bbox [B,O,4]; y [B,O] int64 (0 = padding key); wg [64], bg [1];
+ *      p_save, glin_save [B,O,O] are kept for the backward. -------------------------------------- */
+int l2i_box_attention_fwd(const float* q, const float* k, const float* v, const float* bbox, const int64_t* y,
+                          const float* wg, const float* bg, int B, int O, int D, float* out, float* p_save,
+                          float* glin_save, void* stream);
+int l2i_box_attention_bwd(const float* q, const float* k, const float* v, const float* bbox, const int64_t* y,
+                          const float* p_save, const float* glin_save, const float* dout, int B, int O, int D,
+                          float* dq, float* dk, float* dv, float* dwg, float* dbg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,30 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(l2i_[a-z0-9_]+)\s*\(", txt)))
 
 
+_CTYPES = {"int": ctypes.c_int, "float": ctypes.c_float, "double": ctypes.c_double,
+           "long long": ctypes.c_longlong, "int64_t": ctypes.c_int64}
+
+
+def prototypes():
+    """{name: [ctypes argument types]} parsed from include/l2i.h (pointers -> c_void_p)."""
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|const char\*)\s+(l2i_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", txt):
+        name, args = m.group(1), m.group(2).strip()
+        types = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    types.append(ctypes.c_void_p)
+                else:
+                    base = re.sub(r"\bconst\b", "", a).strip().rsplit(" ", 1)[0].strip()
+                    types.append(_CTYPES[base])
+        out[name] = types
+    return out
+
+
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
@@ -35,23 +59,19 @@ def lib() -> ctypes.CDLL:
                 f"{LIB_PATH} is missing: build it with `python -m layout2img_b200.build` "
                 "(nvcc, sm_100a). There is no fallback path.")
         _lib = ctypes.CDLL(LIB_PATH)
-        _lib.l2i_last_error.restype = ctypes.c_char_p
-        _lib.l2i_version.restype = ctypes.c_int
+        for name, types in prototypes().items():
+            fn = getattr(_lib, name)
+            fn.argtypes = types
+            fn.restype = ctypes.c_char_p if name == "l2i_last_error" else ctypes.c_int
     return _lib
 
 
 def _conv(a):
     import torch
-    if a is None:
-        return None
     if isinstance(a, torch.Tensor):
-        return ctypes.c_void_p(a.data_ptr())
-    if isinstance(a, float):
-        return ctypes.c_float(a)
+        return a.data_ptr()
     if isinstance(a, bool):
-        return ctypes.c_int(int(a))
-    if isinstance(a, int):
-        return ctypes.c_int(a)
+        return int(a)
     return a
 
 
@@ -60,8 +80,7 @@ def call(name: str, *args):
     current torch CUDA stream is appended as the trailing `void* stream` argument."""
     import torch
     fn = getattr(lib(), name)
-    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    rc = fn(*[_conv(a) for a in args], stream)
+    rc = fn(*[_conv(a) for a in args], torch.cuda.current_stream().cuda_stream)
     if rc != 0:
         msg = lib().l2i_last_error().decode(errors="replace")
         if rc in (-1, -2):

@@ -60,4 +60,81 @@ int l2i_conv2d_wgrad(int N, int H, int W, int cin, int cin_pad, int cout, int co
   return conv_wgrad_tc(a, ST(stream));
 }
 
+int l2i_bn_stats(const float* x, long long pixels, int C, double* sums, void* stream) {
+  return bn_stats(x, pixels, C, sums, ST(stream));
+}
+int l2i_bn_finalize(const double* sums, double count, int C, float eps, float momentum, float* running_mean,
+                    float* running_var, float* mean_invstd, void* stream) {
+  return bn_finalize(sums, count, C, eps, momentum, running_mean, running_var, mean_invstd, ST(stream));
+}
+int l2i_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean_invstd,
+                      void* stream) {
+  return bn_eval_stats(running_mean, running_var, C, eps, mean_invstd, ST(stream));
+}
+int l2i_isla_fwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
+                 const float* aff_w, const float* aff_b, int B, int H, int W, int C, int O, float* out, void* hi,
+                 void* lo, int cpad, int relu, int up2, void* stream) {
+  return isla_fwd(x, mean_invstd, mask, gamma, beta, aff_w, aff_b, B, H, W, C, O, out, hi, lo, cpad, relu, up2, ST(stream));
+}
+int l2i_isla_bwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
+                 const float* aff_w, const float* aff_b, const float* dout, int B, int H, int W, int C, int O,
+                 int relu, int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum,
+                 float* dx, void* stream) {
+  return isla_bwd(x, mean_invstd, mask, gamma, beta, aff_w, aff_b, dout, B, H, W, C, O, relu, up2, train, gbuf, dmask,
+                  dgamma, dbeta, csum, dx, ST(stream));
+}
+int l2i_bbox_mask(const float* bbox, int BO, int H, int W, float* out, void* stream) {
+  return bbox_mask(bbox, BO, H, W, out, ST(stream));
+}
+int l2i_masks_to_layout_fwd(const float* bbox, const float* masks, int BO, int M, int S, float* out, void* stream) {
+  return masks_to_layout_fwd(bbox, masks, BO, M, S, out, ST(stream));
+}
+int l2i_masks_to_layout_bwd(const float* bbox, const float* dout, int BO, int M, int S, float* dmasks, void* stream) {
+  return masks_to_layout_bwd(bbox, dout, BO, M, S, dmasks, ST(stream));
+}
+int l2i_mask_resize_fwd(const float* in, int B, int O, int hi, int wi, int h, int w, int pixel_major, float* out,
+                        void* stream) {
+  return mask_resize_fwd(in, B, O, hi, wi, h, w, pixel_major, out, ST(stream));
+}
+int l2i_mask_resize_bwd(const float* dout, int B, int O, int hi, int wi, int h, int w, int pixel_major, float* din,
+                        void* stream) {
+  return mask_resize_bwd(dout, B, O, hi, wi, h, w, pixel_major, din, ST(stream));
+}
+int l2i_stage_mix_fwd(const float* stage, const int64_t* y, const float* alpha, const float* bmask, const float* hard,
+                      int B, int O, int h, int w, int NC, int S, float* out, void* stream) {
+  return stage_mix_fwd(stage, reinterpret_cast<const long long*>(y), alpha, bmask, hard, B, O, h, w, NC, S, out, ST(stream));
+}
+int l2i_stage_mix_bwd(const float* stage, const int64_t* y, const float* alpha, const float* bmask, const float* hard,
+                      const float* dout, int B, int O, int h, int w, int NC, int S, float* dstage, float* dalpha,
+                      float* dsoft, void* stream) {
+  return stage_mix_bwd(stage, reinterpret_cast<const long long*>(y), alpha, bmask, hard, dout, B, O, h, w, NC, S, dstage,
+                       dalpha, dsoft, ST(stream));
+}
+int l2i_roi_align_fwd(const float* feat, const float* rois, int K, int N, int H, int W, int C, int P, float scale,
+                      float* out, void* stream) {
+  return roi_align_fwd(feat, rois, K, N, H, W, C, P, scale, out, ST(stream));
+}
+int l2i_roi_align_bwd(const float* dout, const float* rois, int K, int N, int H, int W, int C, int P, float scale,
+                      float* dfeat, void* stream) {
+  return roi_align_bwd(dout, rois, K, N, H, W, C, P, scale, dfeat, ST(stream));
+}
+int l2i_avgpool2_fwd(const float* x, int N, int H, int W, int C, float* out, void* stream) {
+  return avgpool2_fwd(x, N, H, W, C, out, ST(stream));
+}
+int l2i_avgpool2_bwd(const float* dout, int N, int H, int W, int C, float* dx, void* stream) {
+  return avgpool2_bwd(dout, N, H, W, C, dx, ST(stream));
+}
+int l2i_box_attention_fwd(const float* q, const float* k, const float* v, const float* bbox, const int64_t* y,
+                          const float* wg, const float* bg, int B, int O, int D, float* out, float* p_save,
+                          float* glin_save, void* stream) {
+  return box_attention_fwd(q, k, v, bbox, reinterpret_cast<const long long*>(y), wg, bg, B, O, D, out, p_save, glin_save,
+                           ST(stream));
+}
+int l2i_box_attention_bwd(const float* q, const float* k, const float* v, const float* bbox, const int64_t* y,
+                          const float* p_save, const float* glin_save, const float* dout, int B, int O, int D,
+                          float* dq, float* dk, float* dv, float* dwg, float* dbg, void* stream) {
+  return box_attention_bwd(q, k, v, bbox, reinterpret_cast<const long long*>(y), p_save, glin_save, dout, B, O, D, dq, dk,
+                           dv, dwg, dbg, ST(stream));
+}
+
 }  // extern "C"

@@ -26,11 +26,11 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, long long pixels, i
   const int tpp = blockDim.x / cg > 0 ? blockDim.x / cg : 1;  // pixels handled per block iteration
   const int g = threadIdx.x % cg;
   const int prow = threadIdx.x / cg;
-  if (prow >= tpp) return;
+  const bool active = prow < tpp;
   double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   const long long stride = 1LL * gridDim.x * tpp;
   long long p = 1LL * blockIdx.x * tpp + prow;
-  while (p < pixels) {
+  while (active && p < pixels) {
     float fs[4] = {0, 0, 0, 0}, fq[4] = {0, 0, 0, 0};
 #pragma unroll 4
     for (int it = 0; it < 16 && p < pixels; ++it, p += stride) {
@@ -42,9 +42,11 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, long long pixels, i
     for (int j = 0; j < 4; ++j) { s[j] += fs[j]; q[j] += fq[j]; }
   }
   extern __shared__ double sh_d[];                        // [tpp][C][2]
-  double* mine = sh_d + (static_cast<size_t>(prow) * C + g * 4) * 2;
+  if (active) {
+    double* mine = sh_d + (static_cast<size_t>(prow) * C + g * 4) * 2;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { mine[j * 2] = s[j]; mine[j * 2 + 1] = q[j]; }
+    for (int j = 0; j < 4; ++j) { mine[j * 2] = s[j]; mine[j * 2 + 1] = q[j]; }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
     double a = 0;

@@ -28,4 +28,32 @@ int isla_bwd(const float* x, const float* mean_invstd, const float* mask, const 
              int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum, float* dx,
              cudaStream_t stream);
 
+// layout_ops.cu
+int bbox_mask(const float* bbox, int BO, int H, int W, float* out, cudaStream_t stream);
+int masks_to_layout_fwd(const float* bbox, const float* masks, int BO, int M, int S, float* out, cudaStream_t stream);
+int masks_to_layout_bwd(const float* bbox, const float* dout, int BO, int M, int S, float* dmasks, cudaStream_t stream);
+int mask_resize_fwd(const float* in, int B, int O, int hi, int wi, int h, int w, int pixel_major, float* out,
+                    cudaStream_t stream);
+int mask_resize_bwd(const float* dout, int B, int O, int hi, int wi, int h, int w, int pixel_major, float* din,
+                    cudaStream_t stream);
+int stage_mix_fwd(const float* stage, const long long* y, const float* alpha, const float* bmask, const float* hard,
+                  int B, int O, int h, int w, int NC, int S, float* out, cudaStream_t stream);
+int stage_mix_bwd(const float* stage, const long long* y, const float* alpha, const float* bmask, const float* hard,
+                  const float* dout, int B, int O, int h, int w, int NC, int S, float* dstage, float* dalpha,
+                  float* dsoft, cudaStream_t stream);
+// roi_align.cu
+int roi_align_fwd(const float* feat, const float* rois, int K, int N, int H, int W, int C, int P, float scale, float* out,
+                  cudaStream_t stream);
+int roi_align_bwd(const float* dout, const float* rois, int K, int N, int H, int W, int C, int P, float scale, float* dfeat,
+                  cudaStream_t stream);
+int avgpool2_fwd(const float* x, int N, int H, int W, int C, float* out, cudaStream_t stream);
+int avgpool2_bwd(const float* dout, int N, int H, int W, int C, float* dx, cudaStream_t stream);
+// attention.cu
+int box_attention_fwd(const float* q, const float* k, const float* v, const float* bbox, const long long* y,
+                      const float* wg, const float* bg, int B, int O, int D, float* out, float* p_save, float* glin_save,
+                      cudaStream_t stream);
+int box_attention_bwd(const float* q, const float* k, const float* v, const float* bbox, const long long* y,
+                      const float* p_save, const float* glin_save, const float* dout, int B, int O, int D, float* dq,
+                      float* dk, float* dv, float* dwg, float* dbg, cudaStream_t stream);
+
 }  // namespace l2i

@@ -1,0 +1,332 @@
+// Layout-map kernels of the generator (HBM-trivial, index-exact):
+//   bbox_mask         reference model/resnet_generator_app_v2.py:697-721   (bit-exact {0,1} map)
+//   masks_to_layout   reference utils/bilinear.py:137-192                  (grid_sample paste, fwd + bwd)
+//   mask_resize       F.interpolate(mode='bilinear', align_corners=False)   norm_module.py:176,
+//                     resnet_generator_app_v2.py:470 (fwd + deterministic gather-form bwd)
+//   stage_mask_mix    reference model/resnet_generator_app_v2.py:466-470    (fwd + bwd)
+// Index rules follow SURVEY.md Appendix C.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace l2i {
+
+// torch.linspace(0, 1, n)[i] in fp32: step = fl(1/(n-1)); fl(step*i) below the midpoint,
+// fl(1 - step*(n-1-i)) (single rounding) above it.
+__device__ __forceinline__ float linspace01(int i, int n) {
+  const float step = __fdiv_rn(1.0f, static_cast<float>(n - 1));
+  return (i < n / 2) ? __fmul_rn(step, static_cast<float>(i)) : __fmaf_rn(-step, static_cast<float>(n - 1 - i), 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------ bbox_mask
+__global__ void bbox_mask_kernel(const float* __restrict__ bbox, int BO, int H, int W, float* __restrict__ out) {
+  const long long total = 1LL * BO * H * W;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    const int y = static_cast<int>((i / W) % H);
+    const int bo = static_cast<int>(i / (1LL * W * H));
+    const float x0 = __ldg(bbox + bo * 4), y0 = __ldg(bbox + bo * 4 + 1);
+    const float ww = __ldg(bbox + bo * 4 + 2), hh = __ldg(bbox + bo * 4 + 3);
+    const float X = __fdiv_rn(__fsub_rn(linspace01(x, W), x0), ww);
+    const float Y = __fdiv_rn(__fsub_rn(linspace01(y, H), y0), hh);
+    const bool outside = (X < 0.f) | (X > 1.f) | (Y < 0.f) | (Y > 1.f);
+    out[i] = outside ? 0.f : 1.f;
+  }
+}
+
+int bbox_mask(const float* bbox, int BO, int H, int W, float* out, cudaStream_t stream) {
+  if (!bbox || !out || BO <= 0 || H < 2 || W < 2) { set_error("bbox_mask: bad arguments"); return L2I_ERR_BAD_ARG; }
+  const long long total = 1LL * BO * H * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bbox_mask_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(bbox, BO, H, W, out);
+  return check_launch("bbox_mask_kernel");
+}
+
+// ------------------------------------------------------------------------------------------ masks_to_layout
+struct GridTaps {
+  int x0, y0;
+  float nw, ne, sw, se;
+};
+__device__ __forceinline__ GridTaps grid_taps(const float* __restrict__ box, int x, int y, int S, int M) {
+  const float bx = __ldg(box), by = __ldg(box + 1), bw = __ldg(box + 2), bh = __ldg(box + 3);
+  const float X = __fdiv_rn(__fsub_rn(linspace01(x, S), bx), bw);
+  const float Y = __fdiv_rn(__fsub_rn(linspace01(y, S), by), bh);
+  const float gx = __fsub_rn(__fmul_rn(X, 2.0f), 1.0f), gy = __fsub_rn(__fmul_rn(Y, 2.0f), 1.0f);
+  // grid_sample unnormalise, align_corners=False: ((g + 1) * size - 1) / 2
+  const float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), static_cast<float>(M)), 1.0f), 2.0f);
+  const float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), static_cast<float>(M)), 1.0f), 2.0f);
+  const float fx = floorf(ix), fy = floorf(iy);
+  GridTaps t;
+  // keep the integer conversion safe for far-away (padding) boxes
+  t.x0 = (fx < -2.f) ? -2 : (fx > M + 1.f ? M + 1 : static_cast<int>(fx));
+  t.y0 = (fy < -2.f) ? -2 : (fy > M + 1.f ? M + 1 : static_cast<int>(fy));
+  const float ex = fx + 1.0f, ey = fy + 1.0f;
+  t.nw = (ex - ix) * (ey - iy);
+  t.ne = (ix - fx) * (ey - iy);
+  t.sw = (ex - ix) * (iy - fy);
+  t.se = (ix - fx) * (iy - fy);
+  return t;
+}
+
+__global__ void masks_to_layout_fwd_kernel(const float* __restrict__ bbox, const float* __restrict__ masks, int BO, int M,
+                                           int S, float* __restrict__ out) {
+  const long long total = 1LL * BO * S * S;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int x = static_cast<int>(i % S);
+    const int y = static_cast<int>((i / S) % S);
+    const int bo = static_cast<int>(i / (1LL * S * S));
+    const GridTaps t = grid_taps(bbox + bo * 4, x, y, S, M);
+    const float* m = masks + 1LL * bo * M * M;
+    float v = 0.f;
+    const bool xin0 = t.x0 >= 0 && t.x0 < M, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < M;
+    const bool yin0 = t.y0 >= 0 && t.y0 < M, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < M;
+    if (yin0 && xin0) v += __ldg(m + t.y0 * M + t.x0) * t.nw;
+    if (yin0 && xin1) v += __ldg(m + t.y0 * M + t.x0 + 1) * t.ne;
+    if (yin1 && xin0) v += __ldg(m + (t.y0 + 1) * M + t.x0) * t.sw;
+    if (yin1 && xin1) v += __ldg(m + (t.y0 + 1) * M + t.x0 + 1) * t.se;
+    out[i] = v;
+  }
+}
+
+// one block per (b,o): scatter into a shared M x M tile, then store
+__global__ void masks_to_layout_bwd_kernel(const float* __restrict__ bbox, const float* __restrict__ dout, int M, int S,
+                                           float* __restrict__ dmasks) {
+  extern __shared__ float tile[];
+  const int bo = blockIdx.x;
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x) tile[i] = 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
+    const int x = i % S, y = i / S;
+    const GridTaps t = grid_taps(bbox + bo * 4, x, y, S, M);
+    const float g = __ldg(dout + 1LL * bo * S * S + i);
+    const bool xin0 = t.x0 >= 0 && t.x0 < M, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < M;
+    const bool yin0 = t.y0 >= 0 && t.y0 < M, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < M;
+    if (yin0 && xin0) atomicAdd(tile + t.y0 * M + t.x0, g * t.nw);
+    if (yin0 && xin1) atomicAdd(tile + t.y0 * M + t.x0 + 1, g * t.ne);
+    if (yin1 && xin0) atomicAdd(tile + (t.y0 + 1) * M + t.x0, g * t.sw);
+    if (yin1 && xin1) atomicAdd(tile + (t.y0 + 1) * M + t.x0 + 1, g * t.se);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x) dmasks[1LL * bo * M * M + i] = tile[i];
+}
+
+int masks_to_layout_fwd(const float* bbox, const float* masks, int BO, int M, int S, float* out, cudaStream_t stream) {
+  if (!bbox || !masks || !out || BO <= 0 || M <= 0 || S < 2) { set_error("masks_to_layout_fwd: bad arguments"); return L2I_ERR_BAD_ARG; }
+  const long long total = 1LL * BO * S * S;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  masks_to_layout_fwd_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(bbox, masks, BO, M, S, out);
+  return check_launch("masks_to_layout_fwd_kernel");
+}
+int masks_to_layout_bwd(const float* bbox, const float* dout, int BO, int M, int S, float* dmasks, cudaStream_t stream) {
+  if (!bbox || !dout || !dmasks || BO <= 0 || M <= 0 || M > 64 || S < 2) { set_error("masks_to_layout_bwd: bad arguments"); return L2I_ERR_BAD_ARG; }
+  masks_to_layout_bwd_kernel<<<BO, 256, sizeof(float) * M * M, stream>>>(bbox, dout, M, S, dmasks);
+  return check_launch("masks_to_layout_bwd_kernel");
+}
+
+// ------------------------------------------------------------------------------------------ bilinear resize
+// torch upsample_bilinear2d, align_corners=False: src = max(scale*(dst+0.5)-0.5, 0), scale = in/out
+struct Lin1 { int i0, i1; float l0, l1; };
+__device__ __forceinline__ Lin1 lin_src(int dst, int in, int out) {
+  const float scale = static_cast<float>(in) / static_cast<float>(out);
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  Lin1 r;
+  r.i0 = static_cast<int>(src);
+  if (r.i0 > in - 1) r.i0 = in - 1;
+  r.i1 = r.i0 + ((r.i0 < in - 1) ? 1 : 0);
+  r.l1 = src - static_cast<float>(r.i0);
+  r.l0 = 1.0f - r.l1;
+  return r;
+}
+
+// in (B,O,hi,wi) -> out (B,O,h,w) [pixel_major = 0] or (B,h,w,O) [pixel_major = 1]
+__global__ void mask_resize_fwd_kernel(const float* __restrict__ in, int B, int O, int hi, int wi, int h, int w,
+                                       int pixel_major, float* __restrict__ out) {
+  const long long total = 1LL * B * O * h * w;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    int b, o, y, x;
+    if (pixel_major) {
+      o = static_cast<int>(i % O); x = static_cast<int>((i / O) % w); y = static_cast<int>((i / (1LL * O * w)) % h);
+      b = static_cast<int>(i / (1LL * O * w * h));
+    } else {
+      x = static_cast<int>(i % w); y = static_cast<int>((i / w) % h); o = static_cast<int>((i / (1LL * w * h)) % O);
+      b = static_cast<int>(i / (1LL * w * h * O));
+    }
+    const float* src = in + (1LL * b * O + o) * hi * wi;
+    float v;
+    if (hi == h && wi == w) {
+      v = __ldg(src + y * wi + x);
+    } else {
+      const Lin1 ly = lin_src(y, hi, h), lx = lin_src(x, wi, w);
+      v = ly.l0 * (lx.l0 * __ldg(src + ly.i0 * wi + lx.i0) + lx.l1 * __ldg(src + ly.i0 * wi + lx.i1)) +
+          ly.l1 * (lx.l0 * __ldg(src + ly.i1 * wi + lx.i0) + lx.l1 * __ldg(src + ly.i1 * wi + lx.i1));
+    }
+    out[i] = v;
+  }
+}
+
+// weight with which output index j reads input index i along one axis (0 if it does not)
+__device__ __forceinline__ float lin_weight(int j, int i, int in, int out) {
+  const Lin1 l = lin_src(j, in, out);
+  float wgt = 0.f;
+  if (l.i0 == i) wgt += l.l0;
+  if (l.i1 == i) wgt += l.l1;
+  return wgt;
+}
+
+// gather-form backward (fixed summation order): thread <-> one input pixel (b,o,yi,xi)
+__global__ void mask_resize_bwd_kernel(const float* __restrict__ dout, int B, int O, int hi, int wi, int h, int w,
+                                       int pixel_major, float* __restrict__ din) {
+  const long long total = 1LL * B * O * hi * wi;
+  const float ry = static_cast<float>(h) / static_cast<float>(hi), rx = static_cast<float>(w) / static_cast<float>(wi);
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int xi = static_cast<int>(i % wi), yi = static_cast<int>((i / wi) % hi);
+    const int o = static_cast<int>((i / (1LL * wi * hi)) % O), b = static_cast<int>(i / (1LL * wi * hi * O));
+    float acc = 0.f;
+    if (hi == h && wi == w) {
+      acc = pixel_major ? __ldg(dout + ((1LL * b * h + yi) * w + xi) * O + o) : __ldg(dout + ((1LL * b * O + o) * h + yi) * w + xi);
+    } else {
+      // outputs whose source coordinate lies within (i-1, i+1); edge inputs also collect the clamped range
+      int jy0 = static_cast<int>(floorf((yi - 1.0f + 0.5f) * ry - 0.5f)) - 1, jy1 = static_cast<int>(ceilf((yi + 1.0f + 0.5f) * ry - 0.5f)) + 1;
+      int jx0 = static_cast<int>(floorf((xi - 1.0f + 0.5f) * rx - 0.5f)) - 1, jx1 = static_cast<int>(ceilf((xi + 1.0f + 0.5f) * rx - 0.5f)) + 1;
+      if (yi == 0) jy0 = 0;
+      if (yi == hi - 1) jy1 = h - 1;
+      if (xi == 0) jx0 = 0;
+      if (xi == wi - 1) jx1 = w - 1;
+      jy0 = max(jy0, 0); jy1 = min(jy1, h - 1); jx0 = max(jx0, 0); jx1 = min(jx1, w - 1);
+      for (int jy = jy0; jy <= jy1; ++jy) {
+        const float wy = lin_weight(jy, yi, hi, h);
+        if (wy == 0.f) continue;
+        float row = 0.f;
+        for (int jx = jx0; jx <= jx1; ++jx) {
+          const float wx = lin_weight(jx, xi, wi, w);
+          if (wx == 0.f) continue;
+          const float g = pixel_major ? __ldg(dout + ((1LL * b * h + jy) * w + jx) * O + o)
+                                      : __ldg(dout + ((1LL * b * O + o) * h + jy) * w + jx);
+          row += wx * g;
+        }
+        acc += wy * row;
+      }
+    }
+    din[i] = acc;
+  }
+}
+
+int mask_resize_fwd(const float* in, int B, int O, int hi, int wi, int h, int w, int pixel_major, float* out,
+                    cudaStream_t stream) {
+  if (!in || !out || B <= 0 || O <= 0 || hi <= 0 || wi <= 0 || h <= 0 || w <= 0) { set_error("mask_resize_fwd: bad arguments"); return L2I_ERR_BAD_ARG; }
+  const long long total = 1LL * B * O * h * w;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  mask_resize_fwd_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(in, B, O, hi, wi, h, w, pixel_major, out);
+  return check_launch("mask_resize_fwd_kernel");
+}
+int mask_resize_bwd(const float* dout, int B, int O, int hi, int wi, int h, int w, int pixel_major, float* din,
+                    cudaStream_t stream) {
+  if (!dout || !din || B <= 0 || O <= 0 || hi <= 0 || wi <= 0 || h <= 0 || w <= 0) { set_error("mask_resize_bwd: bad arguments"); return L2I_ERR_BAD_ARG; }
+  const long long total = 1LL * B * O * hi * wi;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  mask_resize_bwd_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(dout, B, O, hi, wi, h, w, pixel_major, din);
+  return check_launch("mask_resize_bwd_kernel");
+}
+
+// ------------------------------------------------------------------------------------------ stage_mask_mix
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// stage (B,h,w,NC) NHWC conv output; y (B,O); alpha (NC); bmask, hard (B,O,S,S); out (B,O,h,w)
+__global__ void stage_mix_fwd_kernel(const float* __restrict__ stage, const long long* __restrict__ y,
+                                     const float* __restrict__ alpha, const float* __restrict__ bmask,
+                                     const float* __restrict__ hard, int B, int O, int h, int w, int NC, int S,
+                                     float* __restrict__ out) {
+  const long long total = 1LL * B * O * h * w;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int x = static_cast<int>(i % w), py = static_cast<int>((i / w) % h);
+    const int o = static_cast<int>((i / (1LL * w * h)) % O), b = static_cast<int>(i / (1LL * w * h * O));
+    const int cls = static_cast<int>(__ldg(y + b * O + o));
+    const float sel = __ldg(stage + ((1LL * b * h + py) * w + x) * NC + cls);
+    // nearest: src = min(floor(dst * (S / h)), S - 1)
+    const int sy = min(static_cast<int>(floorf(py * (static_cast<float>(S) / h))), S - 1);
+    const int sx = min(static_cast<int>(floorf(x * (static_cast<float>(S) / w))), S - 1);
+    const float* bm = bmask + (1LL * b * O + o) * S * S;
+    const float hd = __ldg(hard + (1LL * b * O + o) * S * S + sy * S + sx);
+    float soft;
+    if (S == h && S == w) {
+      soft = __ldg(bm + py * S + x);
+    } else {
+      const Lin1 ly = lin_src(py, S, h), lx = lin_src(x, S, w);
+      soft = ly.l0 * (lx.l0 * __ldg(bm + ly.i0 * S + lx.i0) + lx.l1 * __ldg(bm + ly.i0 * S + lx.i1)) +
+             ly.l1 * (lx.l0 * __ldg(bm + ly.i1 * S + lx.i0) + lx.l1 * __ldg(bm + ly.i1 * S + lx.i1));
+    }
+    const float a = sigmoidf_(__ldg(alpha + cls));
+    const float seman = sigmoidf_(sel) * hd;
+    out[i] = soft * (1.0f - a) + seman * a;
+  }
+}
+
+// dstage (B,h,w,NC) zero-initialised (atomics: two objects of one image may share a class);
+// dalpha (NC) zero-initialised; dsoft (B,O,h,w) = dout * (1 - a)  (then mask_resize_bwd -> dbmask)
+__global__ void stage_mix_bwd_kernel(const float* __restrict__ stage, const long long* __restrict__ y,
+                                     const float* __restrict__ alpha, const float* __restrict__ bmask,
+                                     const float* __restrict__ hard, const float* __restrict__ dout, int B, int O, int h,
+                                     int w, int NC, int S, float* __restrict__ dstage, float* __restrict__ dalpha,
+                                     float* __restrict__ dsoft) {
+  // one block per (b,o) so that the alpha gradient reduces locally
+  const int bo = blockIdx.x;
+  const int b = bo / O;
+  const int cls = static_cast<int>(__ldg(y + bo));
+  const float a = sigmoidf_(__ldg(alpha + cls));
+  const float* bm = bmask + 1LL * bo * S * S;
+  float da = 0.f;
+  for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+    const int x = i % w, py = i / w;
+    const float g = __ldg(dout + 1LL * bo * h * w + i);
+    const float sel = __ldg(stage + ((1LL * b * h + py) * w + x) * NC + cls);
+    const int sy = min(static_cast<int>(floorf(py * (static_cast<float>(S) / h))), S - 1);
+    const int sx = min(static_cast<int>(floorf(x * (static_cast<float>(S) / w))), S - 1);
+    const float hd = __ldg(hard + 1LL * bo * S * S + sy * S + sx);
+    float soft;
+    if (S == h && S == w) {
+      soft = __ldg(bm + py * S + x);
+    } else {
+      const Lin1 ly = lin_src(py, S, h), lx = lin_src(x, S, w);
+      soft = ly.l0 * (lx.l0 * __ldg(bm + ly.i0 * S + lx.i0) + lx.l1 * __ldg(bm + ly.i0 * S + lx.i1)) +
+             ly.l1 * (lx.l0 * __ldg(bm + ly.i1 * S + lx.i0) + lx.l1 * __ldg(bm + ly.i1 * S + lx.i1));
+    }
+    const float sg = sigmoidf_(sel);
+    const float seman = sg * hd;
+    dsoft[1LL * bo * h * w + i] = g * (1.0f - a);
+    const float dsel = g * a * hd * sg * (1.0f - sg);
+    if (dsel != 0.f) atomicAdd(dstage + ((1LL * b * h + py) * w + x) * NC + cls, dsel);
+    da += g * (seman - soft);
+  }
+  da = warp_sum(da);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = da;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) t += red[k];
+    atomicAdd(dalpha + cls, t * a * (1.0f - a));
+  }
+}
+
+int stage_mix_fwd(const float* stage, const long long* y, const float* alpha, const float* bmask, const float* hard,
+                  int B, int O, int h, int w, int NC, int S, float* out, cudaStream_t stream) {
+  if (!stage || !y || !alpha || !bmask || !hard || !out || B <= 0 || O <= 0 || h <= 0 || w <= 0 || NC <= 0 || S <= 0) { set_error("stage_mix_fwd: bad arguments"); return L2I_ERR_BAD_ARG; }
+  const long long total = 1LL * B * O * h * w;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  stage_mix_fwd_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(stage, y, alpha, bmask, hard, B, O, h, w, NC, S, out);
+  return check_launch("stage_mix_fwd_kernel");
+}
+int stage_mix_bwd(const float* stage, const long long* y, const float* alpha, const float* bmask, const float* hard,
+                  const float* dout, int B, int O, int h, int w, int NC, int S, float* dstage, float* dalpha,
+                  float* dsoft, cudaStream_t stream) {
+  if (!stage || !y || !alpha || !bmask || !hard || !dout || !dstage || !dalpha || !dsoft || B <= 0 || O <= 0) { set_error("stage_mix_bwd: bad arguments"); return L2I_ERR_BAD_ARG; }
+  stage_mix_bwd_kernel<<<B * O, 256, 0, stream>>>(stage, y, alpha, bmask, hard, dout, B, O, h, w, NC, S, dstage, dalpha, dsoft);
+  return check_launch("stage_mix_bwd_kernel");
+}
+
+}  // namespace l2i

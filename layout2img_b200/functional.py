@@ -1,0 +1,238 @@
+"""torch.autograd.Function wrappers: the only place where the C-ABI kernels meet autograd.
+
+Each Function's forward/backward is a short sequence of libl2i.so launches (ops.py) plus views;
+the formulas are in the kernels' headers.  Activations are contiguous fp32 (N,H,W,C) tensors.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _c(t):
+    return t if t is None or t.is_contiguous() else t.contiguous()
+
+
+def _dw_to_torch(dw, cout, cin, taps):
+    k = 3 if taps == 9 else 1
+    return dw.view(cout, k, k, cin).permute(0, 3, 1, 2)
+
+
+def _sum2x2(t):
+    n, h2, w2, c = t.shape
+    return t.view(n, h2 // 2, 2, w2 // 2, 2, c).sum(dim=(2, 4))
+
+
+class ConvFn(torch.autograd.Function):
+    """y = conv(up2?(relu?(x)), W) + bias + residual   (3x3 pad 1 or 1x1, stride 1).
+    reference: conv2d() helpers, resnet_generator_app_v2.py:681-686, rcnn_discriminator_app.py:10-15."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, relu_in, up2_in, res_up2):
+        x = _c(x)
+        cout, cin, kh, kw = weight.shape
+        taps = kh * kw
+        xp = ops.act_split(x, relu=relu_in, up2=up2_in)
+        wp = ops.conv_weight_prep(_c(weight), need_dgrad=ctx.needs_input_grad[0])
+        out, _ = ops.conv2d_fwd(xp, wp.f_hi, wp.f_lo, cout, taps, bias=_c(bias), residual=_c(residual), res_up2=res_up2)
+        ctx.save_for_backward(x if relu_in else None, xp.hi, xp.lo, wp.d_hi, wp.d_lo)
+        ctx.meta = (cout, cin, taps, relu_in, up2_in, res_up2, bias is not None, residual is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, xhi, xlo, dhi, dlo = ctx.saved_tensors
+        cout, cin, taps, relu_in, up2_in, res_up2, has_bias, has_res = ctx.meta
+        dout = _c(dout)
+        dyp = ops.act_split(dout)
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            dx, _ = ops.conv2d_fwd(dyp, dhi, dlo, cin, taps)
+            if up2_in:
+                dx = _sum2x2(dx)
+            if relu_in:
+                dx = dx * (x > 0)
+        if ctx.needs_input_grad[1]:
+            dw = _dw_to_torch(ops.conv2d_wgrad(dyp, ops.Pair(xhi, xlo, cin), taps), cout, cin, taps)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = dout.sum(dim=(0, 1, 2))
+        if has_res and ctx.needs_input_grad[3]:
+            dres = _sum2x2(dout) if res_up2 else dout
+        return dx, dw, db, dres, None, None, None
+
+
+def conv2d(x, weight, bias=None, residual=None, relu_in=False, up2_in=False, res_up2=False):
+    return ConvFn.apply(x, weight, bias, residual, relu_in, up2_in, res_up2)
+
+
+class NormConvFn(torch.autograd.Function):
+    """y = conv(up2?(relu(norm(x))), W) + bias + residual with norm = ISLA (mask_pm given) or affine/plain
+    batch norm (mask_pm None).  reference: ResBlock.residual resnet_generator_app_v2.py:653-663,
+    SpatialAdaptiveSynBatchNorm2d norm_module.py:163-186, `final` :416-419, mask heads :645-651."""
+
+    @staticmethod
+    def forward(ctx, x, mask_pm, gamma, beta, aff_w, aff_b, weight, bias, residual, running_mean, running_var,
+                training, momentum, eps, up2, res_up2):
+        x = _c(x)
+        cout, cin, kh, kw = weight.shape
+        taps = kh * kw
+        if training:
+            mi = ops.bn_batch_stats(x, running_mean, running_var, eps, momentum)
+        else:
+            mi = ops.bn_eval_stats(running_mean, running_var, eps)
+        mask_pm, gamma, beta = _c(mask_pm), _c(gamma), _c(beta)
+        _, ap = ops.isla_fwd(x, mi, mask_pm, gamma, beta, _c(aff_w), _c(aff_b), relu=True, up2=up2)
+        wp = ops.conv_weight_prep(_c(weight), need_dgrad=True)
+        out, _ = ops.conv2d_fwd(ap, wp.f_hi, wp.f_lo, cout, taps, bias=_c(bias), residual=_c(residual), res_up2=res_up2)
+        ctx.save_for_backward(x, mi, mask_pm, gamma, beta, aff_w, aff_b, ap.hi, ap.lo, wp.d_hi, wp.d_lo)
+        ctx.meta = (cout, cin, taps, training, up2, res_up2, bias is not None, residual is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, mi, mask_pm, gamma, beta, aff_w, aff_b, ahi, alo, dhi, dlo = ctx.saved_tensors
+        cout, cin, taps, training, up2, res_up2, has_bias, has_res = ctx.meta
+        dout = _c(dout)
+        dyp = ops.act_split(dout)
+        da, _ = ops.conv2d_fwd(dyp, dhi, dlo, cin, taps)
+        dw = _dw_to_torch(ops.conv2d_wgrad(dyp, ops.Pair(ahi, alo, cin), taps), cout, cin, taps)
+        dx, dmask, dgamma, dbeta, csum = ops.isla_bwd(x, mi, mask_pm, gamma, beta, _c(aff_w), _c(aff_b), da,
+                                                      relu=True, up2=up2, train=training)
+        daw = dab = None
+        if aff_w is not None:
+            daw = csum[:, 1].float()
+            dab = csum[:, 0].float()
+        db = dout.sum(dim=(0, 1, 2)) if has_bias else None
+        dres = None
+        if has_res:
+            dres = _sum2x2(dout) if res_up2 else dout
+        return dx, dmask, dgamma, dbeta, daw, dab, dw, db, dres, None, None, None, None, None, None, None
+
+
+def norm_conv(x, weight, bias, running_mean, running_var, training, mask_pm=None, gamma=None, beta=None,
+              aff_w=None, aff_b=None, residual=None, up2=False, res_up2=False, momentum=0.1, eps=1e-5):
+    return NormConvFn.apply(x, mask_pm, gamma, beta, aff_w, aff_b, weight, bias, residual, running_mean, running_var,
+                            training, momentum, eps, up2, res_up2)
+
+
+class AvgPool2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.avgpool2_fwd(_c(x))
+
+    @staticmethod
+    def backward(ctx, dout):
+        return ops.avgpool2_bwd(_c(dout))
+
+
+def avgpool2(x):
+    return AvgPool2Fn.apply(x)
+
+
+class RoiAlignFn(torch.autograd.Function):
+    """torchvision.ops.RoIAlign((8,8), scale, 0) on NHWC features (rcnn_discriminator_app.py:139,143)."""
+
+    @staticmethod
+    def forward(ctx, feat, rois, scale):
+        feat = _c(feat)
+        rois = _c(rois.float())
+        ctx.save_for_backward(rois)
+        ctx.meta = (scale, tuple(feat.shape))
+        return ops.roi_align_fwd(feat, rois, scale)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (rois,) = ctx.saved_tensors
+        scale, shape = ctx.meta
+        return ops.roi_align_bwd(_c(dout), rois, scale, shape), None, None
+
+
+def roi_align(feat, rois, scale):
+    return RoiAlignFn.apply(feat, rois, scale)
+
+
+class MasksToLayoutFn(torch.autograd.Function):
+    """utils/bilinear.py:137-158 (grid_sample paste of per-object masks into the layout map)."""
+
+    @staticmethod
+    def forward(ctx, masks, bbox, size):
+        masks, bbox = _c(masks), _c(bbox)
+        ctx.save_for_backward(bbox)
+        ctx.m = masks.shape[-1]
+        return ops.masks_to_layout_fwd(bbox, masks, size)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (bbox,) = ctx.saved_tensors
+        return ops.masks_to_layout_bwd(bbox, _c(dout), ctx.m), None, None
+
+
+def masks_to_layout(masks, bbox, size):
+    return MasksToLayoutFn.apply(masks, bbox, size)
+
+
+class MaskResizeFn(torch.autograd.Function):
+    """F.interpolate(mask, size=(h,w), mode='bilinear') of norm_module.py:176, optionally emitting the
+    pixel-major (B,h,w,O) layout the ISLA kernels read."""
+
+    @staticmethod
+    def forward(ctx, mask, h, w, pixel_major):
+        mask = _c(mask)
+        ctx.meta = (mask.shape[2], mask.shape[3], pixel_major)
+        return ops.mask_resize_fwd(mask, h, w, pixel_major)
+
+    @staticmethod
+    def backward(ctx, dout):
+        hi, wi, pm = ctx.meta
+        return ops.mask_resize_bwd(_c(dout), hi, wi, pm), None, None, None
+
+
+def mask_resize(mask, h, w, pixel_major=True):
+    return MaskResizeFn.apply(mask, h, w, pixel_major)
+
+
+class StageMixFn(torch.autograd.Function):
+    """resnet_generator_app_v2.py:466-470: stage_bbox = bilinear(bmask)*(1-a) + sigmoid(gather(stage_mask,y))*nearest(hard)*a."""
+
+    @staticmethod
+    def forward(ctx, stage, alpha, bmask, y, hard):
+        stage, bmask = _c(stage), _c(bmask)
+        alpha_flat = _c(alpha.reshape(-1))
+        ctx.save_for_backward(stage, alpha_flat, bmask, y, hard)
+        ctx.alpha_shape = alpha.shape
+        return ops.stage_mix_fwd(stage, y, alpha_flat, bmask, hard)
+
+    @staticmethod
+    def backward(ctx, dout):
+        stage, alpha_flat, bmask, y, hard = ctx.saved_tensors
+        dstage, dalpha, dsoft = ops.stage_mix_bwd(stage, y, alpha_flat, bmask, hard, _c(dout))
+        dbmask = ops.mask_resize_bwd(dsoft, bmask.shape[2], bmask.shape[3], False)
+        return dstage, dalpha.view(ctx.alpha_shape), dbmask, None, None
+
+
+def stage_mix(stage, alpha, bmask, y, hard):
+    return StageMixFn.apply(stage, alpha, bmask, y, hard)
+
+
+class BoxAttentionFn(torch.autograd.Function):
+    """box_attention + relational embedding + WGs gate (resnet_generator_app_v2.py:17-120,172-192)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, bbox, y, wg_w, wg_b):
+        q, k, v, bbox = _c(q), _c(k), _c(v), _c(bbox)
+        wg = _c(wg_w.reshape(-1))
+        out, p, glin = ops.box_attention_fwd(q, k, v, bbox, y, wg, _c(wg_b))
+        ctx.save_for_backward(q, k, v, bbox, y, p, glin)
+        ctx.wshape = wg_w.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, bbox, y, p, glin = ctx.saved_tensors
+        dq, dk, dv, dwg, dbg = ops.box_attention_bwd(q, k, v, bbox, y, p, glin, _c(dout))
+        return dq, dk, dv, None, None, dwg.view(ctx.wshape), dbg
+
+
+def box_attention(q, k, v, bbox, y, wg_w, wg_b):
+    return BoxAttentionFn.apply(q, k, v, bbox, y, wg_w, wg_b)

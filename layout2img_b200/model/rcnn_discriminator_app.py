@@ -1,0 +1,148 @@
+"""Drop-in for the reference's model/rcnn_discriminator_app.py (classes CombineDiscriminator128_app,
+ResnetDiscriminator128_app, OptimizedBlock, ResBlock; helper conv2d).  Same constructors, forward
+signatures and state_dict keys; arithmetic in libl2i.so (sm_100a)."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import functional as L
+from .layers import avg_pool2, conv2d, fire_param_hooks, to_nhwc
+
+__all__ = ["CombineDiscriminator128_app", "ResnetDiscriminator128_app", "OptimizedBlock", "ResBlock", "conv2d"]
+
+
+class OptimizedBlock(nn.Module):
+    """reference :294-314: pool(conv2(relu(conv1 x))) + c_sc(pool x)."""
+
+    def __init__(self, in_ch, out_ch, ksize=3, pad=1, downsample=False):
+        super().__init__()
+        self.conv1 = conv2d(in_ch, out_ch, ksize, 1, pad)
+        self.conv2 = conv2d(out_ch, out_ch, ksize, 1, pad)
+        self.c_sc = conv2d(in_ch, out_ch, 1, 1, 0)
+        self.activation = nn.ReLU()
+        self.downsample = downsample
+
+    def forward(self, in_feat):                      # NHWC
+        x = self.conv1(in_feat)
+        x = self.conv2(x, relu_in=True)
+        if self.downsample:
+            x = avg_pool2(x)
+            return self.c_sc(avg_pool2(in_feat), residual=x)
+        return self.c_sc(in_feat, residual=x)
+
+
+class ResBlock(nn.Module):
+    """reference :317-344: pool?(conv2(relu(conv1(relu x)))) + pool?(c_sc x).  Average pooling is
+    linear, so the shortcut is added in conv2's epilogue and the sum is pooled once."""
+
+    def __init__(self, in_ch, out_ch, ksize=3, pad=1, downsample=False):
+        super().__init__()
+        self.conv1 = conv2d(in_ch, out_ch, ksize, 1, pad)
+        self.conv2 = conv2d(out_ch, out_ch, ksize, 1, pad)
+        self.activation = nn.ReLU()
+        self.downsample = downsample
+        self.learnable_sc = (in_ch != out_ch) or downsample
+        if self.learnable_sc:
+            self.c_sc = conv2d(in_ch, out_ch, 1, 1, 0)
+
+    def forward(self, in_feat):                      # NHWC
+        x = self.conv1(in_feat, relu_in=True)
+        sc = self.c_sc(in_feat) if self.learnable_sc else in_feat
+        x = self.conv2(x, relu_in=True, residual=sc)
+        if self.downsample:
+            x = avg_pool2(x)
+        return x
+
+
+class ResnetDiscriminator128_app(nn.Module):
+    """reference :84-168."""
+
+    def __init__(self, num_classes=0, input_dim=3, ch=64):
+        super().__init__()
+        self.num_classes = num_classes
+        self.block1 = OptimizedBlock(3, ch, downsample=True)
+        self.block2 = ResBlock(ch, ch * 2, downsample=True)
+        self.block3 = ResBlock(ch * 2, ch * 4, downsample=True)
+        self.block4 = ResBlock(ch * 4, ch * 8, downsample=True)
+        self.block5 = ResBlock(ch * 8, ch * 16, downsample=True)
+        self.block6 = ResBlock(ch * 16, ch * 16, downsample=False)
+        self.l7 = nn.utils.spectral_norm(nn.Linear(ch * 16, 1))
+        self.activation = nn.ReLU()
+        self.block_obj3 = ResBlock(ch * 2, ch * 4, downsample=False)
+        self.block_obj4 = ResBlock(ch * 4, ch * 8, downsample=False)
+        self.block_obj5 = ResBlock(ch * 8, ch * 16, downsample=True)
+        self.l_obj = nn.utils.spectral_norm(nn.Linear(ch * 16, 1))
+        self.l_y = nn.utils.spectral_norm(nn.Embedding(num_classes, ch * 16))
+        self.app_conv = ResBlock(ch * 8, ch * 8, downsample=False)
+        self.l_y_app = nn.utils.spectral_norm(nn.Embedding(num_classes, ch * 8))
+        self.app = nn.utils.spectral_norm(nn.Linear(ch * 16, 1))
+
+    def forward(self, x, y=None, bbox=None):         # x NHWC; bbox (K,5) rois in pixels
+        x = self.block1(x)
+        x1 = self.block2(x)
+        x2 = self.block3(x1)
+        x = self.block4(x2)
+        x = self.block5(x)
+        x = self.block6(x)
+        x = F.relu(x).sum(dim=(1, 2))
+        out_im = self.l7(x)
+
+        # small / large object paths (:131-146); order = all large then all small
+        s_idx = ((bbox[:, 3] - bbox[:, 1]) < 64) * ((bbox[:, 4] - bbox[:, 2]) < 64)
+        bbox_l, bbox_s = bbox[~s_idx], bbox[s_idx]
+        y_l, y_s = y[~s_idx], y[s_idx]
+        obj_feat_s = self.block_obj3(x1)
+        obj_feat_s = self.block_obj4(obj_feat_s)
+        obj_feat_s = L.roi_align(obj_feat_s, bbox_s, 1.0 / 4.0)
+        obj_feat_l = self.block_obj4(x2)
+        obj_feat_l = L.roi_align(obj_feat_l, bbox_l, 1.0 / 8.0)
+        obj_feat = torch.cat([obj_feat_l, obj_feat_s], dim=0)          # (K,8,8,512) NHWC
+        y = torch.cat([y_l, y_s], dim=0)
+
+        # appearance head (:148-157).  mean_i Linear([Gram_i, e_y]) is evaluated without forming the
+        # (K,512,512) Gram matrix or the (K,512,1024) concat:
+        #   sum_i Gram[i,:] . w1 = (1/C) sum_p (sum_i F[i,p]) (sum_j F[j,p] w1[j])
+        app_feat = F.relu(self.app_conv(obj_feat))
+        k_, hh, ww_, c = app_feat.shape
+        feat = app_feat.view(k_, hh * ww_, c)
+        fire_param_hooks(self.app)
+        w1, w2 = self.app.weight[0, :c], self.app.weight[0, c:]
+        colsum = feat.sum(dim=2)                                        # (K, P)
+        proj = feat @ w1                                                # (K, P)
+        app_y = self.l_y_app(y)                                         # (K, C)
+        out_app = ((colsum * proj).sum(dim=1, keepdim=True) / (c * c)
+                   + (app_y @ w2).unsqueeze(1) + self.app.bias)
+
+        # object head (:160-166)
+        obj_feat = self.block_obj5(obj_feat)
+        obj_feat = F.relu(obj_feat).sum(dim=(1, 2))                     # (K,1024)
+        out_obj = self.l_obj(obj_feat)
+        out_obj = out_obj + torch.sum(self.l_y(y) * obj_feat, dim=1, keepdim=True)
+        return out_im, out_obj, out_app
+
+
+class CombineDiscriminator128_app(nn.Module):
+    """reference :396-421.  images (b,3,128,128) NCHW; bbox (b,o,4) xywh in [0,1]; label (b,o[,1])."""
+
+    def __init__(self, num_classes=81):
+        super().__init__()
+        self.obD = ResnetDiscriminator128_app(num_classes=num_classes, input_dim=3)
+
+    def forward(self, images, bbox, label, mask=None):
+        if not images.is_cuda:
+            raise RuntimeError("layout2img_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        dev = images.device
+        b, o = bbox.size(0), bbox.size(1)
+        idx = torch.arange(start=0, end=b, device=dev).view(b, 1, 1).expand(-1, o, -1).float()
+        bbox = bbox.to(dev).float().clone()          # the reference edits a GPU-resident bbox in place (:408-409)
+        bbox[:, :, 2] = bbox[:, :, 2] + bbox[:, :, 0]
+        bbox[:, :, 3] = bbox[:, :, 3] + bbox[:, :, 1]
+        bbox = bbox * images.size(2)
+        bbox = torch.cat((idx, bbox), dim=2).view(-1, 5)
+        label = label.to(dev).view(-1)
+        keep = (label != 0).nonzero().view(-1)
+        bbox = bbox[keep]
+        label = label[keep]
+        return self.obD(to_nhwc(images), label, bbox)

@@ -102,3 +102,189 @@ def conv2d_wgrad(dy: Pair, x: Pair, taps: int) -> torch.Tensor:
     dw = torch.empty((dy.C, taps, x.C), dtype=torch.float32, device=dy.hi.device)
     call("l2i_conv2d_wgrad", n, h, w_, x.C, x.cpad, dy.C, cout_pad, taps, dy.hi, dy.lo, x.hi, x.lo, dw)
     return dw
+
+
+# --------------------------------------------------------------------------------------------
+# batch-norm statistics / ISLA
+# --------------------------------------------------------------------------------------------
+def bn_batch_stats(x: torch.Tensor, running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor],
+                   eps: float, momentum: float) -> torch.Tensor:
+    """x (..., C) fp32 -> mean_invstd (2, C); updates the running statistics in place (train mode)."""
+    _chk(x)
+    c = x.shape[-1]
+    pixels = x.numel() // c
+    sums = torch.empty((c, 2), dtype=torch.float64, device=x.device)
+    call("l2i_bn_stats", x, pixels, c, sums)
+    mi = torch.empty((2, c), dtype=torch.float32, device=x.device)
+    call("l2i_bn_finalize", sums, float(pixels), c, float(eps), float(momentum), running_mean, running_var, mi)
+    return mi
+
+
+def bn_eval_stats(running_mean: torch.Tensor, running_var: torch.Tensor, eps: float) -> torch.Tensor:
+    c = running_mean.numel()
+    mi = torch.empty((2, c), dtype=torch.float32, device=running_mean.device)
+    call("l2i_bn_eval_stats", running_mean, running_var, c, float(eps), mi)
+    return mi
+
+
+def isla_fwd(x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, relu: bool, up2: bool,
+             want_f32: bool = False, want_pair: bool = True):
+    """x (B,H,W,C); mask_pm (B,H,W,O) or None; gamma/beta (B,O,C) -> (fp32 out or None, Pair or None)."""
+    _chk(x)
+    b, h, w, c = x.shape
+    o = 0 if mask_pm is None else mask_pm.shape[-1]
+    out = torch.empty_like(x) if want_f32 else None
+    pair = None
+    if want_pair:
+        s = 2 if up2 else 1
+        buf = torch.empty((2, b, h * s, w * s, pad8(c)), dtype=torch.bfloat16, device=x.device)
+        pair = Pair(buf[0], buf[1], c)
+    call("l2i_isla_fwd", x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, b, h, w, c, o, out,
+         pair.hi if pair else None, pair.lo if pair else None, pad8(c), int(relu), int(up2))
+    return out, pair
+
+
+def isla_bwd(x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, dout, relu: bool, up2: bool, train: bool):
+    """-> dx (B,H,W,C), dmask_pm (B,H,W,O) | None, dgamma, dbeta (B,O,C) | None, csum (C,2) fp64."""
+    _chk(x); _chk(dout)
+    b, h, w, c = x.shape
+    o = 0 if mask_pm is None else mask_pm.shape[-1]
+    gbuf = torch.empty_like(x)
+    dx = torch.empty_like(x)
+    csum = torch.empty((c, 2), dtype=torch.float64, device=x.device)
+    dmask = torch.empty_like(mask_pm) if o else None
+    dgamma = torch.empty_like(gamma) if o else None
+    dbeta = torch.empty_like(beta) if o else None
+    call("l2i_isla_bwd", x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, dout, b, h, w, c, o, int(relu), int(up2),
+         int(train), gbuf, dmask, dgamma, dbeta, csum, dx)
+    return dx, dmask, dgamma, dbeta, csum
+
+
+# --------------------------------------------------------------------------------------------
+# layout maps
+# --------------------------------------------------------------------------------------------
+def bbox_mask(bbox: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    _chk(bbox)
+    b, o, _ = bbox.shape
+    out = torch.empty((b, o, H, W), dtype=torch.float32, device=bbox.device)
+    call("l2i_bbox_mask", bbox, b * o, H, W, out)
+    return out
+
+
+def masks_to_layout_fwd(bbox, masks, size: int):
+    _chk(bbox); _chk(masks)
+    b, o, m, m2 = masks.shape
+    assert masks.shape == (b, o, m, m)          # reference utils/bilinear.py:149
+    out = torch.empty((b, o, size, size), dtype=torch.float32, device=masks.device)
+    call("l2i_masks_to_layout_fwd", bbox, masks, b * o, m, size, out)
+    return out
+
+
+def masks_to_layout_bwd(bbox, dout, m: int):
+    _chk(dout)
+    b, o, s, _ = dout.shape
+    dm = torch.empty((b, o, m, m), dtype=torch.float32, device=dout.device)
+    call("l2i_masks_to_layout_bwd", bbox, dout, b * o, m, s, dm)
+    return dm
+
+
+def mask_resize_fwd(mask, h: int, w: int, pixel_major: bool):
+    _chk(mask)
+    b, o, hi, wi = mask.shape
+    out = torch.empty((b, h, w, o) if pixel_major else (b, o, h, w), dtype=torch.float32, device=mask.device)
+    call("l2i_mask_resize_fwd", mask, b, o, hi, wi, h, w, int(pixel_major), out)
+    return out
+
+
+def mask_resize_bwd(dout, hi: int, wi: int, pixel_major: bool):
+    _chk(dout)
+    if pixel_major:
+        b, h, w, o = dout.shape
+    else:
+        b, o, h, w = dout.shape
+    din = torch.empty((b, o, hi, wi), dtype=torch.float32, device=dout.device)
+    call("l2i_mask_resize_bwd", dout, b, o, hi, wi, h, w, int(pixel_major), din)
+    return din
+
+
+def stage_mix_fwd(stage, y, alpha, bmask, hard):
+    _chk(stage); _chk(bmask); _chk(hard); _chk(alpha); _chk(y, torch.int64)
+    b, h, w, nc = stage.shape
+    o, s = bmask.shape[1], bmask.shape[2]
+    out = torch.empty((b, o, h, w), dtype=torch.float32, device=stage.device)
+    call("l2i_stage_mix_fwd", stage, y, alpha, bmask, hard, b, o, h, w, nc, s, out)
+    return out
+
+
+def stage_mix_bwd(stage, y, alpha, bmask, hard, dout):
+    _chk(dout)
+    b, h, w, nc = stage.shape
+    o, s = bmask.shape[1], bmask.shape[2]
+    dstage = torch.zeros_like(stage)
+    dalpha = torch.zeros_like(alpha)
+    dsoft = torch.empty_like(dout)
+    call("l2i_stage_mix_bwd", stage, y, alpha, bmask, hard, dout, b, o, h, w, nc, s, dstage, dalpha, dsoft)
+    return dstage, dalpha, dsoft
+
+
+# --------------------------------------------------------------------------------------------
+# ROIAlign / pooling
+# --------------------------------------------------------------------------------------------
+def roi_align_fwd(feat, rois, scale: float, P: int = 8):
+    _chk(feat)
+    n, h, w, c = feat.shape
+    k = rois.shape[0]
+    out = torch.empty((k, P, P, c), dtype=torch.float32, device=feat.device)
+    if k:
+        _chk(rois)
+        call("l2i_roi_align_fwd", feat, rois, k, n, h, w, c, P, float(scale), out)
+    return out
+
+
+def roi_align_bwd(dout, rois, scale: float, shape, P: int = 8):
+    n, h, w, c = shape
+    k = rois.shape[0]
+    dfeat = torch.empty(shape, dtype=torch.float32, device=dout.device)
+    call("l2i_roi_align_bwd", _chk(dout) if k else None, rois if k else None, k, n, h, w, c, P, float(scale), dfeat)
+    return dfeat
+
+
+def avgpool2_fwd(x):
+    _chk(x)
+    n, h, w, c = x.shape
+    out = torch.empty((n, h // 2, w // 2, c), dtype=torch.float32, device=x.device)
+    call("l2i_avgpool2_fwd", x, n, h, w, c, out)
+    return out
+
+
+def avgpool2_bwd(dout):
+    _chk(dout)
+    n, ho, wo, c = dout.shape
+    dx = torch.empty((n, ho * 2, wo * 2, c), dtype=torch.float32, device=dout.device)
+    call("l2i_avgpool2_bwd", dout, n, ho * 2, wo * 2, c, dx)
+    return dx
+
+
+# --------------------------------------------------------------------------------------------
+# object-context attention
+# --------------------------------------------------------------------------------------------
+def box_attention_fwd(q, k, v, bbox, y, wg, bg):
+    for t in (q, k, v, bbox, wg, bg):
+        _chk(t)
+    _chk(y, torch.int64)
+    b, o, d = q.shape
+    out = torch.empty_like(q)
+    p = torch.empty((b, o, o), dtype=torch.float32, device=q.device)
+    glin = torch.empty((b, o, o), dtype=torch.float32, device=q.device)
+    call("l2i_box_attention_fwd", q, k, v, bbox, y, wg, bg, b, o, d, out, p, glin)
+    return out, p, glin
+
+
+def box_attention_bwd(q, k, v, bbox, y, p, glin, dout):
+    _chk(dout)
+    b, o, d = q.shape
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    dwg = torch.empty((64,), dtype=torch.float32, device=q.device)
+    dbg = torch.empty((1,), dtype=torch.float32, device=q.device)
+    call("l2i_box_attention_bwd", q, k, v, bbox, y, p, glin, dout, b, o, d, dq, dk, dv, dwg, dbg)
+    return dq, dk, dv, dwg, dbg

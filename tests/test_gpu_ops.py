@@ -1,0 +1,317 @@
+"""Per-operator parity on the B200: every libl2i.so kernel against the oracle's restatement of the
+same reference lines (CPU, fp32/fp64) or torch autograd of that restatement.  All calls go through
+the C ABI (layout2img_b200.ops -> ctypes -> libl2i.so)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_case
+from layout2img_b200.synth import synthetic_layout
+from oracle import l2i_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-3, 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def close(got, want, rtol=RTOL, atol=ATOL, what=""):
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    err = (got - want).abs()
+    tol = atol + rtol * want.abs()
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} outside tol, max err {err.max().item():.3e} (ref max {want.abs().max().item():.3e})"
+
+
+CONV_SHAPES = [  # N, Cin, Cout, H, k   (small instances of every channel/tiling class of SURVEY.md App. A)
+    (2, 64, 64, 16, 3), (2, 64, 128, 16, 1), (3, 128, 128, 8, 3), (5, 256, 256, 4, 3), (2, 3, 64, 32, 3),
+    (2, 64, 3, 32, 3), (2, 256, 100, 16, 3), (1, 528, 100, 16, 3), (2, 100, 184, 8, 1), (7, 512, 1024, 8, 3),
+    (2, 256, 1, 16, 1), (2, 128, 64, 64, 3),
+]
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,k", CONV_SHAPES)
+def test_conv_fwd_dgrad_wgrad(dev, N, Cin, Cout, H, k):
+    from layout2img_b200 import functional as L
+    g = torch.Generator().manual_seed(N * 1000 + Cin + Cout + H)
+    x = torch.randn(N, Cin, H, H, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    dy = torch.randn(N, Cout, H, H, generator=g)
+    xr, wr, br = x.double().requires_grad_(), w.double().requires_grad_(), b.double().requires_grad_()
+    ref = F.conv2d(xr, wr, br, padding=k // 2)
+    ref.backward(dy.double())
+    xg = nhwc(x).to(dev).requires_grad_()
+    wg = w.to(dev).requires_grad_()
+    bg = b.to(dev).requires_grad_()
+    out = L.conv2d(xg, wg, bg)
+    out.backward(nhwc(dy).to(dev))
+    scale = ref.abs().max().item()
+    close(out.permute(0, 3, 1, 2), ref, 1e-3, 1e-4 * max(scale, 1), "fwd")
+    close(xg.grad.permute(0, 3, 1, 2), xr.grad, 1e-3, 1e-4 * max(xr.grad.abs().max().item(), 1), "dgrad")
+    close(wg.grad, wr.grad, 1e-3, 2e-4 * max(wr.grad.abs().max().item(), 1), "wgrad")
+    close(bg.grad, br.grad, 1e-3, 1e-4 * max(br.grad.abs().max().item(), 1), "dbias")
+
+
+def test_conv_prologue_epilogue_fusions(dev):
+    """relu-in, nearest-x2-in, residual (same and half resolution) == the unfused composition."""
+    from layout2img_b200 import functional as L
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 64, 8, 8, generator=g)
+    w = torch.randn(128, 64, 3, 3, generator=g) / 24
+    r_lo = torch.randn(2, 128, 8, 8, generator=g)
+    xr, wr, rr = x.double().requires_grad_(), w.double().requires_grad_(), r_lo.double().requires_grad_()
+    ref = F.conv2d(F.interpolate(F.relu(xr), scale_factor=2, mode="nearest"), wr, None, padding=1) + \
+        F.interpolate(rr, scale_factor=2, mode="nearest")
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy.double())
+    xg, wg, rg = nhwc(x).to(dev).requires_grad_(), w.to(dev).requires_grad_(), nhwc(r_lo).to(dev).requires_grad_()
+    out = L.conv2d(xg, wg, None, rg, relu_in=True, up2_in=True, res_up2=True)
+    out.backward(nhwc(dy).to(dev))
+    close(out.permute(0, 3, 1, 2), ref, what="fwd")
+    close(xg.grad.permute(0, 3, 1, 2), xr.grad, what="dx")
+    close(rg.grad.permute(0, 3, 1, 2), rr.grad, what="dres")
+    close(wg.grad, wr.grad, 1e-3, 1e-3, what="dw")
+
+
+@pytest.mark.parametrize("name", ["C", "Cpad", "V"])
+def test_bbox_mask_bit_exact_against_reference_golden(dev, name):
+    from layout2img_b200 import ops
+    z, meta = load_case(name)
+    data = synthetic_layout(meta["batch"], meta["num_obj"], meta["num_classes"], seed=meta["seed"], n_pad=meta["n_pad"])
+    for size in (64, 128):
+        got = ops.bbox_mask(data["bbox"].to(dev), size, size).cpu()
+        assert torch.equal(got, O.bbox_mask(data["bbox"], size, size)), "differs from oracle"
+        assert np.array_equal(np.packbits(got.numpy().astype(np.uint8)), z[f"op.bbox_mask{size}"]), "differs from reference golden"
+
+
+@pytest.mark.parametrize("name", ["C", "Cpad", "V"])
+def test_masks_to_layout_fwd_bwd(dev, name):
+    from layout2img_b200 import functional as L
+    z, meta = load_case(name)
+    data = synthetic_layout(meta["batch"], meta["num_obj"], meta["num_classes"], seed=meta["seed"], n_pad=meta["n_pad"])
+    gm = torch.Generator().manual_seed(meta["seed"] + 100)
+    masks = torch.rand(meta["batch"], meta["num_obj"], 16, 16, generator=gm)
+    mr = masks.clone().requires_grad_()
+    ref = O.masks_to_layout(data["bbox"], mr, 64)
+    dy = torch.randn(ref.shape, generator=gm)
+    ref.backward(dy)
+    mg = masks.to(dev).requires_grad_()
+    out = L.masks_to_layout(mg, data["bbox"].to(dev), 64)
+    out.backward(dy.to(dev))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), z["op.masks_to_layout"], rtol=1e-5, atol=1e-5)
+    close(out, ref, 1e-5, 1e-5, "fwd")
+    close(mg.grad, mr.grad, 1e-4, 1e-4, "bwd")
+
+
+@pytest.mark.parametrize("hi,h", [(64, 4), (64, 8), (64, 64), (8, 16), (32, 64), (64, 128)])
+@pytest.mark.parametrize("pm", [True, False])
+def test_mask_resize_fwd_bwd(dev, hi, h, pm):
+    from layout2img_b200 import functional as L
+    g = torch.Generator().manual_seed(hi + h)
+    m = torch.rand(2, 5, hi, hi, generator=g)
+    mr = m.clone().requires_grad_()
+    ref = F.interpolate(mr, size=(h, h), mode="bilinear", align_corners=False) if hi != h else mr * 1.0
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy)
+    mg = m.to(dev).requires_grad_()
+    out = L.mask_resize(mg, h, h, pm)
+    dyg = dy.to(dev)
+    out.backward(dyg.permute(0, 2, 3, 1).contiguous() if pm else dyg)
+    got = out.permute(0, 3, 1, 2) if pm else out
+    close(got, ref, 1e-5, 1e-6, "fwd")
+    close(mg.grad, mr.grad, 1e-4, 1e-5, "bwd")
+
+
+def _isla_ref(x, mask, gamma, beta, rm, rv, training):
+    xh = F.batch_norm(x, rm, rv, None, None, training, 0.1, 1e-5)
+    m = mask.unsqueeze(2)
+    den = mask.sum(1, keepdim=True) + 1e-6
+    g = (m * gamma[..., None, None]).sum(1) / den + 1
+    b = (m * beta[..., None, None]).sum(1) / den
+    return g * xh + b
+
+
+@pytest.mark.parametrize("B,O,C,H,up,training", [(2, 4, 64, 16, True, True), (3, 8, 256, 8, False, True),
+                                                 (2, 16, 128, 4, True, True), (2, 4, 1024, 4, True, False),
+                                                 (2, 31, 64, 8, False, True)])
+def test_isla_norm_relu_conv_fwd_bwd(dev, B, O, C, H, up, training):
+    """Fused ISLA + ReLU (+ nearest x2) + 3x3 conv against the unfused fp64 composition
+    (norm_module.py:163-186 + ResBlock.residual), forward, every gradient and the running stats."""
+    from layout2img_b200 import functional as L
+    g = torch.Generator().manual_seed(B * 100 + O + C)
+    x = torch.randn(B, C, H, H, generator=g) * 1.5 + 0.3
+    mask = torch.rand(B, O, H, H, generator=g) * (torch.rand(B, O, H, H, generator=g) > 0.4)
+    gamma, beta = torch.randn(B, O, C, generator=g) * 0.3, torch.randn(B, O, C, generator=g) * 0.3
+    w = torch.randn(64, C, 3, 3, generator=g) / (3 * C ** 0.5)
+    bias = torch.randn(64, generator=g) * 0.1
+    rm, rv = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    dbl = [t.double().requires_grad_() for t in (x, mask, gamma, beta, w, bias)]
+    rm_r, rv_r = rm.double().clone(), rv.double().clone()
+    a = F.relu(_isla_ref(dbl[0], dbl[1], dbl[2], dbl[3], rm_r, rv_r, training))
+    if up:
+        a = F.interpolate(a, scale_factor=2, mode="nearest")
+    ref = F.conv2d(a, dbl[4], dbl[5], padding=1)
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy.double())
+    xg = nhwc(x).to(dev).requires_grad_()
+    mg = mask.permute(0, 2, 3, 1).contiguous().to(dev).requires_grad_()
+    gg, bg, wg, biasg = [t.to(dev).requires_grad_() for t in (gamma, beta, w, bias)]
+    rmg, rvg = rm.to(dev), rv.to(dev)
+    out = L.norm_conv(xg, wg, biasg, rmg, rvg, training, mask_pm=mg, gamma=gg, beta=bg, up2=up)
+    out.backward(nhwc(dy).to(dev))
+    close(out.permute(0, 3, 1, 2), ref, what="fwd")
+    close(rmg, rm_r, 1e-4, 1e-5, "running_mean")
+    close(rvg, rv_r, 1e-4, 1e-5, "running_var")
+    close(xg.grad.permute(0, 3, 1, 2), dbl[0].grad, 1e-3, 2e-4, "dx")
+    dm = dbl[1].grad
+    close(mg.grad.permute(0, 3, 1, 2), dm, 2e-3, 1e-4 + 1e-5 * dm.abs().max().item(), "dmask")
+    close(gg.grad, dbl[2].grad, 1e-3, 1e-3, "dgamma")
+    close(bg.grad, dbl[3].grad, 1e-3, 1e-3, "dbeta")
+    close(wg.grad, dbl[4].grad, 1e-3, 1e-3, "dw")
+    close(biasg.grad, dbl[5].grad, 1e-3, 1e-3, "dbias")
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_affine_bn_relu_conv(dev, training):
+    """BN(affine) -> ReLU -> conv (final / mask heads, resnet_generator_app_v2.py:416-419,645-651)."""
+    from layout2img_b200 import functional as L
+    g = torch.Generator().manual_seed(9)
+    C = 100
+    x = torch.randn(3, C, 8, 8, generator=g) + 0.2
+    aw, ab = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    w = torch.randn(184, C, 1, 1, generator=g) / 10
+    bias = torch.randn(184, generator=g) * 0.1
+    rm, rv = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    dbl = [t.double().requires_grad_() for t in (x, aw, ab, w, bias)]
+    rm_r, rv_r = rm.double().clone(), rv.double().clone()
+    ref = F.conv2d(F.relu(F.batch_norm(dbl[0], rm_r, rv_r, dbl[1], dbl[2], training, 0.1, 1e-5)), dbl[3], dbl[4])
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy.double())
+    xg = nhwc(x).to(dev).requires_grad_()
+    awg, abg, wg, biasg = [t.to(dev).requires_grad_() for t in (aw, ab, w, bias)]
+    out = L.norm_conv(xg, wg, biasg, rm.to(dev), rv.to(dev), training, aff_w=awg, aff_b=abg)
+    out.backward(nhwc(dy).to(dev))
+    close(out.permute(0, 3, 1, 2), ref, what="fwd")
+    close(xg.grad.permute(0, 3, 1, 2), dbl[0].grad, 1e-3, 2e-4, "dx")
+    close(awg.grad, dbl[1].grad, 1e-3, 1e-3, "daffw")
+    close(abg.grad, dbl[2].grad, 1e-3, 1e-3, "daffb")
+    close(wg.grad, dbl[3].grad, 1e-3, 1e-3, "dw")
+
+
+@pytest.mark.parametrize("name", ["C", "Cpad", "V"])
+def test_stage_mask_mix_fwd_bwd(dev, name):
+    from layout2img_b200 import functional as L
+    z, meta = load_case(name)
+    data = synthetic_layout(meta["batch"], meta["num_obj"], meta["num_classes"], seed=meta["seed"], n_pad=meta["n_pad"])
+    b, o = meta["batch"], meta["num_obj"]
+    g = torch.Generator().manual_seed(3)
+    hard = O.bbox_mask(data["bbox"], 64, 64)
+    bmask = torch.rand(b, o, 64, 64, generator=g)
+    alpha = torch.randn(1, 184, 1, generator=g)
+    for size in (8, 64):
+        stage = torch.randn(b, 184, size, size, generator=g)
+        sr, ar, br = stage.clone().requires_grad_(), alpha.clone().requires_grad_(), bmask.clone().requires_grad_()
+        ref = O.stage_mask_mix({"alpha1": ar}, 1, sr, br, hard, data["label"], size)
+        dy = torch.randn(ref.shape, generator=g)
+        ref.backward(dy)
+        sg = nhwc(stage).to(dev).requires_grad_()
+        ag, bg = alpha.to(dev).requires_grad_(), bmask.to(dev).requires_grad_()
+        out = L.stage_mix(sg, ag, bg, data["label"].to(dev), hard.to(dev))
+        out.backward(dy.to(dev))
+        close(out, ref, 1e-4, 1e-5, "fwd")
+        close(sg.grad.permute(0, 3, 1, 2), sr.grad, 1e-3, 1e-5, "dstage")
+        close(ag.grad, ar.grad, 1e-3, 1e-4, "dalpha")
+        close(bg.grad, br.grad, 1e-3, 1e-5, "dbmask")
+
+
+@pytest.mark.parametrize("name", ["C", "Cpad", "V"])
+def test_box_attention_fwd_bwd(dev, name):
+    """Kernel vs the oracle's restatement of :17-120,172-192 (embedding, gate, masked softmax, PV)."""
+    from layout2img_b200 import functional as L
+    z, meta = load_case(name)
+    data = synthetic_layout(meta["batch"], meta["num_obj"], meta["num_classes"], seed=meta["seed"], n_pad=meta["n_pad"])
+    b, o, d = meta["batch"], meta["num_obj"], 308
+    g = torch.Generator().manual_seed(21)
+    q, k, v = [torch.randn(b, o, d, generator=g) for _ in range(3)]
+    wgw, wgb = torch.randn(1, 64, generator=g) * 0.3, torch.randn(1, generator=g) * 0.1 + 0.5
+    leaves = [t.clone().requires_grad_() for t in (q, k, v, wgw, wgb)]
+    emb = O.box_relational_embedding(data["bbox"])
+    np.testing.assert_allclose(emb.numpy(), z["op.box_rel_emb"], rtol=1e-5, atol=1e-5)
+    geo = F.relu(F.linear(emb.reshape(-1, 64), leaves[3], leaves[4])).view(b, o, o)
+    score = torch.matmul(leaves[0], leaves[1].transpose(-2, -1)) / d ** 0.5
+    score = score.masked_fill(~(data["label"] != 0)[:, None, :].expand(b, o, o), -1e9)
+    ref = torch.matmul(torch.softmax(torch.log(torch.clamp(geo, min=1e-6)) + score, dim=-1), leaves[2])
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy)
+    gl = [t.to(dev).requires_grad_() for t in (q, k, v, wgw, wgb)]
+    out = L.box_attention(gl[0], gl[1], gl[2], data["bbox"].to(dev), data["label"].to(dev), gl[3], gl[4])
+    out.backward(dy.to(dev))
+    close(out, ref, what="fwd")
+    for nm, a, r in zip(("dq", "dk", "dv", "dwg", "dbg"), gl, leaves):
+        close(a.grad, r.grad, 1e-3, 2e-4, nm)
+
+
+@pytest.mark.parametrize("H,scale", [(32, 0.25), (16, 0.125)])
+def test_roi_align_fwd_bwd(dev, H, scale):
+    """vs torchvision.ops.roi_align (the third-party op the reference calls, rcnn_discriminator_app.py:98-99)."""
+    from torchvision.ops import roi_align as tv_roi_align
+    from layout2img_b200 import functional as L
+    data = synthetic_layout(4, 8, 184, seed=4)
+    rois, _ = O.d_rois(data["bbox"], data["label"], 128)
+    # include degenerate / border boxes
+    extra = torch.tensor([[0, 0, 0, 128, 128], [1, 100, 100, 100.5, 100.2], [2, 120, 3, 128, 60], [3, 0, 0, 1, 1]], dtype=torch.float32)
+    rois = torch.cat([rois, extra])
+    g = torch.Generator().manual_seed(8)
+    feat = torch.randn(4, 64, H, H, generator=g)
+    fr = feat.clone().requires_grad_()
+    ref = tv_roi_align(fr, rois, (8, 8), scale, 0, False)
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy)
+    fg = nhwc(feat).to(dev).requires_grad_()
+    out = L.roi_align(fg, rois.to(dev), scale)
+    out.backward(nhwc(dy).to(dev))
+    close(out.permute(0, 3, 1, 2), ref, 1e-4, 1e-5, "fwd")
+    close(fg.grad.permute(0, 3, 1, 2), fr.grad, 1e-4, 1e-4, "bwd")
+
+
+def test_roi_align_empty(dev):
+    from layout2img_b200 import functional as L
+    fg = torch.randn(2, 16, 16, 64, device=dev, requires_grad=True)
+    out = L.roi_align(fg, torch.zeros((0, 5), device=dev), 0.125)
+    assert out.shape == (0, 8, 8, 64)
+    out.sum().backward()
+    assert torch.count_nonzero(fg.grad) == 0
+
+
+def test_avgpool(dev):
+    from layout2img_b200 import functional as L
+    x = torch.randn(2, 64, 16, 16)
+    xr = x.clone().requires_grad_()
+    ref = F.avg_pool2d(xr, 2)
+    dy = torch.randn(ref.shape)
+    ref.backward(dy)
+    xg = nhwc(x).to(dev).requires_grad_()
+    out = L.avgpool2(xg)
+    out.backward(nhwc(dy).to(dev))
+    close(out.permute(0, 3, 1, 2), ref, 1e-6, 1e-6)
+    close(xg.grad.permute(0, 3, 1, 2), xr.grad, 1e-6, 1e-6)
+
+
+def test_bad_arguments_raise(dev):
+    from layout2img_b200 import ops
+    x = torch.zeros(1, 6, 6, 8, device=dev)      # H, W not powers of two
+    wp = ops.conv_weight_prep(torch.zeros(8, 8, 3, 3, device=dev))
+    with pytest.raises(ValueError):
+        ops.conv2d_fwd(ops.act_split(x), wp.f_hi, wp.f_lo, 8, 9)
+    with pytest.raises(RuntimeError):
+        ops.act_split(torch.zeros(1, 4, 4, 8))   # CPU tensor: no fallback
