@@ -25,6 +25,8 @@ extern "C" {
 
 int l2i_version(void);
 const char* l2i_last_error(void);
+/* number of libl2i kernels launched by this process since the last reset (bench.py's gpu_launches). */
+int l2i_launch_count(int reset);
 
 /* ---- convolution (replaces nn.Conv2d -> cuDNN; reference model/resnet_generator_app_v2.py:633-639,
  *      681-686 and model/rcnn_discriminator_app.py:10-15,297-326) ------------------------------- */

@@ -4,8 +4,10 @@
 #include "../../include/l2i.h"
 #include "kernels.h"
 
+#include <atomic>
 namespace l2i {
 static thread_local char g_err[512] = "";
+static std::atomic<int> g_launches{0};
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -18,6 +20,7 @@ int check_launch(const char* what) {
     set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
     return L2I_ERR_LAUNCH;
   }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return L2I_OK;
 }
 }  // namespace l2i
@@ -29,6 +32,9 @@ extern "C" {
 
 int l2i_version(void) { return 100; }
 const char* l2i_last_error(void) { return g_err; }
+int l2i_launch_count(int reset) {
+  return reset ? g_launches.exchange(0, std::memory_order_relaxed) : g_launches.load(std::memory_order_relaxed);
+}
 
 int l2i_conv_weight_prep(const float* w, const float* sigma, int cout, int cin, int taps, void* fwd_hi, void* fwd_lo,
                          int cin_pad, void* dg_hi, void* dg_lo, int cout_pad, void* stream) {
