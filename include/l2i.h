@@ -125,6 +125,14 @@ int l2i_box_attention_bwd(const float* q, const float* k, const float* v, const 
                           const float* p_save, const float* glin_save, const float* dout, int B, int O, int D,
                           float* dq, float* dk, float* dv, float* dwg, float* dbg, void* stream);
 
+/* ---- optimizer (reference train_context_app_v2.py:113-127,174,189: torch.optim.Adam(betas=(0, 0.999)),
+ *      one parameter group per tensor).  One launch updates every tensor of a network.
+ *      tensors: device array of { float* p; const float* g; float* m; float* v; int64 n; float lr; int pad; }
+ *      (48 bytes each); chunks: device array of n_chunks (tensor index, chunk index) int pairs, each
+ *      covering chunk_elems (multiple of 4) consecutive elements.  Arithmetic = torch's Adam step. ---- */
+int l2i_adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, float beta1, float beta2,
+                  float eps, float bias_correction1, float bias_correction2_sqrt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

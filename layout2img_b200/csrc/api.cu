@@ -143,4 +143,10 @@ int l2i_box_attention_bwd(const float* q, const float* k, const float* v, const 
                            dv, dwg, dbg, ST(stream));
 }
 
+int l2i_adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, float beta1, float beta2,
+                  float eps, float bias_correction1, float bias_correction2_sqrt, void* stream) {
+  return adam_step(tensors, chunks, n_chunks, chunk_elems, beta1, beta2, eps, bias_correction1, bias_correction2_sqrt,
+                   ST(stream));
+}
+
 }  // extern "C"

@@ -8,6 +8,13 @@
 // a_hi*b_hi + a_lo*b_hi + a_hi*b_lo -- three bf16 tcgen05.mma per K step.  Measured against
 // the fp32 reference this is ~60x more accurate than single-pass TF32.
 //
+// Accumulator layout: the tensor core adds each MMA result into the fp32 TMEM accumulator with
+// truncation (measured: a systematic -1.6e-8 relative bias per non-zero add, i.e. -2.7e-5 after the
+// 1728 adds of a K=9216 reduction -- 4x the fp32 reference's own noise).  So the two small cross
+// terms go to their own accumulator (their truncation is 2^-8 smaller), and the hi*hi products
+// rotate over up to three accumulators so that no chain is longer than ~190 adds; the epilogue
+// sums the (up to four) partial tiles in fp32 round-to-nearest.  TMEM columns: 4 * BN.
+//
 // Data layout: activations NHWC (channel count padded to a multiple of 8), one tensor per
 // half of the pair.  Forward / data-gradient:
 //   GEMM M = 128 output pixels (a TW x TH x TN patch), N = BN output channels,
@@ -38,7 +45,33 @@ struct FwdCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = 2 * kTileBytes + 2 * kBBytes;
   static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 4 * BN;   // main0..2 + cross
 };
+
+// sum of the partial accumulator tiles of one 32-column chunk (lane = GEMM row)
+template <int BN>
+__device__ __forceinline__ void load_accum_chunk(uint32_t taddr, int n_main, float (&acc)[32]) {
+  uint32_t r[32], x[32];
+  tmem_ld_32x32(taddr, r);                 // main 0
+  tmem_ld_32x32(taddr + 3 * BN, x);        // cross terms
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+  if (n_main > 1) {
+    tmem_ld_32x32(taddr + BN, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+    if (n_main > 2) {
+      tmem_ld_32x32(taddr + 2 * BN, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(x[j]);
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -77,7 +110,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -104,6 +137,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      const uint32_t d_cross = tmem_base + 3 * BN;
+      int g = 0, rot = 0;                  // global k16 step, main accumulator in use
       for (int it = 0; it < k_iters; ++it) {
         const int s = it % Cfg::kStages;
         const uint32_t ph = (it / Cfg::kStages) & 1;
@@ -119,9 +154,11 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           const uint64_t dal = umma_desc_sw128(a_lo + k * 32, 16, 1024);
           const uint64_t dbh = umma_desc_sw128(b_hi + k * 32, 16, 1024);
           const uint64_t dbl = umma_desc_sw128(b_lo + k * 32, 16, 1024);
-          umma_bf16(tmem_base, dal, dbh, idesc, (it > 0 || k > 0) ? 1u : 0u);  // small terms first
-          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-          umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+          umma_bf16(d_cross, dal, dbh, idesc, g > 0 ? 1u : 0u);
+          umma_bf16(d_cross, dah, dbl, idesc, 1u);
+          umma_bf16(tmem_base + rot * BN, dah, dbh, idesc, g >= p.n_main ? 1u : 0u);
+          ++g;
+          rot = (rot + 1 == p.n_main) ? 0 : rot + 1;
         }
         umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
       }
@@ -144,17 +181,15 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const bool vec_ok = (p.cout & 3) == 0;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
-      uint32_t r[32];
+      float v[32];
       __syncwarp();
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
-      tmem_ld_wait();
+      load_accum_chunk<BN>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, p.n_main, v);
       const int cbase = co0 + c;
       if (!row_ok || cbase >= p.cout) continue;
-      float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int co = cbase + j;
-        float x = __uint_as_float(r[j]);
+        float x = v[j];
         if (co < p.cout) {
           if (p.bias) x += __ldg(p.bias + co);
           if (p.residual) x += __ldg(p.residual + rpix * p.cout + co);
@@ -202,7 +237,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -216,6 +251,7 @@ struct WgCfg {
   static constexpr int kBBytes = BN * 64 * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kTmemCols = 4 * BN;
 };
 
 template <int BN>
@@ -255,7 +291,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_con
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -290,6 +326,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_con
     } else if (warp == 1) {
       if (lane == 0) {
         constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+        const uint32_t d_cross = tmem_base + 3 * BN;
+        const int n_main = min(p.n_main, k_iters * 4);
+        int g = 0, rot = 0;
         for (int it = 0; it < k_iters; ++it) {
           const int s = it % Cfg::kStages;
           const uint32_t ph = (it / Cfg::kStages) & 1;
@@ -305,9 +344,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_con
             const uint64_t dal = umma_desc_sw128(a_lo + k * 2048, 8192, 1024);
             const uint64_t dbh = umma_desc_sw128(b_hi + k * 2048, 8192, 1024);
             const uint64_t dbl = umma_desc_sw128(b_lo + k * 2048, 8192, 1024);
-            umma_bf16(tmem_base, dal, dbh, idesc, (it > 0 || k > 0) ? 1u : 0u);
-            umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-            umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+            umma_bf16(d_cross, dal, dbh, idesc, g > 0 ? 1u : 0u);
+            umma_bf16(d_cross, dah, dbl, idesc, 1u);
+            umma_bf16(tmem_base + rot * BN, dah, dbh, idesc, g >= n_main ? 1u : 0u);
+            ++g;
+            rot = (rot + 1 == n_main) ? 0 : rot + 1;
           }
           umma_commit(&empty_bar[s]);
         }
@@ -320,16 +361,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_con
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
+        float v[32];
         __syncwarp();
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
-        tmem_ld_wait();
+        load_accum_chunk<BN>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, min(p.n_main, k_iters * 4), v);
         if (co >= p.cout) continue;
         float* o = p.dw + (static_cast<size_t>(co) * p.taps + tap) * p.cin + ci0 + c;
         if (p.atomic) {
-          for (int j = 0; j < 32 && ci0 + c + j < p.cin; ++j) atomicAdd(o + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 32 && ci0 + c + j < p.cin; ++j) atomicAdd(o + j, v[j]);
         } else {
-          for (int j = 0; j < 32 && ci0 + c + j < p.cin; ++j) o[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 32 && ci0 + c + j < p.cin; ++j) o[j] = v[j];
         }
       }
     }
@@ -338,7 +378,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_con
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -398,6 +438,12 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int box_
   return L2I_OK;
 }
 
+// hi*hi accumulators to rotate over so that no TMEM accumulation chain exceeds ~144-192 adds
+static int main_accumulators(int k16_steps) {
+  int n = (k16_steps + 143) / 144;
+  return n < 1 ? 1 : (n > 3 ? 3 : n);
+}
+
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // pick a (tw, th, tn) patch of exactly `pixels` pixels
@@ -435,6 +481,7 @@ int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream) {
   p.tiles_w = a.W / p.TW; p.tiles_h = a.H / p.TH;
   const int tiles_n = (a.N + p.TN - 1) / p.TN;
   p.kchunks = (a.cin_pad + kBK - 1) / kBK;
+  p.n_main = main_accumulators(a.taps * p.kchunks * (kBK / 16));
   p.bias = a.bias; p.residual = a.residual; p.res_shift = a.res_shift; p.out = a.out;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(a.out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(a.out_lo);
   p.cout_pad = a.cout_pad; p.relu_split = a.relu_split; p.out_scale = a.out_scale;
@@ -485,6 +532,7 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t stream) {
   p.blocks_per_split = (p.pix_blocks + splits - 1) / splits;
   splits = (p.pix_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
   p.atomic = splits > 1;
+  p.n_main = main_accumulators(p.blocks_per_split * 4);
   p.dw = a.dw;
   if (p.atomic) {
     cudaError_t e = cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.cout * a.taps * a.cin, stream);

@@ -8,6 +8,7 @@ namespace l2i {
 struct ConvFwdParams {          // device-side view
   int N, H, W, cin_pad, cout, taps;
   int TW, TH, TN, tiles_w, tiles_h, kchunks;
+  int n_main;                   // hi*hi accumulators rotated over (1..3)
   const float* bias;            // [cout] or null
   const float* residual;        // [N,H,W,cout] (res_shift=0) or [N,H/2,W/2,cout] nearest-x2 (res_shift=1), or null
   int res_shift;
@@ -33,7 +34,7 @@ struct ConvFwdArgs {            // host-side call
 
 struct ConvWgradParams {
   int N, H, W, cin, cout, taps;
-  int TW, TH, TN, tiles_w, tiles_h, pix_blocks, blocks_per_split, cin_tiles, atomic;
+  int TW, TH, TN, tiles_w, tiles_h, pix_blocks, blocks_per_split, cin_tiles, atomic, n_main;
   float* dw;                    // [cout][taps][cin] fp32
 };
 

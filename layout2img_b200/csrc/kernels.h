@@ -56,4 +56,17 @@ int box_attention_bwd(const float* q, const float* k, const float* v, const floa
                       const float* p_save, const float* glin_save, const float* dout, int B, int O, int D, float* dq,
                       float* dk, float* dv, float* dwg, float* dbg, cudaStream_t stream);
 
+// optim.cu
+struct AdamTensor {       // one entry of the device-resident tensor table (48 bytes, see include/l2i.h)
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long long n;
+  float lr;
+  int pad_;
+};
+int adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, float beta1, float beta2, float eps,
+              float bc1, float bc2_sqrt, cudaStream_t stream);
+
 }  // namespace l2i

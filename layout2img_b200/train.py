@@ -15,10 +15,29 @@ LAMB_OBJ, LAMB_IMG, LAMB_APP = 1.0, 0.1, 1.0       # train_context_app_v2.py:40-
 
 
 def make_optimizers(netG, netD, g_lr: float = 1e-4, d_lr: float = 1e-4):
-    """Adam(betas=(0, 0.999)) with one param group per tensor (train_context_app_v2.py:113-127)."""
-    g_opt = torch.optim.Adam([{"params": [p], "lr": g_lr} for p in netG.parameters()], betas=(0.0, 0.999))
-    d_opt = torch.optim.Adam([{"params": [p], "lr": d_lr} for p in netD.parameters()], betas=(0.0, 0.999))
+    """Adam(betas=(0, 0.999)) with one param group per tensor (train_context_app_v2.py:113-127), executed as
+    one multi-tensor kernel per network (optim.FusedAdam -> csrc/optim.cu)."""
+    from .optim import FusedAdam
+    g_opt = FusedAdam([{"params": [p], "lr": g_lr} for p in netG.parameters()], betas=(0.0, 0.999))
+    d_opt = FusedAdam([{"params": [p], "lr": d_lr} for p in netD.parameters()], betas=(0.0, 0.999))
     return g_opt, d_opt
+
+
+class _frozen:
+    """Temporarily clear requires_grad on a module's parameters: in the G step the reference lets autograd
+    compute D's weight gradients and then discards them at the next netD.zero_grad()
+    (train_context_app_v2.py:156,178-188); skipping them changes nothing observable."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+
+    def __enter__(self):
+        for p in self.params:
+            p.requires_grad_(False)
+
+    def __exit__(self, *exc):
+        for p in self.params:
+            p.requires_grad_(True)
 
 
 def d_loss_fn(real_out, fake_out):
@@ -86,9 +105,10 @@ def train_step(netG, netD, g_opt, d_opt, real, label, bbox, z, z_im=None, sync_g
     d_opt.step()
     # ---- G step (:177-189); D's gradients produced here are discarded by the next zero_grad
     netG.zero_grad()
-    g_out = netD(fake, bbox, lab3)
-    g_loss = g_loss_fn(g_out, fake, real)
-    g_loss.backward()
+    with _frozen(netD):
+        g_out = netD(fake, bbox, lab3)
+        g_loss = g_loss_fn(g_out, fake, real)
+        g_loss.backward()
     if sync_g is not None:
         sync_g()
     if record is not None:

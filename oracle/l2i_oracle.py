@@ -334,7 +334,7 @@ def roi_align(feat: torch.Tensor, rois: torch.Tensor, scale: float, out: int = 8
     """torchvision.ops.RoIAlign((8,8), scale, sampling_ratio=0), aligned=False -- third-party
     (torchvision 0.26.0); call sites rcnn_discriminator_app.py:98-99,139,143."""
     from torchvision.ops import roi_align as tv_roi_align
-    return tv_roi_align(feat, rois, (out, out), scale, 0, False)
+    return tv_roi_align(feat, rois.to(feat.dtype), (out, out), scale, 0, False)   # rois are fp32; feat may be fp64 in diagnostics
 
 
 def d_forward(P: State, images, bbox, label, training: bool, taps: Optional[dict] = None):

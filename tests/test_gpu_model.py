@@ -36,6 +36,65 @@ def close(got, want, rtol=RTOL, atol=ATOL, what=""):
     assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} outside tol, max err {err.max().item():.3e} (ref max {want.abs().max().item():.3e})"
 
 
+def _oracle_step(meta, data, keep, dtype):
+    """One oracle iteration in `dtype`; returns grads ("d.<name>" after d_loss.backward, "g.<name>" after
+    g_loss.backward), losses, fake and the post-step states."""
+    PG = make_state(load_schema("G", meta["num_classes"]), meta["seed_g"])
+    PD = make_state(load_schema("D", meta["num_classes"]), meta["seed_d"])
+    cv = lambda t: t.to(dtype) if t.is_floating_point() else t
+    PG, PD = {k: cv(v) for k, v in PG.items()}, {k: cv(v) for k, v in PD.items()}
+    O.set_requires_grad(PG); O.set_requires_grad(PD)
+    og, od = O.make_adam(PG, 1e-4), O.make_adam(PD, 1e-4)
+    out = {}
+    od_step, og_step = od.step, og.step
+
+    def d_step(*a, **k):
+        for n in O.param_names(PD):
+            out["d." + n] = PD[n].grad.detach().clone()
+        return od_step(*a, **k)
+
+    def g_step(*a, **k):
+        for n in O.param_names(PG):
+            out["g." + n] = PG[n].grad.detach().clone()
+        return og_step(*a, **k)
+
+    od.step, og.step = d_step, g_step
+    rd, rg, rfake = O.train_step(PG, PD, og, od, cv(data["real"]), data["label"], cv(data["bbox"]), cv(data["z"]),
+                                 cv(data["z_im"]), dropout_mask=keep.to(dtype))
+    out.update(d_loss=rd, g_loss=rg, fake=rfake, PG=PG, PD=PD)
+    return out
+
+
+def grad_close(got, want32, want64, what):
+    """End-to-end gradient parity against the fp32 oracle.
+
+    tol1 = 2e-3 * |ref| + 1e-5 + 2e-4 * max|ref| + 4 * (the fp32 oracle's own max deviation from the fp64
+    oracle on this tensor -- gradients that pass through 1/(sum_o m + 1e-6) are only good to ~3e-3 of their
+    max in the reference's own fp32 arithmetic).
+
+    A ReLU whose input is within rounding distance of 0 may land on the other side in any implementation
+    that is not bit-identical to the reference (the fp32 and fp64 oracles disagree with each other the same
+    way, tools/grad_diag.py); every such kink crossing adds or removes one pixel's contribution to the
+    gradients upstream of it.  So on top of tol1: all but 1 % of a tensor's elements must be within
+    5e-3 * max|ref|, every element within 5e-2 * max|ref|, and the relative L2 error below 1e-2.  A wrong
+    formula or index moves most elements by O(max|ref|) and fails all three.  (The tight, kink-free
+    comparisons of every kernel's backward are the per-operator tests in test_gpu_ops.py.)"""
+    got, w32, w64 = got.detach().double().cpu(), want32.detach().double(), want64.detach().double()
+    m = w32.abs().max().item()
+    if m == 0.0:
+        assert got.abs().max().item() <= 1e-12, f"{what}: reference gradient is exactly zero"
+        return
+    noise = (w32 - w64).abs().max().item()
+    err = (got - w32).abs()
+    tol1 = 2e-3 * w32.abs() + 1e-5 + 2e-4 * m + 4 * noise
+    n_loose = int((err > tol1 + 5e-3 * m).sum())
+    msg = (f"{what}: max err {err.max().item():.3e}, ref max {m:.3e}, fp32-ref noise {noise:.3e}, "
+           f"{int((err > tol1).sum())}/{err.numel()} outside tol1, {n_loose} outside tol1 + 5e-3 max")
+    assert n_loose <= max(1, int(0.01 * err.numel())), msg
+    assert bool((err <= tol1 + 5e-2 * m).all()), msg
+    assert err.norm().item() <= 1e-2 * w32.norm().item() + 8 * noise * err.numel() ** 0.5, msg
+
+
 @pytest.mark.parametrize("name", ["C", "Cpad", "V"])
 def test_eval_forward_matches_oracle_and_reference(name):
     dev = torch.device("cuda:0")
@@ -78,40 +137,30 @@ def test_train_step_matches_oracle_and_reference(name):
 
     d_loss, g_loss, fake = train_step(G, D, g_opt, d_opt, data["real"].to(dev), data["label"].to(dev),
                                       data["bbox"].to(dev), data["z"].to(dev), data["z_im"].to(dev), record=record)
-    # ---- oracle on CPU
-    O.set_requires_grad(PG); O.set_requires_grad(PD)
-    og, od = O.make_adam(PG, 1e-4), O.make_adam(PD, 1e-4)
-    ref = {}
-    od_step = od.step
-    def d_step(*a, **k):
-        for n in O.param_names(PD):
-            ref["d." + n] = PD[n].grad.detach().clone()
-        return od_step(*a, **k)
-    od.step = d_step
-    og_step = og.step
-    def g_step(*a, **k):
-        for n in O.param_names(PG):
-            ref["g." + n] = PG[n].grad.detach().clone()
-        return og_step(*a, **k)
-    og.step = g_step
-    rd, rg, rfake = O.train_step(PG, PD, og, od, data["real"], data["label"], data["bbox"], data["z"], data["z_im"],
-                                 dropout_mask=keep)
-    assert abs(d_loss.item() - rd.item()) < 1e-4 and abs(d_loss.item() - float(z["train.d_loss"])) < 1e-4
-    assert abs(g_loss.item() - rg.item()) < 1e-4 and abs(g_loss.item() - float(z["train.g_loss"])) < 1e-4
-    close(fake, rfake, what="train fake")
+    # ---- oracle on CPU, in fp32 (the reference's arithmetic) and in fp64 (to measure that arithmetic's
+    # own rounding noise on this case: gradients that pass through 1/(sum_o m + 1e-6) are only good to
+    # ~3e-3 of their max in the fp32 reference itself)
+    r32 = _oracle_step(meta, data, keep, torch.float32)
+    r64 = _oracle_step(meta, data, keep, torch.float64)
+    for got, want in ((d_loss.item(), r32["d_loss"].item()), (d_loss.item(), float(z["train.d_loss"])),
+                      (g_loss.item(), r32["g_loss"].item()), (g_loss.item(), float(z["train.g_loss"]))):
+        assert abs(got - want) <= ATOL + RTOL * abs(want), (got, want)
+    close(fake, r32["fake"], what="train fake")
     assert_summary_close(fake.cpu(), z["train.fake"], RTOL, ATOL, "train fake vs reference golden")
-    for n in O.param_names(PD):
-        want = ref["d." + n]
-        close(grads["d." + n], want, 2e-3, 1e-5 + 2e-4 * want.abs().max().item(), "D grad " + n)
-        assert_summary_close(grads["d." + n].cpu(), z[f"train.dgrad.{n}"], 2e-3, 1e-5 + 2e-4 * want.abs().max().item(), "D grad vs golden " + n)
-    for n in O.param_names(PG):
-        want = ref["g." + n]
-        # d(mask) carries the reference's 1/(sum_o m + 1e-6) amplification
-        close(grads["g." + n], want, 2e-3, 1e-5 + 5e-4 * want.abs().max().item(), "G grad " + n)
+    for tag, net in (("d", D), ("g", G)):
+        for n, _ in net.named_parameters():
+            k = tag + "." + n
+            grad_close(grads[k], r32[k], r64[k], k)
+    for n in O.param_names(r32["PD"]):
+        want = r32["d." + n]
+        noise = (want.double() - r64["d." + n]).abs().max().item()
+        # sampled elements + moments recorded from the unmodified reference; same kink allowance as grad_close
+        assert_summary_close(grads["d." + n].cpu(), z[f"train.dgrad.{n}"], 2e-3,
+                             1e-5 + 5e-3 * want.abs().max().item() + 4 * noise, "D grad vs golden " + n)
     sdG, sdD = G.state_dict(), D.state_dict()
-    for n, v in PG.items():
+    for n, v in r32["PG"].items():
         close(sdG[n].float(), v.float(), 1e-3, 2e-4, "G state " + n)
-    for n, v in PD.items():
+    for n, v in r32["PD"].items():
         close(sdD[n].float(), v.float(), 1e-3, 2e-4, "D state " + n)
 
 

@@ -315,3 +315,28 @@ def test_bad_arguments_raise(dev):
         ops.conv2d_fwd(ops.act_split(x), wp.f_hi, wp.f_lo, 8, 9)
     with pytest.raises(RuntimeError):
         ops.act_split(torch.zeros(1, 4, 4, 8))   # CPU tensor: no fallback
+
+
+def test_fused_adam_matches_torch_adam(dev):
+    """optim.FusedAdam (one launch for all tensors) vs torch.optim.Adam(betas=(0, 0.999)) with one group per
+    tensor, as the reference builds it (train_context_app_v2.py:113-127): 4 steps, odd sizes, a tensor
+    without gradient."""
+    from layout2img_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(3)
+    shapes = [(1,), (3,), (100, 7), (184, 100, 1, 1), (50001,), (64, 64, 3, 3), (5,)]
+    ps_a = [torch.randn(s, generator=g).to(dev).requires_grad_() for s in shapes]
+    ps_b = [p.detach().clone().requires_grad_() for p in ps_a]
+    lrs = [1e-4 * (1 + i) for i in range(len(shapes))]
+    a = FusedAdam([{"params": [p], "lr": lr} for p, lr in zip(ps_a, lrs)], betas=(0.0, 0.999))
+    b = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(ps_b, lrs)], betas=(0.0, 0.999))
+    for step in range(4):
+        for i, (pa, pb) in enumerate(zip(ps_a, ps_b)):
+            if i == len(shapes) - 1:
+                continue                        # never receives a gradient
+            gr = (torch.randn(pa.shape, generator=g) * 10 ** float(step - 2)).to(dev)
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        a.step(); b.step()
+    for pa, pb in zip(ps_a, ps_b):
+        close(pa, pb, rtol=1e-6, atol=1e-7, what="adam param")
+    for pa, pb in zip(ps_a[:-1], ps_b[:-1]):
+        close(a.state[pa]["exp_avg_sq"], b.state[pb]["exp_avg_sq"], rtol=1e-6, atol=1e-12, what="exp_avg_sq")
