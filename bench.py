@@ -180,8 +180,10 @@ def kernel_breakdown(step_fn):
         return r
 
     import layout2img_b200.ops as ops_mod
+    import layout2img_b200.optim as optim_mod
     _lib.call = timed_call
     ops_mod.call = timed_call
+    optim_mod.call = timed_call
     try:
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
@@ -191,6 +193,7 @@ def kernel_breakdown(step_fn):
     finally:
         _lib.call = orig
         ops_mod.call = orig
+        optim_mod.call = orig
     agg = {}
     for name, e0, e1, fl in rec:
         d = agg.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0})

@@ -41,15 +41,20 @@ int l2i_conv_weight_prep(const float* w, const float* sigma, int cout, int cin, 
 int l2i_act_split(const float* x, int N, int H, int W, int C, int relu, int up2, void* hi, void* lo, int cpad,
                   void* stream);
 
-/* y = (conv(x, w) + bias + residual) * out_scale, stride 1, "same" padding; H, W powers of two.
- * x pair [N,H,W,cin_pad]; w pair [cout][taps][cin_pad]; bias [cout] or NULL; residual [N,H,W,cout]
- * (res_up2 = 0) or [N,H/2,W/2,cout] read with nearest x2 up-sampling (res_up2 = 1), or NULL.
- * Outputs (either may be NULL, not both): out fp32 [N,H,W,cout]; pair [N,H,W,cout_pad] of
+/* v = (conv(x, w) + bias) * out_scale, stride 1, "same" padding; H, W powers of two.
+ * x pair [N,H,W,cin_pad]; w pair [cout][taps][cin_pad]; bias [cout] or NULL.
+ * mask_hi (nullable): bf16 [N,H,W,mask_cpad]; v is zeroed where mask_hi <= 0 -- the ReLU derivative taken
+ *   from the saved (ReLU'd) activation pair when this call computes a data gradient.
+ * pool: 0 none; 1 = 2x2 average, 2 = 2x2 sum of v, stored at (H/2, W/2) (F.avg_pool2d(.,2) of the D blocks;
+ *   the backward of the G blocks' nearest x2 up-sampling).
+ * y = pool(v) + res_scale * residual; residual (nullable) has the stored resolution, or half of it, read
+ *   with nearest x2 up-sampling, when res_up2 = 1 (pool must be 0 then).
+ * Outputs (either may be NULL, not both): out fp32 [N,Ho,Wo,cout]; pair [N,Ho,Wo,cout_pad] of
  * relu_split ? relu(y) : y.  The data gradient is the same call with the dgrad weight pair. */
 int l2i_conv2d_fwd(int N, int H, int W, int cin_pad, int cout, int taps, const void* x_hi, const void* x_lo,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, int res_up2,
-                   float out_scale, float* out, void* out_hi, void* out_lo, int cout_pad, int relu_split,
-                   void* stream);
+                   float res_scale, float out_scale, const void* mask_hi, int mask_cpad, int pool, float* out, void* out_hi,
+                   void* out_lo, int cout_pad, int relu_split, void* stream);
 
 /* dw [cout][taps][cin] fp32 = sum over pixels of dy (x) shifted x.  dy pair [N,H,W,cout_pad],
  * x pair [N,H,W,cin_pad]. */
@@ -130,8 +135,8 @@ int l2i_box_attention_bwd(const float* q, const float* k, const float* v, const 
  *      tensors: device array of { float* p; const float* g; float* m; float* v; int64 n; float lr; int pad; }
  *      (48 bytes each); chunks: device array of n_chunks (tensor index, chunk index) int pairs, each
  *      covering chunk_elems (multiple of 4) consecutive elements.  Arithmetic = torch's Adam step. ---- */
-int l2i_adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, float beta1, float beta2,
-                  float eps, float bias_correction1, float bias_correction2_sqrt, void* stream);
+int l2i_adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, double beta1, double beta2,
+                  double eps, double bias_correction1, double bias_correction2_sqrt, void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,13 +48,14 @@ int l2i_act_split(const float* x, int N, int H, int W, int C, int relu, int up2,
 
 int l2i_conv2d_fwd(int N, int H, int W, int cin_pad, int cout, int taps, const void* x_hi, const void* x_lo,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, int res_up2,
-                   float out_scale, float* out, void* out_hi, void* out_lo, int cout_pad, int relu_split,
-                   void* stream) {
+                   float res_scale, float out_scale, const void* mask_hi, int mask_cpad, int pool, float* out, void* out_hi,
+                   void* out_lo, int cout_pad, int relu_split, void* stream) {
   ConvFwdArgs a;
   a.N = N; a.H = H; a.W = W; a.cin_pad = cin_pad; a.cout = cout; a.taps = taps;
   a.x_hi = x_hi; a.x_lo = x_lo; a.w_hi = w_hi; a.w_lo = w_lo; a.bias = bias; a.residual = residual;
   a.res_shift = res_up2 ? 1 : 0; a.out = out; a.out_hi = out_hi; a.out_lo = out_lo; a.cout_pad = cout_pad;
-  a.relu_split = relu_split; a.out_scale = out_scale;
+  a.relu_split = relu_split; a.out_scale = out_scale; a.res_scale = res_scale;
+  a.mask_hi = mask_hi; a.mask_cpad = mask_cpad; a.pool = pool;
   return conv_fwd_tc(a, ST(stream));
 }
 
@@ -143,8 +144,8 @@ int l2i_box_attention_bwd(const float* q, const float* k, const float* v, const 
                            dv, dwg, dbg, ST(stream));
 }
 
-int l2i_adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, float beta1, float beta2,
-                  float eps, float bias_correction1, float bias_correction2_sqrt, void* stream) {
+int l2i_adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, double beta1, double beta2,
+                  double eps, double bias_correction1, double bias_correction2_sqrt, void* stream) {
   return adam_step(tensors, chunks, n_chunks, chunk_elems, beta1, beta2, eps, bias_correction1, bias_correction2_sqrt,
                    ST(stream));
 }

@@ -8,12 +8,13 @@
 // a_hi*b_hi + a_lo*b_hi + a_hi*b_lo -- three bf16 tcgen05.mma per K step.  Measured against
 // the fp32 reference this is ~60x more accurate than single-pass TF32.
 //
-// Accumulator layout: the tensor core adds each MMA result into the fp32 TMEM accumulator with
+// Accumulation: the tensor core adds each MMA result into the fp32 TMEM accumulator with
 // truncation (measured: a systematic -1.6e-8 relative bias per non-zero add, i.e. -2.7e-5 after the
-// 1728 adds of a K=9216 reduction -- 4x the fp32 reference's own noise).  So the two small cross
-// terms go to their own accumulator (their truncation is 2^-8 smaller), and the hi*hi products
-// rotate over up to three accumulators so that no chain is longer than ~190 adds; the epilogue
-// sums the (up to four) partial tiles in fp32 round-to-nearest.  TMEM columns: 4 * BN.
+// 1728 adds of a K=9216 reduction -- 4x the fp32 reference's own noise).  So (i) the two small cross
+// terms go to their own accumulator (their truncation is 2^-8 smaller), and (ii) the K loop is cut
+// into passes of at most 144 k16 steps; each pass starts a fresh (main, cross) accumulator pair in
+// one of two TMEM buffers, and the epilogue warps add the finished pass into fp32 registers with
+// round-to-nearest while the tensor core already runs the next pass (or the next tile).
 //
 // Data layout: activations NHWC (channel count padded to a multiple of 8), one tensor per
 // half of the pair.  Forward / data-gradient:
@@ -35,6 +36,7 @@ namespace l2i {
 static constexpr int kThreads = 192;
 static constexpr int kBK = 64;          // bf16 elements per smem row (128 B, SWIZZLE_128B)
 static constexpr int kTileBytes = 128 * kBK * 2;   // one 128-row operand tile: 16 KB
+static constexpr int kPassLen = 36;     // k-iterations (of 4 k16 steps) accumulated inside TMEM before the epilogue takes over
 
 // ------------------------------------------------------------------------------------------
 // forward / dgrad
@@ -45,34 +47,28 @@ struct FwdCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = 2 * kTileBytes + 2 * kBBytes;
   static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = 4 * BN;   // main0..2 + cross
+  static constexpr int kTmemCols = 512;      // whole TMEM: one CTA per SM (shared memory already enforces it)
 };
 
-// sum of the partial accumulator tiles of one 32-column chunk (lane = GEMM row)
+// acc (+)= main + cross for the 32-column chunk at `taddr` (lane = GEMM row); cross tile BN columns later
 template <int BN>
-__device__ __forceinline__ void load_accum_chunk(uint32_t taddr, int n_main, float (&acc)[32]) {
+__device__ __forceinline__ void add_pass_chunk(uint32_t taddr, bool first, float* acc) {
   uint32_t r[32], x[32];
-  tmem_ld_32x32(taddr, r);                 // main 0
-  tmem_ld_32x32(taddr + 3 * BN, x);        // cross terms
+  tmem_ld_32x32(taddr, r);
+  tmem_ld_32x32(taddr + BN, x);
   tmem_ld_wait();
+  if (first) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-  if (n_main > 1) {
-    tmem_ld_32x32(taddr + BN, r);
-    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]) + __uint_as_float(x[j]);
+  } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
-    if (n_main > 2) {
-      tmem_ld_32x32(taddr + 2 * BN, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
-    }
+    for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]) + __uint_as_float(x[j]);
   }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(x[j]);
 }
 
+// Persistent kernel: gridDim.x CTAs (one per SM) walk the (m_tile, n_tile) list with stride gridDim.x.
+// The TMA producer and the MMA issuer run ahead across tile boundaries (the smem ring never drains);
+// with two TMEM accumulator buffers the epilogue of tile i overlaps the main loop of tile i+1.
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -83,20 +79,14 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* accum_bar = empty_bar + Cfg::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;     // [2] accumulator buffer complete
+  uint64_t* tempty_bar = tfull_bar + 2;               // [2] accumulator buffer drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile coordinates
-  const int mt = blockIdx.x;
-  const int tw_i = mt % p.tiles_w;
-  const int th_i = (mt / p.tiles_w) % p.tiles_h;
-  const int tn_i = mt / (p.tiles_w * p.tiles_h);
-  const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
-  const int co0 = blockIdx.y * BN;
   const int k_iters = p.taps * p.kchunks;
+  const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
@@ -107,7 +97,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -118,116 +111,208 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % Cfg::kStages;
-        const uint32_t ph = (it / Cfg::kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        const int tap = it / p.kchunks;
-        const int kc = it - tap * p.kchunks;
-        const int dr = (p.taps == 9) ? (tap / 3 - 1) : 0;
-        const int ds = (p.taps == 9) ? (tap % 3 - 1) : 0;
-        uint8_t* st = smem + s * Cfg::kStageBytes;
-        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        tma_load_4d(st, &tm_a_hi, &full_bar[s], kc * kBK, w0 + ds, h0 + dr, n0);
-        tma_load_4d(st + kTileBytes, &tm_a_lo, &full_bar[s], kc * kBK, w0 + ds, h0 + dr, n0);
-        tma_load_2d(st + 2 * kTileBytes, &tm_b_hi, &full_bar[s], tap * p.cin_pad + kc * kBK, co0);
-        tma_load_2d(st + 2 * kTileBytes + Cfg::kBBytes, &tm_b_lo, &full_bar[s], tap * p.cin_pad + kc * kBK, co0);
+      int ring = 0;                               // stage counter, runs on across tiles
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles;
+        const int mt = t / p.n_tiles;
+        const int w0 = (mt % p.tiles_w) * p.TW;
+        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
+        const int co0 = nt * BN;
+        for (int it = 0; it < k_iters; ++it, ++ring) {
+          const int s = ring % Cfg::kStages;
+          const uint32_t ph = (ring / Cfg::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const int tap = it / p.kchunks;
+          const int kc = it - tap * p.kchunks;
+          const int dr = (p.taps == 9) ? (tap / 3 - 1) : 0;
+          const int ds = (p.taps == 9) ? (tap % 3 - 1) : 0;
+          uint8_t* st = smem + s * Cfg::kStageBytes;
+          mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          tma_load_4d(st, &tm_a_hi, &full_bar[s], kc * kBK, w0 + ds, h0 + dr, n0);
+          tma_load_4d(st + kTileBytes, &tm_a_lo, &full_bar[s], kc * kBK, w0 + ds, h0 + dr, n0);
+          tma_load_2d(st + 2 * kTileBytes, &tm_b_hi, &full_bar[s], tap * p.cin_pad + kc * kBK, co0);
+          tma_load_2d(st + 2 * kTileBytes + Cfg::kBBytes, &tm_b_lo, &full_bar[s], tap * p.cin_pad + kc * kBK, co0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-      const uint32_t d_cross = tmem_base + 3 * BN;
-      int g = 0, rot = 0;                  // global k16 step, main accumulator in use
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % Cfg::kStages;
-        const uint32_t ph = (it / Cfg::kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t a_lo = a_hi + kTileBytes;
-        const uint32_t b_hi = a_hi + 2 * kTileBytes;
-        const uint32_t b_lo = b_hi + Cfg::kBBytes;
+      int ring = 0, pass_i = 0;                   // smem stage counter / accumulator pass counter (run across tiles)
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int it = 0;
+        for (int ps = 0; ps < p.n_pass; ++ps, ++pass_i) {
+          const int buf = pass_i & 1;
+          mbar_wait(&tempty_bar[buf], ((pass_i >> 1) & 1) ^ 1);   // epilogue has drained this buffer
+          tc_fence_after();
+          const uint32_t d_main = tmem_base + buf * (2 * BN);
+          const uint32_t d_cross = d_main + BN;
+          const int it_end = min(it + p.pass_len, k_iters);
+          uint32_t fresh = 0;                       // 0 for the first MMA into each accumulator of the pass
+          for (; it < it_end; ++it, ++ring) {
+            const int s = ring % Cfg::kStages;
+            const uint32_t ph = (ring / Cfg::kStages) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
+            const uint32_t a_lo = a_hi + kTileBytes;
+            const uint32_t b_hi = a_hi + 2 * kTileBytes;
+            const uint32_t b_lo = b_hi + Cfg::kBBytes;
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          const uint64_t dah = umma_desc_sw128(a_hi + k * 32, 16, 1024);
-          const uint64_t dal = umma_desc_sw128(a_lo + k * 32, 16, 1024);
-          const uint64_t dbh = umma_desc_sw128(b_hi + k * 32, 16, 1024);
-          const uint64_t dbl = umma_desc_sw128(b_lo + k * 32, 16, 1024);
-          umma_bf16(d_cross, dal, dbh, idesc, g > 0 ? 1u : 0u);
-          umma_bf16(d_cross, dah, dbl, idesc, 1u);
-          umma_bf16(tmem_base + rot * BN, dah, dbh, idesc, g >= p.n_main ? 1u : 0u);
-          ++g;
-          rot = (rot + 1 == p.n_main) ? 0 : rot + 1;
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t dah = umma_desc_sw128(a_hi + k * 32, 16, 1024);
+              const uint64_t dal = umma_desc_sw128(a_lo + k * 32, 16, 1024);
+              const uint64_t dbh = umma_desc_sw128(b_hi + k * 32, 16, 1024);
+              const uint64_t dbl = umma_desc_sw128(b_lo + k * 32, 16, 1024);
+              umma_bf16(d_cross, dal, dbh, idesc, fresh);
+              umma_bf16(d_cross, dah, dbl, idesc, 1u);
+              umma_bf16(d_main, dah, dbh, idesc, fresh);
+              fresh = 1u;
+            }
+            umma_commit(&empty_bar[s]);             // frees the smem stage once these MMAs have read it
+          }
+          umma_commit(&tfull_bar[buf]);             // this pass's accumulators are complete
         }
-        umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
       }
-      umma_commit(accum_bar);         // accumulator complete
     }
   } else {
-    // ---- epilogue: warp q owns TMEM lanes [32q, 32q+32) = GEMM rows
+    // ---- epilogue: warp q owns TMEM lanes [32q, 32q+32) = GEMM rows = pixels of the patch
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int tw = m % p.TW;
     const int th = (m / p.TW) % p.TH;
     const int tn = m / (p.TW * p.TH);
-    const int n_img = n0 + tn;
-    const bool row_ok = n_img < p.N;
-    const size_t pix = (static_cast<size_t>(n_img) * p.H + (h0 + th)) * p.W + (w0 + tw);
-    size_t rpix = pix;
-    if (p.res_shift) rpix = (static_cast<size_t>(n_img) * (p.H >> 1) + ((h0 + th) >> 1)) * (p.W >> 1) + ((w0 + tw) >> 1);
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
     const bool vec_ok = (p.cout & 3) == 0;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
-      __syncwarp();
-      load_accum_chunk<BN>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, p.n_main, v);
-      const int cbase = co0 + c;
-      if (!row_ok || cbase >= p.cout) continue;
+    const bool writer = (p.pool == 0) || (((tw | th) & 1) == 0);
+    const float pool_scale = (p.pool == 1) ? 0.25f : 1.0f;
+    int pass_i = 0;
+    float acc[BN];
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t % p.n_tiles;
+      const int mt = t / p.n_tiles;
+      const int w = (mt % p.tiles_w) * p.TW + tw;
+      const int h = ((mt / p.tiles_w) % p.tiles_h) * p.TH + th;
+      const int n_img = (mt / (p.tiles_w * p.tiles_h)) * p.TN + tn;
+      const int co0 = nt * BN;
+      const bool row_ok = n_img < p.N;
+      const size_t pix = (static_cast<size_t>(n_img) * p.H + h) * p.W + w;          // conv output pixel
+      size_t opix = pix;                                                            // stored pixel
+      if (p.pool) opix = (static_cast<size_t>(n_img) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+      size_t rpix = opix;                                                           // residual pixel
+      if (p.res_shift) rpix = (static_cast<size_t>(n_img) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+      // ---- gather the passes of this tile into registers (fp32 round-to-nearest adds)
+      for (int ps = 0; ps < p.n_pass; ++ps, ++pass_i) {
+        const int buf = pass_i & 1;
+        mbar_wait(&tfull_bar[buf], (pass_i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_base = tmem_base + buf * (2 * BN) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int co = cbase + j;
-        float x = v[j];
-        if (co < p.cout) {
-          if (p.bias) x += __ldg(p.bias + co);
-          if (p.residual) x += __ldg(p.residual + rpix * p.cout + co);
-        } else {
-          x = 0.f;
+        for (int c = 0; c < BN; c += 32) {
+          if (co0 + c < p.cout) add_pass_chunk<BN>(t_base + c, ps == 0, acc + c);
         }
-        v[j] = x * p.out_scale;
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[buf]);              // 128 arrivals hand the buffer back to the MMA issuer
       }
-      if (p.out) {
-        float* o = p.out + pix * p.cout + cbase;
-        if (vec_ok && cbase + 32 <= p.cout) {
+      // ---- finalize and store (the tensor core is already working on the next pass / tile)
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < 32 && cbase + j < p.cout; ++j) o[j] = v[j];
+      for (int c = 0; c < BN; c += 32) {
+        const int cbase = co0 + c;
+        if (cbase >= p.cout) continue;                                              // warp-uniform
+        float* v = acc + c;
+        // (acc + bias) * out_scale, ReLU-derivative mask
+        uint32_t mk[16];
+        const bool use_mask = p.mask_hi != nullptr;
+        if (use_mask) {
+          const __nv_bfloat16* mp = p.mask_hi + pix * p.mask_cpad + cbase;
+          if (row_ok && cbase + 32 <= p.mask_cpad) {
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(mp) + g4);
+              mk[g4 * 4] = u.x; mk[g4 * 4 + 1] = u.y; mk[g4 * 4 + 2] = u.z; mk[g4 * 4 + 3] = u.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              uint32_t lo16 = 0, hi16 = 0;
+              if (row_ok && cbase + j < p.mask_cpad) lo16 = __bfloat16_as_ushort(mp[j]);
+              if (row_ok && cbase + j + 1 < p.mask_cpad) hi16 = __bfloat16_as_ushort(mp[j + 1]);
+              mk[j >> 1] = lo16 | (hi16 << 16);
+            }
+          }
         }
-      }
-      if (p.out_hi) {
-        // split (optionally ReLU'd) copy for a following convolution; channel stride cout_pad
-        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float a = v[j], b = v[j + 1];
-          if (p.relu_split) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-          __nv_bfloat16 ah, al, bh, bl;
-          split_bf16(a, ah, al);
-          split_bf16(b, bh, bl);
-          hi[j >> 1] = pack_bf16x2(ah, bh);
-          lo[j >> 1] = pack_bf16x2(al, bl);
+        for (int j = 0; j < 32; ++j) {
+          const int co = cbase + j;
+          float x = v[j];
+          if (co < p.cout && row_ok) {
+            if (p.bias) x += __ldg(p.bias + co);
+            x *= p.out_scale;
+            if (use_mask) {
+              const uint32_t bits = (mk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+              if ((bits & 0x8000u) || (bits & 0x7FFFu) == 0) x = 0.f;              // saved activation <= 0
+            }
+          } else {
+            x = 0.f;
+          }
+          v[j] = x;
         }
-        __nv_bfloat16* oh = p.out_hi + pix * p.cout_pad + cbase;
-        __nv_bfloat16* ol = p.out_lo + pix * p.cout_pad + cbase;
-        // cout_pad is a multiple of 8 and cbase a multiple of 32: 16-byte groups of 8 channels
+        if (p.pool) {                                                               // 2x2 pooling across lanes
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (cbase + g * 8 < p.cout_pad) {
-            *reinterpret_cast<uint4*>(oh + g * 8) = make_uint4(hi[g * 4], hi[g * 4 + 1], hi[g * 4 + 2], hi[g * 4 + 3]);
-            *reinterpret_cast<uint4*>(ol + g * 8) = make_uint4(lo[g * 4], lo[g * 4 + 1], lo[g * 4 + 2], lo[g * 4 + 3]);
+          for (int j = 0; j < 32; ++j) {
+            float x = v[j];
+            x += __shfl_xor_sync(0xffffffffu, x, 1);
+            x += __shfl_xor_sync(0xffffffffu, x, p.TW);
+            v[j] = x * pool_scale;
+          }
+        }
+        if (!row_ok || !writer) continue;
+        if (p.residual) {
+          const float* rp = p.residual + rpix * p.cout + cbase;
+          if (vec_ok && cbase + 32 <= p.cout) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp + j));
+              v[j] = fmaf(p.res_scale, r4.x, v[j]); v[j + 1] = fmaf(p.res_scale, r4.y, v[j + 1]);
+              v[j + 2] = fmaf(p.res_scale, r4.z, v[j + 2]); v[j + 3] = fmaf(p.res_scale, r4.w, v[j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (cbase + j < p.cout) v[j] = fmaf(p.res_scale, __ldg(rp + j), v[j]);
+          }
+        }
+        if (p.out) {
+          float* o = p.out + opix * p.cout + cbase;
+          if (vec_ok && cbase + 32 <= p.cout) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (cbase + j < p.cout) o[j] = v[j];
+          }
+        }
+        if (p.out_hi) {
+          // split (optionally ReLU'd) copy for a following convolution; channel stride cout_pad
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float a = v[j], b = v[j + 1];
+            if (p.relu_split) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            __nv_bfloat16 ah, al, bh, bl;
+            split_bf16(a, ah, al);
+            split_bf16(b, bh, bl);
+            hi[j >> 1] = pack_bf16x2(ah, bh);
+            lo[j >> 1] = pack_bf16x2(al, bl);
+          }
+          __nv_bfloat16* oh = p.out_hi + opix * p.cout_pad + cbase;
+          __nv_bfloat16* ol = p.out_lo + opix * p.cout_pad + cbase;
+          // cout_pad is a multiple of 8 and cbase a multiple of 32: 16-byte groups of 8 channels
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (cbase + g * 8 < p.cout_pad) {
+              *reinterpret_cast<uint4*>(oh + g * 8) = make_uint4(hi[g * 4], hi[g * 4 + 1], hi[g * 4 + 2], hi[g * 4 + 3]);
+              *reinterpret_cast<uint4*>(ol + g * 8) = make_uint4(lo[g * 4], lo[g * 4 + 1], lo[g * 4 + 2], lo[g * 4 + 3]);
+            }
           }
         }
       }
@@ -251,7 +336,7 @@ struct WgCfg {
   static constexpr int kBBytes = BN * 64 * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
-  static constexpr int kTmemCols = 4 * BN;
+  static constexpr int kTmemCols = 4 * BN;   // two (main, cross) buffers
 };
 
 template <int BN>
@@ -264,8 +349,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* accum_bar = empty_bar + Cfg::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;      // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -288,7 +374,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_con
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -296,6 +385,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // passes of at most kPassLen k-iterations (144 k16 steps), nearly equal
+  const int n_pass = (k_iters + kPassLen - 1) / kPassLen;
+  const int pass_len = n_pass ? (k_iters + n_pass - 1) / n_pass : 0;
 
   if (k_iters > 0) {
     if (warp == 0) {
@@ -326,50 +418,68 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_con
     } else if (warp == 1) {
       if (lane == 0) {
         constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
-        const uint32_t d_cross = tmem_base + 3 * BN;
-        const int n_main = min(p.n_main, k_iters * 4);
-        int g = 0, rot = 0;
-        for (int it = 0; it < k_iters; ++it) {
-          const int s = it % Cfg::kStages;
-          const uint32_t ph = (it / Cfg::kStages) & 1;
-          mbar_wait(&full_bar[s], ph);
+        int it = 0;
+        for (int ps = 0; ps < n_pass; ++ps) {
+          const int buf = ps & 1;
+          mbar_wait(&tempty_bar[buf], ((ps >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
-          const uint32_t a_lo = a_hi + Cfg::kABytes;
-          const uint32_t b_hi = a_hi + 2 * Cfg::kABytes;
-          const uint32_t b_lo = b_hi + Cfg::kBBytes;
+          const uint32_t d_main = tmem_base + buf * (2 * BN);
+          const uint32_t d_cross = d_main + BN;
+          const int it_end = min(it + pass_len, k_iters);
+          uint32_t fresh = 0;
+          for (; it < it_end; ++it) {
+            const int s = it % Cfg::kStages;
+            const uint32_t ph = (it / Cfg::kStages) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
+            const uint32_t a_lo = a_hi + Cfg::kABytes;
+            const uint32_t b_hi = a_hi + 2 * Cfg::kABytes;
+            const uint32_t b_lo = b_hi + Cfg::kBBytes;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {   // 16 pixels per MMA
-            const uint64_t dah = umma_desc_sw128(a_hi + k * 2048, 8192, 1024);
-            const uint64_t dal = umma_desc_sw128(a_lo + k * 2048, 8192, 1024);
-            const uint64_t dbh = umma_desc_sw128(b_hi + k * 2048, 8192, 1024);
-            const uint64_t dbl = umma_desc_sw128(b_lo + k * 2048, 8192, 1024);
-            umma_bf16(d_cross, dal, dbh, idesc, g > 0 ? 1u : 0u);
-            umma_bf16(d_cross, dah, dbl, idesc, 1u);
-            umma_bf16(tmem_base + rot * BN, dah, dbh, idesc, g >= n_main ? 1u : 0u);
-            ++g;
-            rot = (rot + 1 == n_main) ? 0 : rot + 1;
+            for (int k = 0; k < 4; ++k) {   // 16 pixels per MMA
+              const uint64_t dah = umma_desc_sw128(a_hi + k * 2048, 8192, 1024);
+              const uint64_t dal = umma_desc_sw128(a_lo + k * 2048, 8192, 1024);
+              const uint64_t dbh = umma_desc_sw128(b_hi + k * 2048, 8192, 1024);
+              const uint64_t dbl = umma_desc_sw128(b_lo + k * 2048, 8192, 1024);
+              umma_bf16(d_cross, dal, dbh, idesc, fresh);
+              umma_bf16(d_cross, dah, dbl, idesc, 1u);
+              umma_bf16(d_main, dah, dbh, idesc, fresh);
+              fresh = 1u;
+            }
+            umma_commit(&empty_bar[s]);
           }
-          umma_commit(&empty_bar[s]);
+          umma_commit(&tfull_bar[buf]);
         }
-        umma_commit(accum_bar);
       }
     } else {
       const int q = warp & 3;
       const int co = co0 + q * 32 + lane;
-      mbar_wait(accum_bar, 0);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        float v[32];
-        __syncwarp();
-        load_accum_chunk<BN>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, min(p.n_main, k_iters * 4), v);
-        if (co >= p.cout) continue;
-        float* o = p.dw + (static_cast<size_t>(co) * p.taps + tap) * p.cin + ci0 + c;
-        if (p.atomic) {
-          for (int j = 0; j < 32 && ci0 + c + j < p.cin; ++j) atomicAdd(o + j, v[j]);
-        } else {
-          for (int j = 0; j < 32 && ci0 + c + j < p.cin; ++j) o[j] = v[j];
+      float acc[BN];
+      for (int ps = 0; ps < n_pass; ++ps) {
+        const int buf = ps & 1;
+        mbar_wait(&tfull_bar[buf], (ps >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_base = tmem_base + buf * (2 * BN) + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < BN; c += 32) {
+          if (ci0 + c < p.cin) add_pass_chunk<BN>(t_base + c, ps == 0, acc + c);
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[buf]);
+      }
+      if (co < p.cout) {
+#pragma unroll
+        for (int c = 0; c < BN; c += 32) {
+          if (ci0 + c >= p.cin) continue;
+          float* o = p.dw + (static_cast<size_t>(co) * p.taps + tap) * p.cin + ci0 + c;
+          if (p.atomic) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (ci0 + c + j < p.cin) atomicAdd(o + j, acc[c + j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (ci0 + c + j < p.cin) o[j] = acc[c + j];
+          }
         }
       }
     }
@@ -438,12 +548,6 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int box_
   return L2I_OK;
 }
 
-// hi*hi accumulators to rotate over so that no TMEM accumulation chain exceeds ~144-192 adds
-static int main_accumulators(int k16_steps) {
-  int n = (k16_steps + 143) / 144;
-  return n < 1 ? 1 : (n > 3 ? 3 : n);
-}
-
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // pick a (tw, th, tn) patch of exactly `pixels` pixels
@@ -456,9 +560,19 @@ static int pick_tile(int H, int W, int pixels, int* tw, int* th, int* tn) {
   return L2I_OK;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN>
 static int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-                      const CUtensorMap& b_lo, const ConvFwdParams& p, dim3 grid, cudaStream_t stream) {
+                      const CUtensorMap& b_lo, const ConvFwdParams& p, int grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<BN>::kSmem);
@@ -474,25 +588,36 @@ int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream) {
   if (a.cin_pad % 8 || a.cin_pad <= 0 || a.cout <= 0 || a.N <= 0) { set_error("conv: bad channel/batch sizes (cin_pad=%d cout=%d N=%d)", a.cin_pad, a.cout, a.N); return L2I_ERR_BAD_ARG; }
   if (!a.x_hi || !a.x_lo || !a.w_hi || !a.w_lo || (!a.out && !a.out_hi)) { set_error("conv: null operand pointer"); return L2I_ERR_BAD_ARG; }
   if (a.out_hi && (a.cout_pad % 8 || a.cout_pad < a.cout)) { set_error("conv: cout_pad must be a multiple of 8 >= cout"); return L2I_ERR_BAD_ARG; }
-  if (a.res_shift && ((a.H | a.W) & 1)) { set_error("conv: upsampled residual needs even H, W"); return L2I_ERR_BAD_ARG; }
+  if (a.pool < 0 || a.pool > 2) { set_error("conv: pool must be 0 (none), 1 (2x2 average) or 2 (2x2 sum)"); return L2I_ERR_BAD_ARG; }
+  if ((a.res_shift || a.pool) && (((a.H | a.W) & 1) || a.H < 2 || a.W < 2)) { set_error("conv: pooling / upsampled residual need even H, W"); return L2I_ERR_BAD_ARG; }
+  if (a.res_shift && a.pool) { set_error("conv: pooled output with an upsampled residual is not supported"); return L2I_ERR_UNSUPPORTED; }
+  if (a.mask_hi && (a.mask_cpad % 8 || a.mask_cpad < a.cout)) { set_error("conv: mask channel stride must be a multiple of 8 >= cout"); return L2I_ERR_BAD_ARG; }
   ConvFwdParams p;
   p.N = a.N; p.H = a.H; p.W = a.W; p.cin_pad = a.cin_pad; p.cout = a.cout; p.taps = a.taps;
   if (pick_tile(a.H, a.W, 128, &p.TW, &p.TH, &p.TN) != L2I_OK) { set_error("conv: H=%d W=%d must be powers of two", a.H, a.W); return L2I_ERR_UNSUPPORTED; }
   p.tiles_w = a.W / p.TW; p.tiles_h = a.H / p.TH;
   const int tiles_n = (a.N + p.TN - 1) / p.TN;
   p.kchunks = (a.cin_pad + kBK - 1) / kBK;
-  p.n_main = main_accumulators(a.taps * p.kchunks * (kBK / 16));
-  p.bias = a.bias; p.residual = a.residual; p.res_shift = a.res_shift; p.out = a.out;
+  {
+    const int k_iters = a.taps * p.kchunks;
+    p.n_pass = (k_iters + kPassLen - 1) / kPassLen;
+    p.pass_len = (k_iters + p.n_pass - 1) / p.n_pass;
+  }
+  p.bias = a.bias; p.residual = a.residual; p.res_shift = a.res_shift; p.res_scale = a.res_scale; p.out = a.out;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(a.out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(a.out_lo);
   p.cout_pad = a.cout_pad; p.relu_split = a.relu_split; p.out_scale = a.out_scale;
+  p.mask_hi = reinterpret_cast<const __nv_bfloat16*>(a.mask_hi); p.mask_cpad = a.mask_cpad; p.pool = a.pool;
   const int BN = (a.cout > 64) ? 128 : 64;
+  p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+  p.n_tiles = (a.cout + BN - 1) / BN;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
   if ((rc = make_act_map(&ta_hi, a.x_hi, a.N, a.H, a.W, a.cin_pad, p.TW, p.TH, p.TN))) return rc;
   if ((rc = make_act_map(&ta_lo, a.x_lo, a.N, a.H, a.W, a.cin_pad, p.TW, p.TH, p.TN))) return rc;
   if ((rc = make_w_map(&tb_hi, a.w_hi, a.cout, a.taps * a.cin_pad, BN))) return rc;
   if ((rc = make_w_map(&tb_lo, a.w_lo, a.cout, a.taps * a.cin_pad, BN))) return rc;
-  dim3 grid(p.tiles_w * p.tiles_h * tiles_n, (a.cout + BN - 1) / BN);
+  const long long total = 1LL * p.m_tiles * p.n_tiles;
+  const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
   if (BN == 128) return launch_fwd<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
   return launch_fwd<64>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
 }
@@ -532,7 +657,6 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t stream) {
   p.blocks_per_split = (p.pix_blocks + splits - 1) / splits;
   splits = (p.pix_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
   p.atomic = splits > 1;
-  p.n_main = main_accumulators(p.blocks_per_split * 4);
   p.dw = a.dw;
   if (p.atomic) {
     cudaError_t e = cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.cout * a.taps * a.cin, stream);

@@ -8,7 +8,12 @@ namespace l2i {
 struct ConvFwdParams {          // device-side view
   int N, H, W, cin_pad, cout, taps;
   int TW, TH, TN, tiles_w, tiles_h, kchunks;
-  int n_main;                   // hi*hi accumulators rotated over (1..3)
+  int n_pass, pass_len;         // K loop = n_pass passes of pass_len (tap, chunk) iterations, one TMEM buffer each
+  int m_tiles, n_tiles;         // persistent tile list: tile t -> (t / n_tiles, t % n_tiles)
+  const __nv_bfloat16* mask_hi; // [N,H,W,mask_cpad]: output element is zeroed where mask_hi <= 0 (ReLU backward), or null
+  int mask_cpad;
+  int pool;                     // 0 none, 1 = 2x2 average, 2 = 2x2 sum of the conv output (stored at H/2 x W/2)
+  float res_scale;
   const float* bias;            // [cout] or null
   const float* residual;        // [N,H,W,cout] (res_shift=0) or [N,H/2,W/2,cout] nearest-x2 (res_shift=1), or null
   int res_shift;
@@ -30,11 +35,14 @@ struct ConvFwdArgs {            // host-side call
   void *out_hi, *out_lo;
   int cout_pad, relu_split;
   float out_scale;
+  const void* mask_hi;
+  int mask_cpad, pool;
+  float res_scale;
 };
 
 struct ConvWgradParams {
   int N, H, W, cin, cout, taps;
-  int TW, TH, TN, tiles_w, tiles_h, pix_blocks, blocks_per_split, cin_tiles, atomic, n_main;
+  int TW, TH, TN, tiles_w, tiles_h, pix_blocks, blocks_per_split, cin_tiles, atomic;
   float* dw;                    // [cout][taps][cin] fp32
 };
 

@@ -66,7 +66,7 @@ struct AdamTensor {       // one entry of the device-resident tensor table (48 b
   float lr;
   int pad_;
 };
-int adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, float beta1, float beta2, float eps,
-              float bc1, float bc2_sqrt, cudaStream_t stream);
+int adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, double beta1, double beta2, double eps,
+              double bc1, double bc2_sqrt, cudaStream_t stream);
 
 }  // namespace l2i

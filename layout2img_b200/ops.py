@@ -71,26 +71,33 @@ def act_split(x: torch.Tensor, relu: bool = False, up2: bool = False) -> Pair:
 
 def conv2d_fwd(x: Pair, w_hi: torch.Tensor, w_lo: torch.Tensor, cout: int, taps: int,
                bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-               res_up2: bool = False, out_scale: float = 1.0, want_f32: bool = True,
+               res_up2: bool = False, res_scale: float = 1.0, out_scale: float = 1.0,
+               mask_hi: Optional[torch.Tensor] = None, pool: int = 0, want_f32: bool = True,
                want_pair: bool = False, relu_pair: bool = False):
-    """(conv(x, w) + bias + residual) * out_scale -> (fp32 NHWC or None, Pair or None)."""
+    """pool((conv(x, w) + bias) * out_scale * [mask_hi > 0]) + res_scale * residual
+    -> (fp32 NHWC or None, Pair or None); see include/l2i.h."""
     n, h, w_, cin_pad = x.hi.shape
     if w_hi.shape != (cout, taps, cin_pad):
         raise ValueError(f"weight operand {tuple(w_hi.shape)} does not match ({cout},{taps},{cin_pad})")
-    out = torch.empty((n, h, w_, cout), dtype=torch.float32, device=x.hi.device) if want_f32 else None
+    ho, wo = (h // 2, w_ // 2) if pool else (h, w_)
+    out = torch.empty((n, ho, wo, cout), dtype=torch.float32, device=x.hi.device) if want_f32 else None
     pair = None
     if want_pair:
-        buf = torch.empty((2, n, h, w_, pad8(cout)), dtype=torch.bfloat16, device=x.hi.device)
-        if pad8(cout) != cout:
-            buf.zero_()
+        buf = torch.empty((2, n, ho, wo, pad8(cout)), dtype=torch.bfloat16, device=x.hi.device)
         pair = Pair(buf[0], buf[1], cout)
     if residual is not None:
         _chk(residual)
-        exp = (n, h // 2, w_ // 2, cout) if res_up2 else (n, h, w_, cout)
+        exp = (n, ho // 2, wo // 2, cout) if res_up2 else (n, ho, wo, cout)
         if tuple(residual.shape) != exp:
             raise ValueError(f"residual shape {tuple(residual.shape)} != {exp}")
+    mask_cpad = 0
+    if mask_hi is not None:
+        if mask_hi.dtype != torch.bfloat16 or tuple(mask_hi.shape[:3]) != (n, h, w_) or not mask_hi.is_contiguous():
+            raise ValueError("mask_hi must be a contiguous bf16 (N,H,W,Cpad) tensor at the conv's resolution")
+        mask_cpad = mask_hi.shape[3]
     call("l2i_conv2d_fwd", n, h, w_, cin_pad, cout, taps, x.hi, x.lo, w_hi, w_lo, bias, residual, int(res_up2),
-         float(out_scale), out, pair.hi if pair else None, pair.lo if pair else None, pad8(cout), int(relu_pair))
+         float(res_scale), float(out_scale), mask_hi, mask_cpad, int(pool), out, pair.hi if pair else None,
+         pair.lo if pair else None, pad8(cout), int(relu_pair))
     return out, pair
 
 

@@ -154,9 +154,11 @@ def test_train_step_matches_oracle_and_reference(name):
     for n in O.param_names(r32["PD"]):
         want = r32["d." + n]
         noise = (want.double() - r64["d." + n]).abs().max().item()
-        # sampled elements + moments recorded from the unmodified reference; same kink allowance as grad_close
+        # 64 sampled elements + moments recorded from the unmodified reference.  No per-element outlier
+        # budget is possible on a sample, so the bound is grad_close's outer one (a kink crossing may move an
+        # element by a few 1e-3 of max|ref|; a wrong formula moves it by O(max|ref|)).
         assert_summary_close(grads["d." + n].cpu(), z[f"train.dgrad.{n}"], 2e-3,
-                             1e-5 + 5e-3 * want.abs().max().item() + 4 * noise, "D grad vs golden " + n)
+                             1e-5 + 2e-2 * want.abs().max().item() + 4 * noise, "D grad vs golden " + n)
     sdG, sdD = G.state_dict(), D.state_dict()
     for n, v in r32["PG"].items():
         close(sdG[n].float(), v.float(), 1e-3, 2e-4, "G state " + n)

@@ -83,6 +83,35 @@ def test_conv_prologue_epilogue_fusions(dev):
     close(wg.grad, wr.grad, 1e-3, 1e-3, what="dw")
 
 
+@pytest.mark.parametrize("N,Cin,Cout,H,pool,taps", [(3, 64, 128, 16, 1, 9), (2, 128, 64, 8, 2, 9), (9, 72, 100, 4, 1, 1),
+                                                   (2, 64, 3, 32, 2, 9), (150, 64, 128, 16, 1, 9)])
+def test_conv_epilogue_mask_pool_residual_pair(dev, N, Cin, Cout, H, pool, taps):
+    """The fused epilogue of l2i_conv2d_fwd: ReLU-derivative mask from a saved bf16 activation, 2x2
+    average/sum pooling, scaled residual at the stored resolution, (ReLU'd) pair output -- against the
+    unfused fp64 composition.  N=150 gives more tiles than SMs (persistent loop, both TMEM buffers)."""
+    from layout2img_b200 import ops
+    g = torch.Generator().manual_seed(N + Cin + Cout + H + pool)
+    k = 3 if taps == 9 else 1
+    x = torch.randn(N, Cin, H, H, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * taps) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    act = torch.randn(N, Cout, H, H, generator=g)                    # the saved activation whose sign masks
+    res = torch.randn(N, Cout, H // 2, H // 2, generator=g)
+    v = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2) * (act.double() > 0)
+    v = F.avg_pool2d(v, 2) * (1.0 if pool == 1 else 4.0)
+    ref = v + 0.25 * res.double()
+    xp = ops.act_split(nhwc(x).to(dev))
+    wp = ops.conv_weight_prep(w.to(dev), need_dgrad=False)
+    mask = ops.act_split(nhwc(act).to(dev), relu=True)               # mask_hi = hi half of relu(act)
+    out, pair = ops.conv2d_fwd(xp, wp.f_hi, wp.f_lo, Cout, taps, bias=b.to(dev), residual=nhwc(res).to(dev),
+                               res_scale=0.25, mask_hi=mask.hi, pool=pool, want_f32=True, want_pair=True, relu_pair=True)
+    scale = max(ref.abs().max().item(), 1.0)
+    close(out.permute(0, 3, 1, 2), ref, 1e-3, 1e-4 * scale, "pooled masked conv")
+    got_pair = (pair.hi.float() + pair.lo.float())[..., :Cout].permute(0, 3, 1, 2)
+    close(got_pair, F.relu(ref), 1e-3, 1e-4 * scale, "relu pair output")
+    assert pair.hi.shape[-1] % 8 == 0 and float(pair.hi[..., Cout:].abs().sum()) == 0.0
+
+
 @pytest.mark.parametrize("name", ["C", "Cpad", "V"])
 def test_bbox_mask_bit_exact_against_reference_golden(dev, name):
     from layout2img_b200 import ops
