@@ -41,6 +41,19 @@ int l2i_conv_weight_prep(const float* w, const float* sigma, int cout, int cin, 
 int l2i_act_split(const float* x, int N, int H, int W, int C, int relu, int up2, void* hi, void* lo, int cpad,
                   void* stream);
 
+/* Residual-block operand preparation: one read of x [N,H,W,C] fp32 gives pair a = relu_a ? relu(x) : x at
+ * full resolution and, for b_mode 1 / 2, pair b = x / avgpool2x2(x) (never ReLU'd) -- the inputs of conv1 and
+ * of the 1x1 shortcut of rcnn_discriminator_app.py:294-344. */
+int l2i_act_split2(const float* x, int N, int H, int W, int C, int relu_a, void* a_hi, void* a_lo, int b_mode,
+                   void* b_hi, void* b_lo, int cpad, void* stream);
+/* Gradient arriving at a block output, g [N,H,W,C] fp32: pair (lo_hi, lo_lo) = g (nullable), pair (up_hi, up_lo)
+ * = up_scale * nearest_x2(g) at [N,2H,2W,cpad] (nullable; up_scale 0.25 = backward of avg_pool2d), and
+ * colsum [C] = sum over pixels of g (the bias gradients). */
+int l2i_grad_split(const float* g, int N, int H, int W, int C, void* lo_hi, void* lo_lo, float up_scale, void* up_hi,
+                   void* up_lo, float* colsum, int cpad, void* stream);
+/* colsum [C] = sum over pixels of (hi + lo) [pixels, cpad]. */
+int l2i_pair_colsum(const void* hi, const void* lo, long long pixels, int C, int cpad, float* colsum, void* stream);
+
 /* v = (conv(x, w) + bias) * out_scale, stride 1, "same" padding; H, W powers of two.
  * x pair [N,H,W,cin_pad]; w pair [cout][taps][cin_pad]; bias [cout] or NULL.
  * mask_hi (nullable): bf16 [N,H,W,mask_cpad]; v is zeroed where mask_hi <= 0 -- the ReLU derivative taken

@@ -46,6 +46,18 @@ int l2i_act_split(const float* x, int N, int H, int W, int C, int relu, int up2,
   return act_split(x, N, H, W, C, relu, up2, hi, lo, cpad, ST(stream));
 }
 
+int l2i_act_split2(const float* x, int N, int H, int W, int C, int relu_a, void* a_hi, void* a_lo, int b_mode,
+                   void* b_hi, void* b_lo, int cpad, void* stream) {
+  return act_split2(x, N, H, W, C, relu_a, a_hi, a_lo, b_mode, b_hi, b_lo, cpad, ST(stream));
+}
+int l2i_grad_split(const float* g, int N, int H, int W, int C, void* lo_hi, void* lo_lo, float up_scale, void* up_hi,
+                   void* up_lo, float* colsum, int cpad, void* stream) {
+  return grad_split(g, N, H, W, C, lo_hi, lo_lo, up_scale, up_hi, up_lo, colsum, cpad, ST(stream));
+}
+int l2i_pair_colsum(const void* hi, const void* lo, long long pixels, int C, int cpad, float* colsum, void* stream) {
+  return pair_colsum(hi, lo, pixels, C, cpad, colsum, ST(stream));
+}
+
 int l2i_conv2d_fwd(int N, int H, int W, int cin_pad, int cout, int taps, const void* x_hi, const void* x_lo,
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, int res_up2,
                    float res_scale, float out_scale, const void* mask_hi, int mask_cpad, int pool, float* out, void* out_hi,

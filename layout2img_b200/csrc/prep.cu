@@ -115,3 +115,198 @@ int act_split(const float* x, int N, int H, int W, int C, int relu, int up2, voi
 }
 
 }  // namespace l2i
+
+// ------------------------------------------------------------------------------------------------
+// Block-level operand preparation for the discriminator / generator residual blocks
+// (reference rcnn_discriminator_app.py:294-344): one read of a tensor produces every operand
+// pair the block's convolutions need, and the per-channel sums that are the bias gradients.
+// ------------------------------------------------------------------------------------------------
+namespace l2i {
+
+__device__ __forceinline__ void load8(const float* src, int c0, int C, float (&v)[8]) {
+  if ((C & 3) == 0 && c0 + 8 <= C) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? __ldg(src + j) : 0.f;
+  }
+}
+
+__device__ __forceinline__ void store_pair8(const float (&v)[8], __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    __nv_bfloat16 ah, al, bh, bl;
+    split_bf16(v[j], ah, al);
+    split_bf16(v[j + 1], bh, bl);
+    ph[j >> 1] = pack_bf16x2(ah, bh);
+    pl[j >> 1] = pack_bf16x2(al, bl);
+  }
+  *reinterpret_cast<uint4*>(hi) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  *reinterpret_cast<uint4*>(lo) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+// a = relu?(x) at full resolution; b = x (b_mode 1) or avgpool2(x) (b_mode 2), never ReLU'd.
+// One thread: 8 channels of one pixel (b_mode 0/1) or of one 2x2 quad (b_mode 2).
+__global__ void act_split2_kernel(const float* __restrict__ x, int N, int H, int W, int C, int relu_a,
+                                  __nv_bfloat16* __restrict__ a_hi, __nv_bfloat16* __restrict__ a_lo, int b_mode,
+                                  __nv_bfloat16* __restrict__ b_hi, __nv_bfloat16* __restrict__ b_lo, int cpad) {
+  const int groups = cpad >> 3;
+  const int sh = (b_mode == 2) ? 1 : 0;
+  const int Hq = H >> sh, Wq = W >> sh;
+  const long long total = 1LL * N * Hq * Wq * groups;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    const long long q = i / groups;
+    const int wq = static_cast<int>(q % Wq);
+    const int hq = static_cast<int>((q / Wq) % Hq);
+    const int n = static_cast<int>(q / (1LL * Wq * Hq));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int reps = sh ? 2 : 1;
+    for (int dy = 0; dy < reps; ++dy) {
+      for (int dx = 0; dx < reps; ++dx) {
+        const long long pix = (1LL * n * H + (hq << sh) + dy) * W + (wq << sh) + dx;
+        float v[8];
+        load8(x + pix * C + g * 8, g * 8, C, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        if (relu_a) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        store_pair8(v, a_hi + pix * cpad + g * 8, a_lo + pix * cpad + g * 8);
+      }
+    }
+    if (b_mode) {
+      if (sh) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
+      }
+      store_pair8(acc, b_hi + q * cpad + g * 8, b_lo + q * cpad + g * 8);
+    }
+  }
+}
+
+int act_split2(const float* x, int N, int H, int W, int C, int relu_a, void* a_hi, void* a_lo, int b_mode, void* b_hi,
+               void* b_lo, int cpad, cudaStream_t stream) {
+  if (!x || !a_hi || !a_lo || N <= 0 || H <= 0 || W <= 0 || C <= 0 || cpad < C || cpad % 8 || b_mode < 0 || b_mode > 2 ||
+      (b_mode && (!b_hi || !b_lo)) || (b_mode == 2 && ((H | W) & 1))) {
+    set_error("act_split2: bad arguments (N=%d H=%d W=%d C=%d cpad=%d b_mode=%d)", N, H, W, C, cpad, b_mode);
+    return L2I_ERR_BAD_ARG;
+  }
+  const int sh = (b_mode == 2) ? 1 : 0;
+  const long long total = 1LL * N * (H >> sh) * (W >> sh) * (cpad >> 3);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  act_split2_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+      x, N, H, W, C, relu_a, reinterpret_cast<__nv_bfloat16*>(a_hi), reinterpret_cast<__nv_bfloat16*>(a_lo), b_mode,
+      reinterpret_cast<__nv_bfloat16*>(b_hi), reinterpret_cast<__nv_bfloat16*>(b_lo), cpad);
+  return check_launch("act_split2_kernel");
+}
+
+// Per-channel sums: thread t of a 256-thread block owns channel group t % groups of pixel slot t / groups.
+// MODE 0: g fp32 [P, C] -> pair `lo` at the same resolution, optional pair `up` = up_scale * nearest-x2(g),
+//         colsum[c] += sum_p g[p, c].          (gradient arriving at a residual block's output)
+// MODE 1: (hi, lo) pair [P, cpad] -> colsum only.   (bias gradient of a conv whose output gradient is a pair)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+colsum_split_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ in_hi,
+                    const __nv_bfloat16* __restrict__ in_lo, int N, int H, int W, int C, int cpad,
+                    __nv_bfloat16* __restrict__ lo_hi, __nv_bfloat16* __restrict__ lo_lo, float up_scale,
+                    __nv_bfloat16* __restrict__ up_hi, __nv_bfloat16* __restrict__ up_lo, float* __restrict__ colsum) {
+  extern __shared__ float s_sum[];          // [cpad]
+  const int groups = cpad >> 3;
+  const int ppb = 256 / groups;
+  const int grp = threadIdx.x % groups;
+  const int slot = threadIdx.x / groups;
+  for (int i = threadIdx.x; i < cpad; i += 256) s_sum[i] = 0.f;
+  __syncthreads();
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const long long P = 1LL * N * H * W;
+  if (slot < ppb) {
+    for (long long pix = 1LL * blockIdx.x * ppb + slot; pix < P; pix += 1LL * gridDim.x * ppb) {
+      float v[8];
+      if (MODE == 0) {
+        load8(g + pix * C + grp * 8, grp * 8, C, v);
+        if (lo_hi) store_pair8(v, lo_hi + pix * cpad + grp * 8, lo_lo + pix * cpad + grp * 8);
+        if (up_hi) {
+          const int w = static_cast<int>(pix % W);
+          const int h = static_cast<int>((pix / W) % H);
+          const long long n = pix / (1LL * W * H);
+          float u[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) u[j] = v[j] * up_scale;
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              const long long op = (n * (2 * H) + 2 * h + dy) * (2 * W) + 2 * w + dx;
+              store_pair8(u, up_hi + op * cpad + grp * 8, up_lo + op * cpad + grp * 8);
+            }
+        }
+      } else {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(in_hi + pix * cpad + grp * 8));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(in_lo + pix * cpad + grp * 8));
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[2 * j] = __uint_as_float(aw[j] << 16) + __uint_as_float(bw[j] << 16);
+          v[2 * j + 1] = __uint_as_float(aw[j] & 0xFFFF0000u) + __uint_as_float(bw[j] & 0xFFFF0000u);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_sum[grp * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) atomicAdd(colsum + c, s_sum[c]);
+}
+
+static int colsum_grid(long long P, int ppb) {
+  long long blocks = (P + ppb - 1) / ppb;
+  // enough pixels per thread that the shared/global atomics are noise, enough blocks to fill the chip
+  long long cap = 148 * 8;
+  if (blocks > cap) blocks = cap;
+  return static_cast<int>(blocks < 1 ? 1 : blocks);
+}
+
+int grad_split(const float* g, int N, int H, int W, int C, void* lo_hi, void* lo_lo, float up_scale, void* up_hi,
+               void* up_lo, float* colsum, int cpad, cudaStream_t stream) {
+  if (!g || N <= 0 || H <= 0 || W <= 0 || C <= 0 || cpad < C || cpad % 8 || cpad > 2048 || !colsum ||
+      (lo_hi && !lo_lo) || (up_hi && !up_lo)) {
+    set_error("grad_split: bad arguments (N=%d H=%d W=%d C=%d cpad=%d)", N, H, W, C, cpad);
+    return L2I_ERR_BAD_ARG;
+  }
+  cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * C, stream);
+  if (e != cudaSuccess) { set_error("grad_split: memset failed: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
+  const int ppb = 256 / (cpad >> 3);
+  colsum_split_kernel<0><<<colsum_grid(1LL * N * H * W, ppb), 256, cpad * sizeof(float), stream>>>(
+      g, nullptr, nullptr, N, H, W, C, cpad, reinterpret_cast<__nv_bfloat16*>(lo_hi),
+      reinterpret_cast<__nv_bfloat16*>(lo_lo), up_scale, reinterpret_cast<__nv_bfloat16*>(up_hi),
+      reinterpret_cast<__nv_bfloat16*>(up_lo), colsum);
+  return check_launch("colsum_split_kernel<0>");
+}
+
+int pair_colsum(const void* hi, const void* lo, long long pixels, int C, int cpad, float* colsum, cudaStream_t stream) {
+  if (!hi || !lo || pixels <= 0 || C <= 0 || cpad < C || cpad % 8 || cpad > 2048 || !colsum) {
+    set_error("pair_colsum: bad arguments (pixels=%lld C=%d cpad=%d)", pixels, C, cpad);
+    return L2I_ERR_BAD_ARG;
+  }
+  cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * C, stream);
+  if (e != cudaSuccess) { set_error("pair_colsum: memset failed: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
+  const int ppb = 256 / (cpad >> 3);
+  colsum_split_kernel<1><<<colsum_grid(pixels, ppb), 256, cpad * sizeof(float), stream>>>(
+      nullptr, reinterpret_cast<const __nv_bfloat16*>(hi), reinterpret_cast<const __nv_bfloat16*>(lo), 1, 1,
+      static_cast<int>(pixels), C, cpad, nullptr, nullptr, 1.f, nullptr, nullptr, colsum);
+  return check_launch("colsum_split_kernel<1>");
+}
+
+}  // namespace l2i

@@ -66,6 +66,81 @@ def conv2d(x, weight, bias=None, residual=None, relu_in=False, up2_in=False, res
     return ConvFn.apply(x, weight, bias, residual, relu_in, up2_in, res_up2)
 
 
+class DBlockFn(torch.autograd.Function):
+    """A whole discriminator residual block (reference rcnn_discriminator_app.py:294-344) as one autograd node:
+
+        OptimizedBlock:  pool(conv2(relu(conv1(x)))) + c_sc(pool(x))
+        ResBlock:        pool?(conv2(relu(conv1(relu(x))))) + pool?(c_sc(x))   |   ... + x  (no learnable shortcut)
+
+    Forward = 1 operand-preparation kernel + 3 tensor-core convolutions; the 1x1 shortcut runs on the pooled
+    input (it commutes with average pooling) and its result is added after the 2x2 pooling in conv2's
+    epilogue; the intermediate activation only ever exists as the ReLU'd bf16 pair conv2 consumes.
+    Backward = 1 gradient-split kernel (+ bias gradients), 3 weight-gradient and 3 data-gradient launches;
+    the ReLU derivatives are applied in the data-gradient epilogues from the saved pairs."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, wsc, bsc, down, optimized):
+        x = _c(x)
+        has_sc = wsc is not None
+        if down and not has_sc:
+            raise ValueError("a down-sampling block needs its 1x1 shortcut")
+        need_dx = ctx.needs_input_grad[0]
+        a0, s0 = ops.act_split2(x, relu_a=not optimized, b_mode=(2 if down else 1) if has_sc else 0)
+        c1, cin = w1.shape[0], w1.shape[1]
+        c2 = w2.shape[0]
+        wp1 = ops.conv_weight_prep(_c(w1), need_dgrad=need_dx)
+        wp2 = ops.conv_weight_prep(_c(w2), need_dgrad=True)
+        _, a1 = ops.conv2d_fwd(a0, wp1.f_hi, wp1.f_lo, c1, 9, bias=_c(b1), want_f32=False, want_pair=True, relu_pair=True)
+        if has_sc:
+            wps = ops.conv_weight_prep(_c(wsc), need_dgrad=need_dx)
+            sc, _ = ops.conv2d_fwd(s0, wps.f_hi, wps.f_lo, c2, 1, bias=_c(bsc))
+        else:
+            wps, sc = None, x
+        out, _ = ops.conv2d_fwd(a1, wp2.f_hi, wp2.f_lo, c2, 9, bias=_c(b2), residual=sc, pool=1 if down else 0)
+        ctx.save_for_backward(a0.hi, a0.lo, s0.hi if has_sc else None, s0.lo if has_sc else None, a1.hi, a1.lo,
+                              wp1.d_hi, wp1.d_lo, wp2.d_hi, wp2.d_lo, wps.d_hi if has_sc else None,
+                              wps.d_lo if has_sc else None)
+        ctx.meta = (cin, c1, c2, down, optimized, has_sc)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a0h, a0l, s0h, s0l, a1h, a1l, d1h, d1l, d2h, d2l, dsh, dsl = ctx.saved_tensors
+        cin, c1, c2, down, optimized, has_sc = ctx.meta
+        need = ctx.needs_input_grad
+        dout = _c(dout)
+        g_lo, g_up, colsum = ops.grad_split(dout, want_lo=has_sc or not down, up=down, up_scale=0.25)
+        g_full = g_up if down else g_lo                      # gradient at conv2's output resolution
+        a0, a1 = ops.Pair(a0h, a0l, cin), ops.Pair(a1h, a1l, c1)
+        dw1 = db1 = dw2 = db2 = dwsc = dbsc = dx = None
+        if need[3]:
+            dw2 = _dw_to_torch(ops.conv2d_wgrad(g_full, a1, 9), c2, c1, 9)
+        if need[4]:
+            db2 = colsum
+        if has_sc and need[5]:
+            dwsc = _dw_to_torch(ops.conv2d_wgrad(g_lo, ops.Pair(s0h, s0l, cin), 1), c2, cin, 1)
+        if has_sc and need[6]:
+            dbsc = colsum.clone() if need[4] else colsum
+        if need[0] or need[1] or need[2]:
+            _, d1 = ops.conv2d_fwd(g_full, d2h, d2l, c1, 9, mask_hi=a1h, want_f32=False, want_pair=True)
+            if need[1]:
+                dw1 = _dw_to_torch(ops.conv2d_wgrad(d1, a0, 9), c1, cin, 9)
+            if need[2]:
+                db1 = ops.pair_colsum(d1)
+            if need[0]:
+                if has_sc:
+                    r, _ = ops.conv2d_fwd(g_lo, dsh, dsl, cin, 1)
+                else:
+                    r = dout
+                dx, _ = ops.conv2d_fwd(d1, d1h, d1l, cin, 9, mask_hi=None if optimized else a0h, residual=r,
+                                       res_up2=down, res_scale=0.25 if down else 1.0)
+        return dx, dw1, db1, dw2, db2, dwsc, dbsc, None, None
+
+
+def d_block(x, w1, b1, w2, b2, wsc=None, bsc=None, down=False, optimized=False):
+    return DBlockFn.apply(x, w1, b1, w2, b2, wsc, bsc, down, optimized)
+
+
 class NormConvFn(torch.autograd.Function):
     """y = conv(up2?(relu(norm(x))), W) + bias + residual with norm = ISLA (mask_pm given) or affine/plain
     batch norm (mask_pm None).  reference: ResBlock.residual resnet_generator_app_v2.py:653-663,

@@ -14,7 +14,7 @@ __all__ = ["CombineDiscriminator128_app", "ResnetDiscriminator128_app", "Optimiz
 
 
 class OptimizedBlock(nn.Module):
-    """reference :294-314: pool(conv2(relu(conv1 x))) + c_sc(pool x)."""
+    """reference :294-314: pool(conv2(relu(conv1 x))) + c_sc(pool x) -- one fused autograd node (functional.DBlockFn)."""
 
     def __init__(self, in_ch, out_ch, ksize=3, pad=1, downsample=False):
         super().__init__()
@@ -25,17 +25,16 @@ class OptimizedBlock(nn.Module):
         self.downsample = downsample
 
     def forward(self, in_feat):                      # NHWC
-        x = self.conv1(in_feat)
-        x = self.conv2(x, relu_in=True)
-        if self.downsample:
-            x = avg_pool2(x)
-            return self.c_sc(avg_pool2(in_feat), residual=x)
-        return self.c_sc(in_feat, residual=x)
+        for m in (self.conv1, self.conv2, self.c_sc):
+            fire_param_hooks(m)                      # spectral-norm power iteration + W / sigma
+        return L.d_block(in_feat, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
+                         self.c_sc.weight, self.c_sc.bias, down=self.downsample, optimized=True)
 
 
 class ResBlock(nn.Module):
-    """reference :317-344: pool?(conv2(relu(conv1(relu x)))) + pool?(c_sc x).  Average pooling is
-    linear, so the shortcut is added in conv2's epilogue and the sum is pooled once."""
+    """reference :317-344: pool?(conv2(relu(conv1(relu x)))) + pool?(c_sc x).  The 1x1 shortcut commutes with
+    average pooling, so it runs on the pooled input and is added after the pooling in conv2's epilogue
+    (functional.DBlockFn)."""
 
     def __init__(self, in_ch, out_ch, ksize=3, pad=1, downsample=False):
         super().__init__()
@@ -48,12 +47,13 @@ class ResBlock(nn.Module):
             self.c_sc = conv2d(in_ch, out_ch, 1, 1, 0)
 
     def forward(self, in_feat):                      # NHWC
-        x = self.conv1(in_feat, relu_in=True)
-        sc = self.c_sc(in_feat) if self.learnable_sc else in_feat
-        x = self.conv2(x, relu_in=True, residual=sc)
-        if self.downsample:
-            x = avg_pool2(x)
-        return x
+        mods = (self.conv1, self.conv2, self.c_sc) if self.learnable_sc else (self.conv1, self.conv2)
+        for m in mods:
+            fire_param_hooks(m)
+        sc_w = self.c_sc.weight if self.learnable_sc else None
+        sc_b = self.c_sc.bias if self.learnable_sc else None
+        return L.d_block(in_feat, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
+                         sc_w, sc_b, down=self.downsample, optimized=False)
 
 
 class ResnetDiscriminator128_app(nn.Module):

@@ -69,6 +69,41 @@ def act_split(x: torch.Tensor, relu: bool = False, up2: bool = False) -> Pair:
     return Pair(out[0], out[1], c)
 
 
+def act_split2(x: torch.Tensor, relu_a: bool, b_mode: int):
+    """x (N,H,W,C) -> (pair a = relu_a ? relu(x) : x, pair b = None | x | avgpool2(x))  [b_mode 0 | 1 | 2]."""
+    _chk(x)
+    n, h, w, c = x.shape
+    cp = pad8(c)
+    a = torch.empty((2, n, h, w, cp), dtype=torch.bfloat16, device=x.device)
+    b = None
+    if b_mode == 1:
+        b = torch.empty((2, n, h, w, cp), dtype=torch.bfloat16, device=x.device)
+    elif b_mode == 2:
+        b = torch.empty((2, n, h // 2, w // 2, cp), dtype=torch.bfloat16, device=x.device)
+    call("l2i_act_split2", x, n, h, w, c, int(relu_a), a[0], a[1], int(b_mode), b[0] if b is not None else None,
+         b[1] if b is not None else None, cp)
+    return Pair(a[0], a[1], c), (Pair(b[0], b[1], c) if b is not None else None)
+
+
+def grad_split(g: torch.Tensor, want_lo: bool = True, up: bool = False, up_scale: float = 0.25):
+    """g (N,H,W,C) fp32 -> (pair of g | None, pair of up_scale * nearest_x2(g) | None, colsum (C,))."""
+    _chk(g)
+    n, h, w, c = g.shape
+    cp = pad8(c)
+    lo = torch.empty((2, n, h, w, cp), dtype=torch.bfloat16, device=g.device) if want_lo else None
+    hi = torch.empty((2, n, 2 * h, 2 * w, cp), dtype=torch.bfloat16, device=g.device) if up else None
+    colsum = torch.empty((c,), dtype=torch.float32, device=g.device)
+    call("l2i_grad_split", g, n, h, w, c, lo[0] if want_lo else None, lo[1] if want_lo else None, float(up_scale),
+         hi[0] if up else None, hi[1] if up else None, colsum, cp)
+    return (Pair(lo[0], lo[1], c) if want_lo else None), (Pair(hi[0], hi[1], c) if up else None), colsum
+
+
+def pair_colsum(p: Pair) -> torch.Tensor:
+    colsum = torch.empty((p.C,), dtype=torch.float32, device=p.hi.device)
+    call("l2i_pair_colsum", p.hi, p.lo, p.hi.numel() // p.cpad, p.C, p.cpad, colsum)
+    return colsum
+
+
 def conv2d_fwd(x: Pair, w_hi: torch.Tensor, w_lo: torch.Tensor, cout: int, taps: int,
                bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
                res_up2: bool = False, res_scale: float = 1.0, out_scale: float = 1.0,

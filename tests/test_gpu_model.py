@@ -160,10 +160,13 @@ def test_train_step_matches_oracle_and_reference(name):
         assert_summary_close(grads["d." + n].cpu(), z[f"train.dgrad.{n}"], 2e-3,
                              1e-5 + 2e-2 * want.abs().max().item() + 4 * noise, "D grad vs golden " + n)
     sdG, sdD = G.state_dict(), D.state_dict()
+    # Post-step state.  With betas=(0, .999) the first Adam update is lr * g / (|g| + 1e-8): every element moves
+    # by +-lr = 1e-4 whatever its size, so an element whose gradient is rounding noise may move the other way
+    # (2e-4 apart); the spectral-norm vectors of the G-step forward are power iterations on those weights.
     for n, v in r32["PG"].items():
-        close(sdG[n].float(), v.float(), 1e-3, 2e-4, "G state " + n)
+        close(sdG[n].float(), v.float(), 1e-3, 1e-3 if n.endswith(("_u", "_v")) else 2e-4, "G state " + n)
     for n, v in r32["PD"].items():
-        close(sdD[n].float(), v.float(), 1e-3, 2e-4, "D state " + n)
+        close(sdD[n].float(), v.float(), 1e-3, 1e-3 if n.endswith(("_u", "_v")) else 2e-4, "D state " + n)
 
 
 def test_train_mode_buffers_advance_like_reference():

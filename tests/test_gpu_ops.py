@@ -369,3 +369,53 @@ def test_fused_adam_matches_torch_adam(dev):
         close(pa, pb, rtol=1e-6, atol=1e-7, what="adam param")
     for pa, pb in zip(ps_a[:-1], ps_b[:-1]):
         close(a.state[pa]["exp_avg_sq"], b.state[pb]["exp_avg_sq"], rtol=1e-6, atol=1e-12, what="exp_avg_sq")
+
+
+@pytest.mark.parametrize("cin,cout,H,down,optimized", [(3, 64, 32, True, True), (64, 128, 16, True, False),
+                                                      (128, 256, 8, False, False), (72, 72, 8, False, False),
+                                                      (512, 1024, 8, True, False)])
+def test_d_block_fused_matches_composition(dev, cin, cout, H, down, optimized):
+    """functional.d_block (one autograd node: operand prep + 3 convs with fused ReLU / pooling / shortcut) vs
+    the reference composition of rcnn_discriminator_app.py:294-344 in fp64, forward and every gradient."""
+    from layout2img_b200 import functional as L
+    N = 3
+    has_sc = down or cin != cout
+    g = torch.Generator().manual_seed(cin + cout + H)
+    x = torch.randn(N, cin, H, H, generator=g)
+    w1 = torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+    w2 = torch.randn(cout, cout, 3, 3, generator=g) / (9 * cout) ** 0.5
+    wsc = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    b1, b2, bsc = (torch.randn(cout, generator=g) for _ in range(3))
+    leaves = [t.double().requires_grad_() for t in (x, w1, b1, w2, b2, wsc, bsc)]
+    xr, w1r, b1r, w2r, b2r, wscr, bscr = leaves
+    # The inner ReLU sits on a K = 9*cin reduction: a pre-activation within rounding distance of 0 may land on
+    # either side of the kink in two correct implementations.  Give the fp64 composition the side the kernels
+    # took (the unfused conv produces bit-identical accumulators), so the comparison tests the arithmetic.
+    with torch.no_grad():
+        h1 = L.conv2d(nhwc(x).to(dev), w1.to(dev), b1.to(dev), relu_in=not optimized)
+        m1 = (h1 > 0).permute(0, 3, 1, 2).double().cpu()
+    if optimized:
+        r = F.conv2d(F.conv2d(xr, w1r, b1r, padding=1) * m1, w2r, b2r, padding=1)
+        ref = F.avg_pool2d(r, 2) + F.conv2d(F.avg_pool2d(xr, 2), wscr, bscr)
+    else:
+        r = F.conv2d(F.conv2d(F.relu(xr), w1r, b1r, padding=1) * m1, w2r, b2r, padding=1)
+        s = F.conv2d(xr, wscr, bscr) if has_sc else xr
+        if down:
+            r, s = F.avg_pool2d(r, 2), F.avg_pool2d(s, 2)
+        ref = r + s
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy.double())
+    xg = nhwc(x).to(dev).requires_grad_()
+    ps = [t.to(dev).requires_grad_() for t in (w1, b1, w2, b2, wsc, bsc)]
+    out = L.d_block(xg, ps[0], ps[1], ps[2], ps[3], ps[4] if has_sc else None, ps[5] if has_sc else None,
+                    down=down, optimized=optimized)
+    out.backward(nhwc(dy).to(dev))
+    sc = lambda t: max(t.abs().max().item(), 1.0)
+    close(out.permute(0, 3, 1, 2), ref, 1e-3, 1e-4 * sc(ref), "fwd")
+    close(xg.grad.permute(0, 3, 1, 2), xr.grad, 1e-3, 1e-4 * sc(xr.grad), "dx")
+    names = ["w1", "b1", "w2", "b2", "wsc", "bsc"]
+    for i, (p, rl) in enumerate(zip(ps, leaves[1:])):
+        if i >= 4 and not has_sc:
+            assert p.grad is None
+            continue
+        close(p.grad, rl.grad, 1e-3, 2e-4 * sc(rl.grad), "d" + names[i])
