@@ -284,8 +284,9 @@ def run_ours(args, rank, local_rank, world):
     e2e = world * B * args.steps / (ms_e2e / 1e3)
 
     line = None
+    # every rank runs the instrumented step (it contains the gradient all-reduces); rank 0 reports it
+    agg, step_ms = kernel_breakdown(step_resident)
     if rank == 0:
-        agg, step_ms = kernel_breakdown(step_resident)
         pk = peaks()
         conv = agg.get("l2i_conv2d_fwd", {"calls": 0, "ms": 0.0, "flops": 0.0})
         wg = agg.get("l2i_conv2d_wgrad", {"calls": 0, "ms": 0.0, "flops": 0.0})

@@ -143,6 +143,34 @@ int l2i_box_attention_bwd(const float* q, const float* k, const float* v, const 
                           const float* p_save, const float* glin_save, const float* dout, int B, int O, int D,
                           float* dq, float* dk, float* dv, float* dwg, float* dbg, void* stream);
 
+/* ---- pyramid pooling of the res4 mask head (reference model/resnet_generator_app_v2.py:724-752, PSPModule;
+ *      sizes (1, 2, 3, 6) -> 50 cells per image in that order, row-major inside a size) -------------------- */
+/* pooled [B,50,C] = the four AdaptiveAvgPool2d of x [B,H,W,C]. */
+int l2i_psp_pool_fwd(const float* x, int B, int H, int W, int C, float* pooled, void* stream);
+/* dx [B,H,W,C] = (base ? base[b,h,w,base_off + c] with channel stride base_stride : 0) + pooling backward of
+ * dpooled [B,50,C]. */
+int l2i_psp_pool_bwd(const float* dpooled, const float* base, int base_stride, int base_off, int B, int H, int W, int C,
+                     float* dx, void* stream);
+/* pair [B,H,W,cpad] of cat[ up(priors_1), up(priors_2), up(priors_3), up(priors_6), feats ]: priors [B,50,CP]
+ * bilinearly up-sampled with align_corners=True, feats [B,H,W,C]; channels >= 4*CP + C are zero. */
+int l2i_psp_concat_fwd(const float* feats, const float* priors, int B, int H, int W, int C, int CP, void* hi, void* lo,
+                       int cpad, void* stream);
+/* dpriors [B,50,CP] = backward of the four up-samplings from dcat [B,H,W,cstride] (channels [0, 4*CP)). */
+int l2i_psp_concat_bwd(const float* dcat, int B, int H, int W, int CP, int cstride, float* dpriors, void* stream);
+
+/* ---- spectral normalisation (torch.nn.utils.spectral_norm as used at resnet_generator_app_v2.py:681-686 and
+ *      rcnn_discriminator_app.py:10-15).  W [R, Cc] fp32 (weight_orig viewed 2-D), u [R], v [Cc]. ------------ */
+/* training != 0: one power iteration, u and v updated in place (v <- normalize(W^T u), u <- normalize(W v), eps
+ * as in F.normalize).  Always: sigma[0] = u . (W v); u_used / v_used receive the vectors sigma was computed with
+ * (for the backward).  work: Cc + R floats of scratch.  W / sigma itself is never materialised:
+ * l2i_conv_weight_prep takes sigma. */
+int l2i_sn_sigma(const float* W, int R, int Cc, float* u, float* v, int training, float eps, float* u_used, float* v_used,
+                 float* sigma, float* work, void* stream);
+/* dW [R][cin][taps] (torch layout of weight_orig) = (G - <G, W>/sigma * u v^T) / sigma from the tensor-core
+ * weight gradient G [R][taps][cin] (l2i_conv2d_wgrad's layout).  scratch: 1 float. */
+int l2i_sn_weight_grad(const float* G, const float* W, const float* u, const float* v, const float* sigma, int R, int cin,
+                       int taps, float* dW, float* scratch, void* stream);
+
 /* ---- optimizer (reference train_context_app_v2.py:113-127,174,189: torch.optim.Adam(betas=(0, 0.999)),
  *      one parameter group per tensor).  One launch updates every tensor of a network.
  *      tensors: device array of { float* p; const float* g; float* m; float* v; int64 n; float lr; int pad; }

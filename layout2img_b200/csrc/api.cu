@@ -156,6 +156,28 @@ int l2i_box_attention_bwd(const float* q, const float* k, const float* v, const 
                            dv, dwg, dbg, ST(stream));
 }
 
+int l2i_psp_pool_fwd(const float* x, int B, int H, int W, int C, float* pooled, void* stream) {
+  return psp_pool_fwd(x, B, H, W, C, pooled, ST(stream));
+}
+int l2i_psp_pool_bwd(const float* dpooled, const float* base, int base_stride, int base_off, int B, int H, int W, int C,
+                     float* dx, void* stream) {
+  return psp_pool_bwd(dpooled, base, base_stride, base_off, B, H, W, C, dx, ST(stream));
+}
+int l2i_psp_concat_fwd(const float* feats, const float* priors, int B, int H, int W, int C, int CP, void* hi, void* lo,
+                       int cpad, void* stream) {
+  return psp_concat_fwd(feats, priors, B, H, W, C, CP, hi, lo, cpad, ST(stream));
+}
+int l2i_psp_concat_bwd(const float* dcat, int B, int H, int W, int CP, int cstride, float* dpriors, void* stream) {
+  return psp_concat_bwd(dcat, B, H, W, CP, cstride, dpriors, ST(stream));
+}
+int l2i_sn_sigma(const float* W, int R, int Cc, float* u, float* v, int training, float eps, float* u_used, float* v_used,
+                 float* sigma, float* work, void* stream) {
+  return sn_sigma(W, R, Cc, u, v, training, eps, u_used, v_used, sigma, work, ST(stream));
+}
+int l2i_sn_weight_grad(const float* G, const float* W, const float* u, const float* v, const float* sigma, int R, int cin,
+                       int taps, float* dW, float* scratch, void* stream) {
+  return sn_weight_grad(G, W, u, v, sigma, R, cin, taps, dW, scratch, ST(stream));
+}
 int l2i_adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, double beta1, double beta2,
                   double eps, double bias_correction1, double bias_correction2_sqrt, void* stream) {
   return adam_step(tensors, chunks, n_chunks, chunk_elems, beta1, beta2, eps, bias_correction1, bias_correction2_sqrt,

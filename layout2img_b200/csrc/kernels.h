@@ -62,6 +62,20 @@ int box_attention_bwd(const float* q, const float* k, const float* v, const floa
                       const float* p_save, const float* glin_save, const float* dout, int B, int O, int D, float* dq,
                       float* dk, float* dv, float* dwg, float* dbg, cudaStream_t stream);
 
+// psp.cu
+int psp_pool_fwd(const float* x, int B, int H, int W, int C, float* pooled, cudaStream_t stream);
+int psp_pool_bwd(const float* dpooled, const float* base, int base_stride, int base_off, int B, int H, int W, int C,
+                 float* dx, cudaStream_t stream);
+int psp_concat_fwd(const float* feats, const float* priors, int B, int H, int W, int C, int CP, void* hi, void* lo, int cpad,
+                   cudaStream_t stream);
+int psp_concat_bwd(const float* dcat, int B, int H, int W, int CP, int cstride, float* dpriors, cudaStream_t stream);
+
+// specnorm.cu
+int sn_sigma(const float* W, int R, int Cc, float* u, float* v, int training, float eps, float* u_used, float* v_used,
+             float* sigma, float* work, cudaStream_t stream);
+int sn_weight_grad(const float* G, const float* W, const float* u, const float* v, const float* sigma, int R, int cin,
+                   int taps, float* dW, float* scratch, cudaStream_t stream);
+
 // optim.cu
 struct AdamTensor {       // one entry of the device-resident tensor table (48 bytes, see include/l2i.h)
   float* p;

@@ -1,0 +1,197 @@
+// Spectral normalisation as the reference applies it to every conv / linear weight
+// (torch.nn.utils.spectral_norm, call sites resnet_generator_app_v2.py:681-686, rcnn_discriminator_app.py:10-15):
+//   training:  v <- normalize(W^T u, eps);  u <- normalize(W v, eps)      (one power iteration, in place)
+//   always:    sigma = u . (W v);   W_sn = W / sigma
+//   backward:  dW = (G - <G, W>/sigma * u v^T) / sigma                    (u, v constants)
+// W is viewed as [R, Cc] (R = out channels).  torch runs this as ~15 small launches per module and
+// materialises W / sigma; here: 3 launches (two passes over W) produce sigma, which the operand-preparation
+// kernel folds into the bf16 split, and 2 launches map the tensor-core weight gradient G (layout
+// [R][taps][cin]) to the gradient of weight_orig (torch layout [R][cin][taps]).  HBM-bound: 2 reads of W
+// forward, 1 read of W + 1 read of G + 1 write backward.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace l2i {
+
+__device__ __forceinline__ float block_sum(float v, float* red) {   // blockDim.x <= 1024; all threads call
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (warp == 0) {
+    t = warp_sum(t);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+// t[c] (+)= sum_{r in split} W[r,c] * u[r]
+__global__ void __launch_bounds__(256) sn_wt_u_kernel(const float* __restrict__ W, const float* __restrict__ u, int R, int Cc,
+                                                      int rows_per_split, float* __restrict__ t) {
+  extern __shared__ float s_u[];
+  const int r0 = blockIdx.y * rows_per_split, r1 = min(R, r0 + rows_per_split);
+  for (int i = threadIdx.x; i < r1 - r0; i += blockDim.x) s_u[i] = __ldg(u + r0 + i);
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cc) return;
+  float acc = 0.f;
+  const float* wp = W + static_cast<size_t>(r0) * Cc + c;
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r, wp += Cc) acc = fmaf(__ldg(wp), s_u[r - r0], acc);
+  atomicAdd(t + c, acc);
+}
+
+// v = normalize_v ? t / max(|t|, eps) : t;  s[r] = W[r,:] . v  (one warp per row);  block 0 also stores v
+__global__ void __launch_bounds__(256) sn_w_v_kernel(const float* __restrict__ W, const float* __restrict__ t, int R, int Cc,
+                                                     int normalize_v, float eps, float* __restrict__ v_out,
+                                                     float* __restrict__ v_out2, float* __restrict__ s) {
+  extern __shared__ float s_v[];          // [Cc] + 32
+  float* red = s_v + Cc;
+  float inv = 1.f;
+  if (normalize_v) {
+    float q = 0.f;
+    for (int i = threadIdx.x; i < Cc; i += blockDim.x) { const float x = __ldg(t + i); q = fmaf(x, x, q); }
+    const float n2 = block_sum(q, red);
+    inv = 1.0f / fmaxf(sqrtf(n2), eps);
+  }
+  for (int i = threadIdx.x; i < Cc; i += blockDim.x) {
+    const float x = __ldg(t + i) * inv;
+    s_v[i] = x;
+    if (blockIdx.x == 0) {
+      if (v_out) v_out[i] = x;
+      if (v_out2) v_out2[i] = x;
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (r >= R) return;
+  const float* wp = W + static_cast<size_t>(r) * Cc;
+  float acc = 0.f;
+  for (int c = lane; c < Cc; c += 32) acc = fmaf(__ldg(wp + c), s_v[c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) s[r] = acc;
+}
+
+// update_u: u = s / max(|s|, eps) (stored to u_out and u_out2);  sigma = u . s
+__global__ void __launch_bounds__(1024) sn_finish_kernel(const float* __restrict__ s, const float* __restrict__ u_in, int R,
+                                                         int update_u, float eps, float* __restrict__ u_out,
+                                                         float* __restrict__ u_out2, float* __restrict__ sigma) {
+  __shared__ float red[32];
+  float inv = 1.f;
+  if (update_u) {
+    float q = 0.f;
+    for (int i = threadIdx.x; i < R; i += blockDim.x) { const float x = __ldg(s + i); q = fmaf(x, x, q); }
+    inv = 1.0f / fmaxf(sqrtf(block_sum(q, red)), eps);
+  }
+  float d = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    const float sv = __ldg(s + i);
+    const float uv = update_u ? sv * inv : __ldg(u_in + i);
+    if (update_u && u_out) u_out[i] = uv;
+    if (u_out2) u_out2[i] = uv;
+    d = fmaf(uv, sv, d);
+  }
+  d = block_sum(d, red);
+  if (threadIdx.x == 0) *sigma = d;
+}
+
+int sn_sigma(const float* W, int R, int Cc, float* u, float* v, int training, float eps, float* u_used, float* v_used,
+             float* sigma, float* work, cudaStream_t stream) {
+  // work: [Cc + R] floats of scratch (t, s)
+  if (!W || !u || !v || !sigma || !work || !u_used || !v_used || R <= 0 || Cc <= 0 || Cc > 40000) {
+    set_error("sn_sigma: bad arguments (R=%d Cc=%d)", R, Cc);
+    return L2I_ERR_BAD_ARG;
+  }
+  float* t = work;
+  float* s = work + Cc;
+  const size_t smem_v = sizeof(float) * (Cc + 32);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(sn_w_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40032 * 4);
+    configured = true;
+  }
+  if (training) {
+    cudaError_t e = cudaMemsetAsync(t, 0, sizeof(float) * Cc, stream);
+    if (e != cudaSuccess) { set_error("sn_sigma: memset: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
+    const int col_blocks = (Cc + 255) / 256;
+    int splits = (296 + col_blocks - 1) / col_blocks;
+    if (splits > (R + 15) / 16) splits = (R + 15) / 16;
+    if (splits < 1) splits = 1;
+    const int rps = (R + splits - 1) / splits;
+    splits = (R + rps - 1) / rps;
+    sn_wt_u_kernel<<<dim3(col_blocks, splits), 256, sizeof(float) * rps, stream>>>(W, u, R, Cc, rps, t);
+    int rc = check_launch("sn_wt_u_kernel");
+    if (rc) return rc;
+    sn_w_v_kernel<<<(R + 7) / 8, 256, smem_v, stream>>>(W, t, R, Cc, 1, eps, v, v_used, s);
+  } else {
+    sn_w_v_kernel<<<(R + 7) / 8, 256, smem_v, stream>>>(W, v, R, Cc, 0, eps, nullptr, v_used, s);
+  }
+  int rc = check_launch("sn_w_v_kernel");
+  if (rc) return rc;
+  sn_finish_kernel<<<1, 1024, 0, stream>>>(s, u, R, training, eps, u, u_used, sigma);
+  return check_launch("sn_finish_kernel");
+}
+
+// d += sum G[r][tap][ci] * W[r][ci][tap]
+__global__ void __launch_bounds__(256) sn_bwd_dot_kernel(const float* __restrict__ G, const float* __restrict__ W, int R, int cin,
+                                                         int taps, float* __restrict__ d) {
+  __shared__ float red[32];
+  const long long total = 1LL * R * cin * taps;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    // i indexes G: (r, tap, ci)
+    const int ci = static_cast<int>(i % cin);
+    const int tap = static_cast<int>((i / cin) % taps);
+    const long long r = i / (1LL * cin * taps);
+    acc = fmaf(__ldg(G + i), __ldg(W + (r * cin + ci) * taps + tap), acc);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(d, acc);
+}
+
+// dW[r][ci][tap] = (G[r][tap][ci] - d / sigma * u[r] * v[ci * taps + tap]) / sigma
+__global__ void __launch_bounds__(256) sn_bwd_apply_kernel(const float* __restrict__ G, const float* __restrict__ u,
+                                                           const float* __restrict__ v, const float* __restrict__ sigma,
+                                                           const float* __restrict__ d, int R, int cin, int taps,
+                                                           float* __restrict__ dW) {
+  const float sg = __ldg(sigma);
+  const float inv = 1.0f / sg;
+  const float coef = __ldg(d) * inv;
+  const long long total = 1LL * R * cin * taps;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    // i indexes dW (torch layout): (r, ci, tap)
+    const int tap = static_cast<int>(i % taps);
+    const int ci = static_cast<int>((i / taps) % cin);
+    const long long r = i / (1LL * cin * taps);
+    const float g = __ldg(G + (r * taps + tap) * cin + ci);
+    dW[i] = (g - coef * __ldg(u + r) * __ldg(v + ci * taps + tap)) * inv;
+  }
+}
+
+int sn_weight_grad(const float* G, const float* W, const float* u, const float* v, const float* sigma, int R, int cin,
+                   int taps, float* dW, float* scratch, cudaStream_t stream) {
+  if (!G || !W || !u || !v || !sigma || !dW || !scratch || R <= 0 || cin <= 0 || taps <= 0) {
+    set_error("sn_weight_grad: bad arguments");
+    return L2I_ERR_BAD_ARG;
+  }
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float), stream);
+  if (e != cudaSuccess) { set_error("sn_weight_grad: memset: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
+  const long long total = 1LL * R * cin * taps;
+  long long blocks = (total + 256 * 8 - 1) / (256 * 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  sn_bwd_dot_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(G, W, R, cin, taps, scratch);
+  int rc = check_launch("sn_bwd_dot_kernel");
+  if (rc) return rc;
+  blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sn_bwd_apply_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(G, u, v, sigma, scratch, R, cin, taps, dW);
+  return check_launch("sn_bwd_apply_kernel");
+}
+
+}  // namespace l2i

@@ -79,7 +79,9 @@ class DBlockFn(torch.autograd.Function):
     the ReLU derivatives are applied in the data-gradient epilogues from the saved pairs."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, wsc, bsc, down, optimized):
+    def forward(ctx, x, w1, b1, w2, b2, wsc, bsc, down, optimized, sn1, sn2, snsc):
+        # sn* = None (w* is the weight itself) or (u, v, eps, training): w* is weight_orig and the spectral
+        # normalisation (power iteration + 1/sigma) happens here, fused into the operand preparation
         x = _c(x)
         has_sc = wsc is not None
         if down and not has_sc:
@@ -88,43 +90,56 @@ class DBlockFn(torch.autograd.Function):
         a0, s0 = ops.act_split2(x, relu_a=not optimized, b_mode=(2 if down else 1) if has_sc else 0)
         c1, cin = w1.shape[0], w1.shape[1]
         c2 = w2.shape[0]
-        wp1 = ops.conv_weight_prep(_c(w1), need_dgrad=need_dx)
-        wp2 = ops.conv_weight_prep(_c(w2), need_dgrad=True)
+        st1 = ops.sn_sigma(_c(w1), *sn1[:2], training=sn1[3], eps=sn1[2]) if sn1 else None
+        st2 = ops.sn_sigma(_c(w2), *sn2[:2], training=sn2[3], eps=sn2[2]) if sn2 else None
+        stsc = ops.sn_sigma(_c(wsc), *snsc[:2], training=snsc[3], eps=snsc[2]) if (snsc and has_sc) else None
+        wp1 = ops.conv_weight_prep(_c(w1), st1.sigma if st1 else None, need_dgrad=need_dx)
+        wp2 = ops.conv_weight_prep(_c(w2), st2.sigma if st2 else None, need_dgrad=True)
         _, a1 = ops.conv2d_fwd(a0, wp1.f_hi, wp1.f_lo, c1, 9, bias=_c(b1), want_f32=False, want_pair=True, relu_pair=True)
         if has_sc:
-            wps = ops.conv_weight_prep(_c(wsc), need_dgrad=need_dx)
+            wps = ops.conv_weight_prep(_c(wsc), stsc.sigma if stsc else None, need_dgrad=need_dx)
             sc, _ = ops.conv2d_fwd(s0, wps.f_hi, wps.f_lo, c2, 1, bias=_c(bsc))
         else:
             wps, sc = None, x
         out, _ = ops.conv2d_fwd(a1, wp2.f_hi, wp2.f_lo, c2, 9, bias=_c(b2), residual=sc, pool=1 if down else 0)
+        none3 = (None, None, None)
         ctx.save_for_backward(a0.hi, a0.lo, s0.hi if has_sc else None, s0.lo if has_sc else None, a1.hi, a1.lo,
                               wp1.d_hi, wp1.d_lo, wp2.d_hi, wp2.d_lo, wps.d_hi if has_sc else None,
-                              wps.d_lo if has_sc else None)
+                              wps.d_lo if has_sc else None, w1, w2, wsc, *(st1 or none3), *(st2 or none3),
+                              *(stsc or none3))
         ctx.meta = (cin, c1, c2, down, optimized, has_sc)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        a0h, a0l, s0h, s0l, a1h, a1l, d1h, d1l, d2h, d2l, dsh, dsl = ctx.saved_tensors
+        (a0h, a0l, s0h, s0l, a1h, a1l, d1h, d1l, d2h, d2l, dsh, dsl, w1, w2, wsc,
+         sg1, u1, v1, sg2, u2, v2, sgs, us, vs) = ctx.saved_tensors
         cin, c1, c2, down, optimized, has_sc = ctx.meta
         need = ctx.needs_input_grad
         dout = _c(dout)
         g_lo, g_up, colsum = ops.grad_split(dout, want_lo=has_sc or not down, up=down, up_scale=0.25)
         g_full = g_up if down else g_lo                      # gradient at conv2's output resolution
         a0, a1 = ops.Pair(a0h, a0l, cin), ops.Pair(a1h, a1l, c1)
+
+        def wgrad(dy, xin, taps, w, sg, u, v):
+            g = ops.conv2d_wgrad(dy, xin, taps)              # (Cout, taps, Cin)
+            if sg is not None:
+                return ops.sn_weight_grad(g, w, ops.SNState(sg, u, v))
+            return _dw_to_torch(g, g.shape[0], g.shape[2], taps)
+
         dw1 = db1 = dw2 = db2 = dwsc = dbsc = dx = None
         if need[3]:
-            dw2 = _dw_to_torch(ops.conv2d_wgrad(g_full, a1, 9), c2, c1, 9)
+            dw2 = wgrad(g_full, a1, 9, w2, sg2, u2, v2)
         if need[4]:
             db2 = colsum
         if has_sc and need[5]:
-            dwsc = _dw_to_torch(ops.conv2d_wgrad(g_lo, ops.Pair(s0h, s0l, cin), 1), c2, cin, 1)
+            dwsc = wgrad(g_lo, ops.Pair(s0h, s0l, cin), 1, wsc, sgs, us, vs)
         if has_sc and need[6]:
             dbsc = colsum.clone() if need[4] else colsum
         if need[0] or need[1] or need[2]:
             _, d1 = ops.conv2d_fwd(g_full, d2h, d2l, c1, 9, mask_hi=a1h, want_f32=False, want_pair=True)
             if need[1]:
-                dw1 = _dw_to_torch(ops.conv2d_wgrad(d1, a0, 9), c1, cin, 9)
+                dw1 = wgrad(d1, a0, 9, w1, sg1, u1, v1)
             if need[2]:
                 db1 = ops.pair_colsum(d1)
             if need[0]:
@@ -134,11 +149,32 @@ class DBlockFn(torch.autograd.Function):
                     r = dout
                 dx, _ = ops.conv2d_fwd(d1, d1h, d1l, cin, 9, mask_hi=None if optimized else a0h, residual=r,
                                        res_up2=down, res_scale=0.25 if down else 1.0)
-        return dx, dw1, db1, dw2, db2, dwsc, dbsc, None, None
+        return dx, dw1, db1, dw2, db2, dwsc, dbsc, None, None, None, None, None
 
 
-def d_block(x, w1, b1, w2, b2, wsc=None, bsc=None, down=False, optimized=False):
-    return DBlockFn.apply(x, w1, b1, w2, b2, wsc, bsc, down, optimized)
+def _sn_of(conv):
+    """(weight tensor to differentiate, bias, (u, v, eps, training) | None) of a (possibly spectrally normalised)
+    conv module.  For a normalised module the hook is bypassed: its arithmetic runs in csrc/specnorm.cu."""
+    from torch.nn.utils.spectral_norm import SpectralNorm
+    for hook in conv._forward_pre_hooks.values():
+        if isinstance(hook, SpectralNorm):
+            if hook.n_power_iterations != 1 or hook.dim != 0:
+                raise ValueError("layout2img_b200 implements spectral_norm(n_power_iterations=1, dim=0)")
+            return conv.weight_orig, conv.bias, (conv.weight_u, conv.weight_v, hook.eps, conv.training)
+    return conv.weight, conv.bias, None
+
+
+def d_block(x, conv1, conv2, c_sc=None, down=False, optimized=False):
+    """Fused residual block of the discriminator from its conv modules (rcnn_discriminator_app.py:294-344)."""
+    w1, b1, sn1 = _sn_of(conv1)
+    w2, b2, sn2 = _sn_of(conv2)
+    wsc, bsc, snsc = _sn_of(c_sc) if c_sc is not None else (None, None, None)
+    return DBlockFn.apply(x, w1, b1, w2, b2, wsc, bsc, down, optimized, sn1, sn2, snsc)
+
+
+def d_block_raw(x, w1, b1, w2, b2, wsc=None, bsc=None, down=False, optimized=False):
+    """Same block from plain (already normalised) weight tensors."""
+    return DBlockFn.apply(x, w1, b1, w2, b2, wsc, bsc, down, optimized, None, None, None)
 
 
 class NormConvFn(torch.autograd.Function):
@@ -189,6 +225,54 @@ def norm_conv(x, weight, bias, running_mean, running_var, training, mask_pm=None
               aff_w=None, aff_b=None, residual=None, up2=False, res_up2=False, momentum=0.1, eps=1e-5):
     return NormConvFn.apply(x, mask_pm, gamma, beta, aff_w, aff_b, weight, bias, residual, running_mean, running_var,
                             training, momentum, eps, up2, res_up2)
+
+
+class PspPoolFn(torch.autograd.Function):
+    """The four AdaptiveAvgPool2d of PSPModule (resnet_generator_app_v2.py:741-746) in one pass: (B,H,W,C) -> (B,50,C)."""
+
+    @staticmethod
+    def forward(ctx, feats):
+        feats = _c(feats)
+        ctx.shape = tuple(feats.shape)
+        return ops.psp_pool_fwd(feats)
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        return ops.psp_pool_bwd(_c(dpooled), ctx.shape)
+
+
+def psp_pool(feats):
+    return PspPoolFn.apply(feats)
+
+
+class PspBottleneckFn(torch.autograd.Function):
+    """conv3x3(cat[up(priors_1..6), feats]) of PSPModule (resnet_generator_app_v2.py:736,748-751): the concat is
+    written directly as the convolution's bf16 operand pair; priors (B,50,CP) are the ReLU'd stage outputs."""
+
+    @staticmethod
+    def forward(ctx, feats, priors, weight):
+        feats, priors = _c(feats), _c(priors)
+        cout = weight.shape[0]
+        pair = ops.psp_concat_fwd(feats, priors)
+        wp = ops.conv_weight_prep(_c(weight), need_dgrad=True)
+        out, _ = ops.conv2d_fwd(pair, wp.f_hi, wp.f_lo, cout, 9)
+        ctx.save_for_backward(pair.hi, pair.lo, wp.d_hi, wp.d_lo)
+        ctx.meta = (cout, pair.C, priors.shape[2])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        phi, plo, dhi, dlo = ctx.saved_tensors
+        cout, ctot, cp = ctx.meta
+        dyp = ops.act_split(_c(dout))
+        dcat, _ = ops.conv2d_fwd(dyp, dhi, dlo, ctot, 9)
+        dw = _dw_to_torch(ops.conv2d_wgrad(dyp, ops.Pair(phi, plo, ctot), 9), cout, ctot, 9)
+        dpriors = ops.psp_concat_bwd(dcat, cp)
+        return dcat[..., 4 * cp:], dpriors, dw
+
+
+def psp_bottleneck(feats, priors, weight):
+    return PspBottleneckFn.apply(feats, priors, weight)
 
 
 class AvgPool2Fn(torch.autograd.Function):

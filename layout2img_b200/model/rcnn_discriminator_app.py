@@ -25,10 +25,8 @@ class OptimizedBlock(nn.Module):
         self.downsample = downsample
 
     def forward(self, in_feat):                      # NHWC
-        for m in (self.conv1, self.conv2, self.c_sc):
-            fire_param_hooks(m)                      # spectral-norm power iteration + W / sigma
-        return L.d_block(in_feat, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
-                         self.c_sc.weight, self.c_sc.bias, down=self.downsample, optimized=True)
+        # spectral norm (power iteration, 1/sigma) of the three convs runs inside the fused node
+        return L.d_block(in_feat, self.conv1, self.conv2, self.c_sc, down=self.downsample, optimized=True)
 
 
 class ResBlock(nn.Module):
@@ -47,13 +45,8 @@ class ResBlock(nn.Module):
             self.c_sc = conv2d(in_ch, out_ch, 1, 1, 0)
 
     def forward(self, in_feat):                      # NHWC
-        mods = (self.conv1, self.conv2, self.c_sc) if self.learnable_sc else (self.conv1, self.conv2)
-        for m in mods:
-            fire_param_hooks(m)
-        sc_w = self.c_sc.weight if self.learnable_sc else None
-        sc_b = self.c_sc.bias if self.learnable_sc else None
-        return L.d_block(in_feat, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
-                         sc_w, sc_b, down=self.downsample, optimized=False)
+        return L.d_block(in_feat, self.conv1, self.conv2, self.c_sc if self.learnable_sc else None,
+                         down=self.downsample, optimized=False)
 
 
 class ResnetDiscriminator128_app(nn.Module):

@@ -61,6 +61,9 @@ class PSPModule(nn.Module):
 
     def __init__(self, features, out_features=512, sizes=(1, 2, 3, 6)):
         super().__init__()
+        if tuple(sizes) != (1, 2, 3, 6):
+            raise ValueError("layout2img_b200 PSPModule implements the reference's pyramid sizes (1, 2, 3, 6)")
+        self.sizes = tuple(sizes)
         self.stages = nn.ModuleList([self._make_stage(features, out_features, size) for size in sizes])
         self.bottleneck = nn.Sequential(
             Conv2d(features + len(sizes) * out_features, out_features, kernel_size=3, padding=1, dilation=1, bias=False),
@@ -75,16 +78,14 @@ class PSPModule(nn.Module):
 
     def forward(self, feats):                       # feats NHWC
         b, h, w, c = feats.shape
-        f = to_nchw_view(feats)
-        priors = []
-        for stage in self.stages:
-            p = stage[0](f)                                             # (b,c,s,s)
-            p = F.linear(p.permute(0, 2, 3, 1), stage[1].weight.view(stage[1].out_channels, c))
-            p = F.relu(stage[2](p.permute(0, 3, 1, 2)))
-            p = F.interpolate(p, size=(h, w), mode="bilinear", align_corners=True)
-            priors.append(p.permute(0, 2, 3, 1))
-        priors.append(feats)
-        x = self.bottleneck[0](torch.cat(priors, dim=3).contiguous())   # (b,h,w,100)
+        pooled = L.psp_pool(feats)                                      # (b, 50, c): all four adaptive pools
+        priors, off = [], 0
+        for stage, s in zip(self.stages, self.sizes):
+            p = F.linear(pooled[:, off:off + s * s], stage[1].weight.view(stage[1].out_channels, c))   # 1x1 conv
+            p = stage[2](p.view(b, s, s, -1).permute(0, 3, 1, 2))       # nn.BatchNorm2d over the b*s*s samples
+            priors.append(F.relu(p).permute(0, 2, 3, 1).reshape(b, s * s, -1))
+            off += s * s
+        x = L.psp_bottleneck(feats, torch.cat(priors, dim=1), self.bottleneck[0].weight)   # (b,h,w,100)
         bn = self.bottleneck[1]
         x = F.batch_norm(x.view(-1, x.shape[-1]), bn.running_mean, bn.running_var, bn.weight, bn.bias,
                          bn.training, bn.momentum, bn.eps).view_as(x)

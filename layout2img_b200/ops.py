@@ -59,6 +59,36 @@ def conv_weight_prep(w: torch.Tensor, sigma: Optional[torch.Tensor] = None, need
     return WeightPair(f[0], f[1], d[0] if need_dgrad else None, d[1] if need_dgrad else None, cout, cin, taps)
 
 
+class SNState(NamedTuple):
+    """What the backward of a spectrally normalised weight needs: sigma (1,), the u / v it was computed with."""
+    sigma: torch.Tensor
+    u: torch.Tensor
+    v: torch.Tensor
+
+
+def sn_sigma(w_orig: torch.Tensor, u: torch.Tensor, v: torch.Tensor, training: bool, eps: float) -> SNState:
+    """torch.nn.utils.spectral_norm's pre-forward step: in training one power iteration updates u, v IN PLACE;
+    returns sigma = u . (W v) and copies of the vectors used."""
+    _chk(w_orig); _chk(u); _chk(v)
+    r = w_orig.shape[0]
+    cc = w_orig.numel() // r
+    if u.numel() != r or v.numel() != cc:
+        raise ValueError(f"spectral norm vectors ({u.numel()}, {v.numel()}) do not match weight ({r}, {cc})")
+    out = torch.empty(1 + 2 * (r + cc), dtype=torch.float32, device=w_orig.device)
+    sigma, u_used, v_used, work = out[:1], out[1:1 + r], out[1 + r:1 + r + cc], out[1 + r + cc:]
+    call("l2i_sn_sigma", w_orig, r, cc, u, v, int(training), float(eps), u_used, v_used, sigma, work)
+    return SNState(sigma, u_used, v_used)
+
+
+def sn_weight_grad(g_ours: torch.Tensor, w_orig: torch.Tensor, st: SNState) -> torch.Tensor:
+    """Tensor-core weight gradient (Cout, taps, Cin) -> gradient of weight_orig (Cout, Cin, kh, kw)."""
+    cout, taps, cin = g_ours.shape
+    dw = torch.empty_like(w_orig)
+    scratch = torch.empty(1, dtype=torch.float32, device=w_orig.device)
+    call("l2i_sn_weight_grad", g_ours, w_orig, st.u, st.v, st.sigma, cout, cin, taps, dw, scratch)
+    return dw
+
+
 def act_split(x: torch.Tensor, relu: bool = False, up2: bool = False) -> Pair:
     """x (N,H,W,C) fp32 -> Pair at (N, H<<up2, W<<up2, pad8(C)), optional ReLU first."""
     _chk(x)
@@ -267,6 +297,48 @@ def stage_mix_bwd(stage, y, alpha, bmask, hard, dout):
     dsoft = torch.empty_like(dout)
     call("l2i_stage_mix_bwd", stage, y, alpha, bmask, hard, dout, b, o, h, w, nc, s, dstage, dalpha, dsoft)
     return dstage, dalpha, dsoft
+
+
+# --------------------------------------------------------------------------------------------
+# pyramid pooling (PSPModule)
+# --------------------------------------------------------------------------------------------
+PSP_CELLS = 50          # sizes (1, 2, 3, 6)
+
+
+def psp_pool_fwd(x):
+    _chk(x)
+    b, h, w, c = x.shape
+    pooled = torch.empty((b, PSP_CELLS, c), dtype=torch.float32, device=x.device)
+    call("l2i_psp_pool_fwd", x, b, h, w, c, pooled)
+    return pooled
+
+
+def psp_pool_bwd(dpooled, shape):
+    _chk(dpooled)
+    b, h, w, c = shape
+    dx = torch.empty(shape, dtype=torch.float32, device=dpooled.device)
+    call("l2i_psp_pool_bwd", dpooled, None, 0, 0, b, h, w, c, dx)
+    return dx
+
+
+def psp_concat_fwd(feats, priors) -> Pair:
+    _chk(feats); _chk(priors)
+    b, h, w, c = feats.shape
+    cp = priors.shape[2]
+    if priors.shape != (b, PSP_CELLS, cp):
+        raise ValueError(f"priors must be (B, {PSP_CELLS}, CP), got {tuple(priors.shape)}")
+    ctot = 4 * cp + c
+    buf = torch.empty((2, b, h, w, pad8(ctot)), dtype=torch.bfloat16, device=feats.device)
+    call("l2i_psp_concat_fwd", feats, priors, b, h, w, c, cp, buf[0], buf[1], pad8(ctot))
+    return Pair(buf[0], buf[1], ctot)
+
+
+def psp_concat_bwd(dcat, cp: int):
+    _chk(dcat)
+    b, h, w, cs = dcat.shape
+    dpriors = torch.empty((b, PSP_CELLS, cp), dtype=torch.float32, device=dcat.device)
+    call("l2i_psp_concat_bwd", dcat, b, h, w, cp, cs, dpriors)
+    return dpriors
 
 
 # --------------------------------------------------------------------------------------------

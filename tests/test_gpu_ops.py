@@ -407,8 +407,8 @@ def test_d_block_fused_matches_composition(dev, cin, cout, H, down, optimized):
     ref.backward(dy.double())
     xg = nhwc(x).to(dev).requires_grad_()
     ps = [t.to(dev).requires_grad_() for t in (w1, b1, w2, b2, wsc, bsc)]
-    out = L.d_block(xg, ps[0], ps[1], ps[2], ps[3], ps[4] if has_sc else None, ps[5] if has_sc else None,
-                    down=down, optimized=optimized)
+    out = L.d_block_raw(xg, ps[0], ps[1], ps[2], ps[3], ps[4] if has_sc else None, ps[5] if has_sc else None,
+                        down=down, optimized=optimized)
     out.backward(nhwc(dy).to(dev))
     sc = lambda t: max(t.abs().max().item(), 1.0)
     close(out.permute(0, 3, 1, 2), ref, 1e-3, 1e-4 * sc(ref), "fwd")
@@ -419,3 +419,67 @@ def test_d_block_fused_matches_composition(dev, cin, cout, H, down, optimized):
             assert p.grad is None
             continue
         close(p.grad, rl.grad, 1e-3, 2e-4 * sc(rl.grad), "d" + names[i])
+
+
+def test_psp_pool_and_concat_match_torch(dev):
+    """csrc/psp.cu against the library composition of PSPModule (resnet_generator_app_v2.py:741-751): adaptive
+    average pools (1,2,3,6), bilinear align_corners=True up-sampling, concat, 3x3 conv -- forward and backward."""
+    from layout2img_b200 import functional as L
+    g = torch.Generator().manual_seed(9)
+    B, H, C, CP = 3, 64, 128, 100
+    feats = torch.randn(B, C, H, H, generator=g)
+    w = torch.randn(100, 4 * CP + C, 3, 3, generator=g) / (9 * (4 * CP + C)) ** 0.5
+    mix = [torch.randn(CP, C, generator=g) / C ** 0.5 for _ in range(4)]
+    fr, wr = feats.double().requires_grad_(), w.double().requires_grad_()
+    priors = []
+    for s, m in zip((1, 2, 3, 6), mix):
+        p = F.relu(torch.einsum("oc,bchw->bohw", m.double(), F.adaptive_avg_pool2d(fr, s)))
+        priors.append(F.interpolate(p, size=(H, H), mode="bilinear", align_corners=True))
+    ref = F.conv2d(torch.cat(priors + [fr], 1), wr, None, padding=1)
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy.double())
+
+    fg, wg = nhwc(feats).to(dev).requires_grad_(), w.to(dev).requires_grad_()
+    pooled = L.psp_pool(fg)
+    ps, off = [], 0
+    for s, m in zip((1, 2, 3, 6), mix):
+        ps.append(F.relu(pooled[:, off:off + s * s] @ m.to(dev).t()))
+        off += s * s
+    out = L.psp_bottleneck(fg, torch.cat(ps, 1), wg)
+    out.backward(nhwc(dy).to(dev))
+    close(out.permute(0, 3, 1, 2), ref, 1e-3, 1e-4 * max(ref.abs().max().item(), 1), "psp fwd")
+    close(fg.grad.permute(0, 3, 1, 2), fr.grad, 1e-3, 1e-4 * max(fr.grad.abs().max().item(), 1), "psp dfeats")
+    close(wg.grad, wr.grad, 1e-3, 2e-4 * max(wr.grad.abs().max().item(), 1), "psp dw")
+
+
+@pytest.mark.parametrize("shape,training", [((64, 3, 3, 3), True), ((1024, 512, 3, 3), True), ((256, 128, 1, 1), True),
+                                            ((128, 64, 3, 3), False)])
+def test_spectral_norm_kernels_match_torch(dev, shape, training):
+    """csrc/specnorm.cu vs torch.nn.utils.spectral_norm: the in-place power iteration, sigma, the normalised
+    weight (through the operand pair) and the gradient w.r.t. weight_orig."""
+    from layout2img_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape))
+    conv = torch.nn.Conv2d(shape[1], shape[0], shape[2], 1, shape[2] // 2)
+    conv = torch.nn.utils.spectral_norm(conv, eps=1e-4)
+    with torch.no_grad():
+        conv.weight_orig.copy_(torch.randn(shape, generator=g) * 0.05)
+    conv = conv.double()
+    conv.train(training)
+    w_orig = conv.weight_orig.detach().float().to(dev)
+    u, v = conv.weight_u.detach().float().to(dev), conv.weight_v.detach().float().to(dev)
+    for hook in conv._forward_pre_hooks.values():
+        hook(conv, None)                                    # torch: power iteration (train) + W / sigma
+    gy = torch.randn(shape, generator=g).double()
+    (conv.weight * gy).sum().backward()
+    st = ops.sn_sigma(w_orig, u, v, training, 1e-4)
+    close(u, conv.weight_u, 1e-4, 1e-6, "u"); close(v, conv.weight_v, 1e-4, 1e-6, "v")
+    close(st.u, conv.weight_u, 1e-4, 1e-6, "u used"); close(st.v, conv.weight_v, 1e-4, 1e-6, "v used")
+    sigma_ref = torch.dot(conv.weight_u, conv.weight_orig.detach().reshape(shape[0], -1) @ conv.weight_v)
+    close(st.sigma, sigma_ref.reshape(1), 1e-5, 1e-7, "sigma")
+    taps = shape[2] * shape[3]
+    wp = ops.conv_weight_prep(w_orig, st.sigma, need_dgrad=False)
+    w_sn = (wp.f_hi.float() + wp.f_lo.float())[..., :shape[1]].reshape(shape[0], shape[2], shape[3], shape[1]).permute(0, 3, 1, 2)
+    close(w_sn, conv.weight.detach(), 1e-4, 1e-5 * conv.weight.abs().max().item(), "W / sigma via the operand pair")
+    g_ours = gy.float().permute(0, 2, 3, 1).reshape(shape[0], taps, shape[1]).contiguous().to(dev)
+    dw = ops.sn_weight_grad(g_ours, w_orig, st)
+    close(dw, conv.weight_orig.grad, 1e-4, 1e-5 * conv.weight_orig.grad.abs().max().item(), "d weight_orig")
