@@ -26,14 +26,17 @@
 //   GEMM M = 128 output channels, N = BN input channels, K = pixels (64 per stage), both
 //   operands MN-major straight out of the NHWC tensors; one tap per CTA, split-K over pixels.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> global).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, then the epilogue warps
+// (TMEM -> registers -> global): 8 in the forward/dgrad kernel (two per TMEM lane quarter, each taking half
+// of the tile's columns -- with one warp per SM sub-partition the epilogue, not the tensor core, paced every
+// layer with K <= 2304), 4 in the weight-gradient kernel.
 #include "common.cuh"
 #include "conv_tc.h"
 
 namespace l2i {
 
-static constexpr int kThreads = 192;
+static constexpr int kThreads = 192;       // weight-gradient kernel
+static constexpr int kFwdThreads = 320;    // forward / data-gradient kernel: 2 + 8 warps
 static constexpr int kBK = 64;          // bf16 elements per smem row (128 B, SWIZZLE_128B)
 static constexpr int kTileBytes = 128 * kBK * 2;   // one 128-row operand tile: 16 KB
 static constexpr int kPassLen = 36;     // k-iterations (of 4 k16 steps) accumulated inside TMEM before the epilogue takes over
@@ -70,7 +73,7 @@ __device__ __forceinline__ void add_pass_chunk(uint32_t taddr, bool first, float
 // The TMA producer and the MMA issuer run ahead across tile boundaries (the smem ring never drains);
 // with two TMEM accumulator buffers the epilogue of tile i overlaps the main loop of tile i+1.
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                 const ConvFwdParams p) {
@@ -99,7 +102,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 128);
+      mbar_init(&tempty_bar[b], kFwdThreads - 64);
     }
     fence_barrier_init();
   }
@@ -177,8 +180,11 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       }
     }
   } else {
-    // ---- epilogue: warp q owns TMEM lanes [32q, 32q+32) = GEMM rows = pixels of the patch
+    // ---- epilogue: warps 2..9; warp w reads TMEM lanes [32q, 32q+32), q = w % 4 (GEMM rows = pixels of the
+    // patch) and the column half (w - 2) / 4 of the tile
+    constexpr int HN = BN / 2;
     const int q = warp & 3;
+    const int c_half = ((warp - 2) >> 2) * HN;
     const int m = q * 32 + lane;
     const int tw = m % p.TW;
     const int th = (m / p.TW) % p.TH;
@@ -187,14 +193,14 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const bool writer = (p.pool == 0) || (((tw | th) & 1) == 0);
     const float pool_scale = (p.pool == 1) ? 0.25f : 1.0f;
     int pass_i = 0;
-    float acc[BN];
+    float acc[HN];
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nt = t % p.n_tiles;
       const int mt = t / p.n_tiles;
       const int w = (mt % p.tiles_w) * p.TW + tw;
       const int h = ((mt / p.tiles_w) % p.tiles_h) * p.TH + th;
       const int n_img = (mt / (p.tiles_w * p.tiles_h)) * p.TN + tn;
-      const int co0 = nt * BN;
+      const int co0 = nt * BN + c_half;
       const bool row_ok = n_img < p.N;
       const size_t pix = (static_cast<size_t>(n_img) * p.H + h) * p.W + w;          // conv output pixel
       size_t opix = pix;                                                            // stored pixel
@@ -206,17 +212,17 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const int buf = pass_i & 1;
         mbar_wait(&tfull_bar[buf], (pass_i >> 1) & 1);
         tc_fence_after();
-        const uint32_t t_base = tmem_base + buf * (2 * BN) + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t t_base = tmem_base + buf * (2 * BN) + c_half + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = 0; c < HN; c += 32) {
           if (co0 + c < p.cout) add_pass_chunk<BN>(t_base + c, ps == 0, acc + c);
         }
         tc_fence_before();
-        mbar_arrive(&tempty_bar[buf]);              // 128 arrivals hand the buffer back to the MMA issuer
+        mbar_arrive(&tempty_bar[buf]);              // 256 arrivals hand the buffer back to the MMA issuer
       }
       // ---- finalize and store (the tensor core is already working on the next pass / tile)
 #pragma unroll
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = 0; c < HN; c += 32) {
         const int cbase = co0 + c;
         if (cbase >= p.cout) continue;                                              // warp-uniform
         float* v = acc + c;
@@ -241,13 +247,23 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             }
           }
         }
+        float bz[32];
+        if (p.bias && vec_ok && cbase + 32 <= p.cout) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));   // warp-uniform address
+            bz[j] = b4.x; bz[j + 1] = b4.y; bz[j + 2] = b4.z; bz[j + 3] = b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bz[j] = (p.bias && cbase + j < p.cout) ? __ldg(p.bias + cbase + j) : 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int co = cbase + j;
           float x = v[j];
           if (co < p.cout && row_ok) {
-            if (p.bias) x += __ldg(p.bias + co);
-            x *= p.out_scale;
+            x = (x + bz[j]) * p.out_scale;
             if (use_mask) {
               const uint32_t bits = (mk[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
               if ((bits & 0x8000u) || (bits & 0x7FFFu) == 0) x = 0.f;              // saved activation <= 0
@@ -579,7 +595,7 @@ static int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_fwd): %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
     configured = true;
   }
-  conv_fwd_kernel<BN><<<grid, kThreads, FwdCfg<BN>::kSmem, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  conv_fwd_kernel<BN><<<grid, kFwdThreads, FwdCfg<BN>::kSmem, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
   return check_launch("conv_fwd_kernel");
 }
 
