@@ -42,10 +42,11 @@ int l2i_act_split(const float* x, int N, int H, int W, int C, int relu, int up2,
                   void* stream);
 
 /* Residual-block operand preparation: one read of x [N,H,W,C] fp32 gives pair a = relu_a ? relu(x) : x at
- * full resolution and, for b_mode 1 / 2, pair b = x / avgpool2x2(x) (never ReLU'd) -- the inputs of conv1 and
- * of the 1x1 shortcut of rcnn_discriminator_app.py:294-344. */
+ * full resolution and, for b_mode 1 / 2, pair b = b_scale * x / b_scale * (2x2 sum of x) (never ReLU'd):
+ * b_scale 0.25 = avg_pool2d (input of the pooled 1x1 shortcut of rcnn_discriminator_app.py:294-344), 1.0 = the
+ * backward of nearest x2 up-sampling (resnet_generator_app_v2.py:665-670). */
 int l2i_act_split2(const float* x, int N, int H, int W, int C, int relu_a, void* a_hi, void* a_lo, int b_mode,
-                   void* b_hi, void* b_lo, int cpad, void* stream);
+                   float b_scale, void* b_hi, void* b_lo, int cpad, void* stream);
 /* Gradient arriving at a block output, g [N,H,W,C] fp32: pair (lo_hi, lo_lo) = g (nullable), pair (up_hi, up_lo)
  * = up_scale * nearest_x2(g) at [N,2H,2W,cpad] (nullable; up_scale 0.25 = backward of avg_pool2d), and
  * colsum [C] = sum over pixels of g (the bias gradients). */

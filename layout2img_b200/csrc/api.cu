@@ -47,8 +47,8 @@ int l2i_act_split(const float* x, int N, int H, int W, int C, int relu, int up2,
 }
 
 int l2i_act_split2(const float* x, int N, int H, int W, int C, int relu_a, void* a_hi, void* a_lo, int b_mode,
-                   void* b_hi, void* b_lo, int cpad, void* stream) {
-  return act_split2(x, N, H, W, C, relu_a, a_hi, a_lo, b_mode, b_hi, b_lo, cpad, ST(stream));
+                   float b_scale, void* b_hi, void* b_lo, int cpad, void* stream) {
+  return act_split2(x, N, H, W, C, relu_a, a_hi, a_lo, b_mode, b_scale, b_hi, b_lo, cpad, ST(stream));
 }
 int l2i_grad_split(const float* g, int N, int H, int W, int C, void* lo_hi, void* lo_lo, float up_scale, void* up_hi,
                    void* up_lo, float* colsum, int cpad, void* stream) {

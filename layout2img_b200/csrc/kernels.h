@@ -15,8 +15,8 @@ int weight_prep(const float* w, const float* sigma, int cout, int cin, int taps,
 int act_split(const float* x, int N, int H, int W, int C, int relu, int up2, void* hi, void* lo, int cpad,
               cudaStream_t stream);
 
-int act_split2(const float* x, int N, int H, int W, int C, int relu_a, void* a_hi, void* a_lo, int b_mode, void* b_hi,
-               void* b_lo, int cpad, cudaStream_t stream);
+int act_split2(const float* x, int N, int H, int W, int C, int relu_a, void* a_hi, void* a_lo, int b_mode, float b_scale,
+               void* b_hi, void* b_lo, int cpad, cudaStream_t stream);
 int grad_split(const float* g, int N, int H, int W, int C, void* lo_hi, void* lo_lo, float up_scale, void* up_hi,
                void* up_lo, float* colsum, int cpad, cudaStream_t stream);
 int pair_colsum(const void* hi, const void* lo, long long pixels, int C, int cpad, float* colsum, cudaStream_t stream);

@@ -148,11 +148,12 @@ __device__ __forceinline__ void store_pair8(const float (&v)[8], __nv_bfloat16* 
   *reinterpret_cast<uint4*>(lo) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
 }
 
-// a = relu?(x) at full resolution; b = x (b_mode 1) or avgpool2(x) (b_mode 2), never ReLU'd.
+// a = relu?(x) at full resolution; b = b_scale * x (b_mode 1) or b_scale * (2x2 sum of x) (b_mode 2), never ReLU'd.
 // One thread: 8 channels of one pixel (b_mode 0/1) or of one 2x2 quad (b_mode 2).
 __global__ void act_split2_kernel(const float* __restrict__ x, int N, int H, int W, int C, int relu_a,
                                   __nv_bfloat16* __restrict__ a_hi, __nv_bfloat16* __restrict__ a_lo, int b_mode,
-                                  __nv_bfloat16* __restrict__ b_hi, __nv_bfloat16* __restrict__ b_lo, int cpad) {
+                                  float b_scale, __nv_bfloat16* __restrict__ b_hi, __nv_bfloat16* __restrict__ b_lo,
+                                  int cpad) {
   const int groups = cpad >> 3;
   const int sh = (b_mode == 2) ? 1 : 0;
   const int Hq = H >> sh, Wq = W >> sh;
@@ -182,17 +183,15 @@ __global__ void act_split2_kernel(const float* __restrict__ x, int N, int H, int
       }
     }
     if (b_mode) {
-      if (sh) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
-      }
+      for (int j = 0; j < 8; ++j) acc[j] *= b_scale;
       store_pair8(acc, b_hi + q * cpad + g * 8, b_lo + q * cpad + g * 8);
     }
   }
 }
 
-int act_split2(const float* x, int N, int H, int W, int C, int relu_a, void* a_hi, void* a_lo, int b_mode, void* b_hi,
-               void* b_lo, int cpad, cudaStream_t stream) {
+int act_split2(const float* x, int N, int H, int W, int C, int relu_a, void* a_hi, void* a_lo, int b_mode, float b_scale,
+               void* b_hi, void* b_lo, int cpad, cudaStream_t stream) {
   if (!x || !a_hi || !a_lo || N <= 0 || H <= 0 || W <= 0 || C <= 0 || cpad < C || cpad % 8 || b_mode < 0 || b_mode > 2 ||
       (b_mode && (!b_hi || !b_lo)) || (b_mode == 2 && ((H | W) & 1))) {
     set_error("act_split2: bad arguments (N=%d H=%d W=%d C=%d cpad=%d b_mode=%d)", N, H, W, C, cpad, b_mode);
@@ -204,7 +203,7 @@ int act_split2(const float* x, int N, int H, int W, int C, int relu_a, void* a_h
   if (blocks > 148 * 32) blocks = 148 * 32;
   act_split2_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
       x, N, H, W, C, relu_a, reinterpret_cast<__nv_bfloat16*>(a_hi), reinterpret_cast<__nv_bfloat16*>(a_lo), b_mode,
-      reinterpret_cast<__nv_bfloat16*>(b_hi), reinterpret_cast<__nv_bfloat16*>(b_lo), cpad);
+      b_scale, reinterpret_cast<__nv_bfloat16*>(b_hi), reinterpret_cast<__nv_bfloat16*>(b_lo), cpad);
   return check_launch("act_split2_kernel");
 }
 

@@ -42,35 +42,61 @@ __global__ void __launch_bounds__(128) psp_pool_fwd_kernel(const float* __restri
   }
 }
 
-// dx[b,h,w,c] = base[b,h,w,base_off + c] (optional) + sum over the cells that contain (h,w) of dpooled / area
+// dx[b,h,w,c] = base[b,h,w,base_off + c] (optional) + sum over the cells that contain (h,w) of dpooled / area.
+// block = (image row h, image b); the (<= 2 per axis and stage) bins covering each coordinate are tabulated in
+// shared memory once per block; thread <-> (w, float4 channel group).
 __global__ void __launch_bounds__(256) psp_pool_bwd_kernel(const float* __restrict__ dpooled, const float* __restrict__ base,
-                                                           int base_stride, int base_off, int B, int H, int W, int C,
+                                                           int base_stride, int base_off, int H, int W, int C,
                                                            float* __restrict__ dx) {
-  const long long total = 1LL * B * H * W * C;
-  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
-    const int c = static_cast<int>(i % C);
-    const long long pix = i / C;
-    const int w = static_cast<int>(pix % W);
-    const int h = static_cast<int>((pix / W) % H);
-    const int b = static_cast<int>(pix / (1LL * W * H));
-    float acc = base ? __ldg(base + pix * base_stride + base_off + c) : 0.f;
+  extern __shared__ unsigned char s_raw[];
+  int* s_wbin = reinterpret_cast<int*>(s_raw);                    // [4][W][2]
+  float* s_winv = reinterpret_cast<float*>(s_wbin + 8 * W);        // [4][W][2]
+  __shared__ int s_hbin[4][2];
+  __shared__ float s_hinv[4][2];
+  const int h = blockIdx.x, b = blockIdx.y;
+  for (int i = threadIdx.x; i < 4 * (W + 1); i += blockDim.x) {
+    const int st = i / (W + 1), pos = i % (W + 1);
+    const int s = kPspSize[st];
+    const bool is_h = pos == W;
+    const int coord = is_h ? h : pos, extent = is_h ? H : W;
+    int n = 0, bins[2] = {-1, -1};
+    float inv[2] = {0.f, 0.f};
+    const int c0 = (coord * s) / extent;
+    for (int k = max(c0 - 1, 0); k <= min(c0 + 1, s - 1) && n < 2; ++k) {
+      const int lo = bin_start(k, extent, s), hi = bin_end(k, extent, s);
+      if (coord >= lo && coord < hi) { bins[n] = k; inv[n] = 1.0f / static_cast<float>(hi - lo); ++n; }
+    }
+    for (int k = 0; k < 2; ++k) {
+      if (is_h) { s_hbin[st][k] = bins[k]; s_hinv[st][k] = inv[k]; }
+      else { s_wbin[(st * W + pos) * 2 + k] = bins[k]; s_winv[(st * W + pos) * 2 + k] = inv[k]; }
+    }
+  }
+  __syncthreads();
+  const int c4n = C >> 2;
+  const float* dp = dpooled + static_cast<size_t>(b) * kPspCells * C;
+  for (int i = threadIdx.x; i < W * c4n; i += blockDim.x) {
+    const int w = i / c4n, c = (i - w * c4n) * 4;
+    const size_t pix = (static_cast<size_t>(b) * H + h) * W + w;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (base) acc = __ldg(reinterpret_cast<const float4*>(base + pix * base_stride + base_off + c));
 #pragma unroll
     for (int st = 0; st < 4; ++st) {
       const int s = kPspSize[st];
-      // candidate bins: floor(h*s/H) and its predecessor (adaptive bins overlap by at most one pixel row)
-      const int by = (h * s) / H, bx = (w * s) / W;
-      for (int iy = max(by - 1, 0); iy <= min(by + 1, s - 1); ++iy) {
-        const int h0 = bin_start(iy, H, s), h1 = bin_end(iy, H, s);
-        if (h < h0 || h >= h1) continue;
-        for (int ix = max(bx - 1, 0); ix <= min(bx + 1, s - 1); ++ix) {
-          const int w0 = bin_start(ix, W, s), w1 = bin_end(ix, W, s);
-          if (w < w0 || w >= w1) continue;
-          acc += __ldg(dpooled + (static_cast<size_t>(b) * kPspCells + kPspOff[st] + iy * s + ix) * C + c) /
-                 static_cast<float>((h1 - h0) * (w1 - w0));
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int iy = s_hbin[st][a];
+        if (iy < 0) continue;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ix = s_wbin[(st * W + w) * 2 + e];
+          if (ix < 0) continue;
+          const float wt = s_hinv[st][a] * s_winv[(st * W + w) * 2 + e];
+          const float4 g = __ldg(reinterpret_cast<const float4*>(dp + static_cast<size_t>(kPspOff[st] + iy * s + ix) * C + c));
+          acc.x = fmaf(wt, g.x, acc.x); acc.y = fmaf(wt, g.y, acc.y); acc.z = fmaf(wt, g.z, acc.z); acc.w = fmaf(wt, g.w, acc.w);
         }
       }
     }
-    dx[i] = acc;
+    *reinterpret_cast<float4*>(dx + pix * C + c) = acc;
   }
 }
 
@@ -170,11 +196,11 @@ int psp_pool_fwd(const float* x, int B, int H, int W, int C, float* pooled, cuda
 
 int psp_pool_bwd(const float* dpooled, const float* base, int base_stride, int base_off, int B, int H, int W, int C,
                  float* dx, cudaStream_t stream) {
-  if (!dpooled || !dx || B <= 0 || H < 6 || W < 6 || C <= 0) { set_error("psp_pool_bwd: bad arguments"); return L2I_ERR_BAD_ARG; }
-  const long long total = 1LL * B * H * W * C;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  psp_pool_bwd_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(dpooled, base, base_stride, base_off, B, H, W, C, dx);
+  if (!dpooled || !dx || B <= 0 || H < 6 || W < 6 || C <= 0 || (C & 3) || W > 512 || (base && ((base_stride | base_off) & 3))) {
+    set_error("psp_pool_bwd: bad arguments (C and the base offsets must be multiples of 4)");
+    return L2I_ERR_BAD_ARG;
+  }
+  psp_pool_bwd_kernel<<<dim3(H, B), 256, 16 * W * sizeof(float), stream>>>(dpooled, base, base_stride, base_off, H, W, C, dx);
   return check_launch("psp_pool_bwd_kernel");
 }
 

@@ -177,6 +177,90 @@ def d_block_raw(x, w1, b1, w2, b2, wsc=None, bsc=None, down=False, optimized=Fal
     return DBlockFn.apply(x, w1, b1, w2, b2, wsc, bsc, down, optimized, None, None, None)
 
 
+class GBlockFn(torch.autograd.Function):
+    """A whole up-sampling generator block (reference resnet_generator_app_v2.py:653-678, ResBlock.residual +
+    shortcut) as one autograd node:
+
+        out = conv2(relu(b2(conv1(up2(relu(b1(x))))))) + up2(c_sc(x)),   b1/b2 = ISLA norm (norm_module.py:163-186)
+
+    Forward: 2 x (batch statistics, ISLA apply -> ReLU -> [nearest x2] -> bf16 operand pair), 3 tensor-core convs
+    (the 1x1 shortcut at the low resolution, added up-sampled in conv2's epilogue).  Backward: every gradient
+    tensor is read once -- the 2x2 sums that undo the up-sampling are taken in the data-gradient epilogue (conv1)
+    and in the operand-preparation kernel (shortcut); bias gradients come from the same passes."""
+
+    @staticmethod
+    def forward(ctx, x, mask1, gamma1, beta1, mask2, gamma2, beta2, w1, b1, w2, b2, wsc, bsc, sn1, sn2, snsc, bn1, bn2):
+        # bn* = (running_mean, running_var, training, momentum, eps); sn* as in DBlockFn
+        x = _c(x)
+        mask1, gamma1, beta1, mask2, gamma2, beta2 = (_c(t) for t in (mask1, gamma1, beta1, mask2, gamma2, beta2))
+        cin, ch, cout = w1.shape[1], w1.shape[0], w2.shape[0]
+
+        def stats(t, bn):
+            rm, rv, training, momentum, eps = bn
+            return ops.bn_batch_stats(t, rm, rv, eps, momentum) if training else ops.bn_eval_stats(rm, rv, eps)
+
+        st1 = ops.sn_sigma(_c(w1), *sn1[:2], training=sn1[3], eps=sn1[2]) if sn1 else None
+        st2 = ops.sn_sigma(_c(w2), *sn2[:2], training=sn2[3], eps=sn2[2]) if sn2 else None
+        stsc = ops.sn_sigma(_c(wsc), *snsc[:2], training=snsc[3], eps=snsc[2]) if snsc else None
+        wp1 = ops.conv_weight_prep(_c(w1), st1.sigma if st1 else None, need_dgrad=True)
+        wp2 = ops.conv_weight_prep(_c(w2), st2.sigma if st2 else None, need_dgrad=True)
+        wps = ops.conv_weight_prep(_c(wsc), stsc.sigma if stsc else None, need_dgrad=True)
+        mi1 = stats(x, bn1)
+        _, a0 = ops.isla_fwd(x, mi1, mask1, gamma1, beta1, None, None, relu=True, up2=True)
+        h1, _ = ops.conv2d_fwd(a0, wp1.f_hi, wp1.f_lo, ch, 9, bias=_c(b1))
+        mi2 = stats(h1, bn2)
+        _, a1 = ops.isla_fwd(h1, mi2, mask2, gamma2, beta2, None, None, relu=True, up2=False)
+        xs = ops.act_split(x)
+        sc, _ = ops.conv2d_fwd(xs, wps.f_hi, wps.f_lo, cout, 1, bias=_c(bsc))
+        out, _ = ops.conv2d_fwd(a1, wp2.f_hi, wp2.f_lo, cout, 9, bias=_c(b2), residual=sc, res_up2=True)
+        none3 = (None, None, None)
+        ctx.save_for_backward(x, mi1, mask1, gamma1, beta1, a0.hi, a0.lo, h1, mi2, mask2, gamma2, beta2, a1.hi, a1.lo,
+                              xs.hi, xs.lo, wp1.d_hi, wp1.d_lo, wp2.d_hi, wp2.d_lo, wps.d_hi, wps.d_lo, w1, w2, wsc,
+                              *(st1 or none3), *(st2 or none3), *(stsc or none3))
+        ctx.meta = (cin, ch, cout, bn1[2], bn2[2])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x, mi1, mask1, gamma1, beta1, a0h, a0l, h1, mi2, mask2, gamma2, beta2, a1h, a1l, xsh, xsl,
+         d1h, d1l, d2h, d2l, dsh, dsl, w1, w2, wsc, sg1, u1, v1, sg2, u2, v2, sgs, us, vs) = ctx.saved_tensors
+        cin, ch, cout, train1, train2 = ctx.meta
+        dout = _c(dout)
+
+        def wgrad(dy, xin, taps, w, sg, u, v):
+            g = ops.conv2d_wgrad(dy, xin, taps)
+            if sg is not None:
+                return ops.sn_weight_grad(g, w, ops.SNState(sg, u, v))
+            return _dw_to_torch(g, g.shape[0], g.shape[2], taps)
+
+        # gradient at the block output: full-resolution pair (conv2) + 2x2-summed pair (shortcut) in one read
+        g_full, g_sum = ops.act_split2(dout, relu_a=False, b_mode=2, b_scale=1.0)
+        db2 = ops.pair_colsum(g_sum)                          # = sum over pixels of dout = d bias of conv2 and c_sc
+        dw2 = wgrad(g_full, ops.Pair(a1h, a1l, ch), 9, w2, sg2, u2, v2)
+        da1, _ = ops.conv2d_fwd(g_full, d2h, d2l, ch, 9)
+        dh1, dmask2, dgamma2, dbeta2, _ = ops.isla_bwd(h1, mi2, mask2, gamma2, beta2, None, None, da1, relu=True,
+                                                       up2=False, train=train2)
+        dh1_p, _, db1 = ops.grad_split(dh1, want_lo=True, up=False)
+        dw1 = wgrad(dh1_p, ops.Pair(a0h, a0l, cin), 9, w1, sg1, u1, v1)
+        da0, _ = ops.conv2d_fwd(dh1_p, d1h, d1l, cin, 9, pool=2)        # 2x2 sum = backward of the nearest x2
+        dx1, dmask1, dgamma1, dbeta1, _ = ops.isla_bwd(x, mi1, mask1, gamma1, beta1, None, None, da0, relu=True,
+                                                       up2=False, train=train1)
+        dwsc = wgrad(g_sum, ops.Pair(xsh, xsl, cin), 1, wsc, sgs, us, vs)
+        dx, _ = ops.conv2d_fwd(g_sum, dsh, dsl, cin, 1, residual=dx1)
+        return (dx, dmask1, dgamma1, dbeta1, dmask2, dgamma2, dbeta2, dw1, db1, dw2, db2, dwsc, db2.clone(),
+                None, None, None, None, None)
+
+
+def g_block(x, mask1, gamma1, beta1, mask2, gamma2, beta2, conv1, conv2, c_sc, bn1, bn2):
+    """Fused up-sampling generator block from its modules (resnet_generator_app_v2.py:628-678)."""
+    w1, b1, sn1 = _sn_of(conv1)
+    w2, b2, sn2 = _sn_of(conv2)
+    wsc, bsc, snsc = _sn_of(c_sc)
+    pack = lambda bn: (bn.running_mean, bn.running_var, bn.training, bn.momentum, bn.eps)
+    return GBlockFn.apply(x, mask1, gamma1, beta1, mask2, gamma2, beta2, w1, b1, w2, b2, wsc, bsc, sn1, sn2, snsc,
+                          pack(bn1), pack(bn2))
+
+
 class NormConvFn(torch.autograd.Function):
     """y = conv(up2?(relu(norm(x))), W) + bias + residual with norm = ISLA (mask_pm given) or affine/plain
     batch norm (mask_pm None).  reference: ResBlock.residual resnet_generator_app_v2.py:653-663,

@@ -127,10 +127,18 @@ class ResBlock(nn.Module):
                                                Conv2d(100, 184, 1, 1, 0, bias=True))
 
     def forward(self, in_feat, w, bbox):            # in_feat NHWC, bbox (b,o,hm,wm)
-        up = self.upsample
-        x = self.conv1(in_feat, up2_in=up, norm=self.b1.operands(in_feat, w, bbox))
-        sc = self.c_sc(in_feat) if self.learnable_sc else in_feat
-        out_feat = self.conv2(x, residual=sc, res_up2=up and self.learnable_sc, norm=self.b2.operands(x, w, bbox))
+        if not (self.upsample and self.learnable_sc):
+            raise ValueError("layout2img_b200 ResBlock implements the generator's configuration: upsample=True")
+        b, h, wd, _ = in_feat.shape
+        o = bbox.shape[1]
+        # ISLA operands (norm_module.py:173-180): masks bilinearly resized to each norm's resolution, pixel-major;
+        # gamma / beta = spectrally normalised linear projections of the object latents
+        m1 = L.mask_resize(bbox, h, wd, True)
+        m2 = L.mask_resize(bbox, 2 * h, 2 * wd, True)
+        g1, be1 = self.b1.weight_proj(w).view(b, o, -1), self.b1.bias_proj(w).view(b, o, -1)
+        g2, be2 = self.b2.weight_proj(w).view(b, o, -1), self.b2.bias_proj(w).view(b, o, -1)
+        out_feat = L.g_block(in_feat, m1, g1, be1, m2, g2, be2, self.conv1, self.conv2, self.c_sc,
+                             self.b1.batch_norm2d, self.b2.batch_norm2d)
         if not self.predict_mask:
             return out_feat, None
         if self.psp:

@@ -99,8 +99,11 @@ def act_split(x: torch.Tensor, relu: bool = False, up2: bool = False) -> Pair:
     return Pair(out[0], out[1], c)
 
 
-def act_split2(x: torch.Tensor, relu_a: bool, b_mode: int):
-    """x (N,H,W,C) -> (pair a = relu_a ? relu(x) : x, pair b = None | x | avgpool2(x))  [b_mode 0 | 1 | 2]."""
+def act_split2(x: torch.Tensor, relu_a: bool, b_mode: int, b_scale: Optional[float] = None):
+    """x (N,H,W,C) -> (pair a = relu_a ? relu(x) : x, pair b = None | x | avgpool2(x))  [b_mode 0 | 1 | 2];
+    b_scale overrides b's factor (default 1 for b_mode 1, 0.25 = average for b_mode 2; 1.0 there = 2x2 sum)."""
+    if b_scale is None:
+        b_scale = 0.25 if b_mode == 2 else 1.0
     _chk(x)
     n, h, w, c = x.shape
     cp = pad8(c)
@@ -110,8 +113,8 @@ def act_split2(x: torch.Tensor, relu_a: bool, b_mode: int):
         b = torch.empty((2, n, h, w, cp), dtype=torch.bfloat16, device=x.device)
     elif b_mode == 2:
         b = torch.empty((2, n, h // 2, w // 2, cp), dtype=torch.bfloat16, device=x.device)
-    call("l2i_act_split2", x, n, h, w, c, int(relu_a), a[0], a[1], int(b_mode), b[0] if b is not None else None,
-         b[1] if b is not None else None, cp)
+    call("l2i_act_split2", x, n, h, w, c, int(relu_a), a[0], a[1], int(b_mode), float(b_scale),
+         b[0] if b is not None else None, b[1] if b is not None else None, cp)
     return Pair(a[0], a[1], c), (Pair(b[0], b[1], c) if b is not None else None)
 
 
