@@ -224,7 +224,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 #pragma unroll
       for (int c = 0; c < HN; c += 32) {
         const int cbase = co0 + c;
-        if (cbase >= p.cout) continue;                                              // warp-uniform
+        if (cbase >= (p.out_hi ? p.cout_pad : p.cout)) continue;                    // warp-uniform; pad channels of a pair are written as zeros
         float* v = acc + c;
         // (acc + bias) * out_scale, ReLU-derivative mask
         uint32_t mk[16];

@@ -513,12 +513,24 @@ int isla_bwd(const float* x, const float* mean_invstd, const float* mask, const 
   {
     long long blocks = (pixels + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    const bool half = C <= 64;
-    if (half) blocks = (blocks + 1) / 2;
+    // lanes per pixel: each lane should own >= 4 float4 channel groups, so that the per-pixel shuffle reduction
+    // of the O mask gradients is amortised (C = 64 -> 4 lanes, 8 pixels per warp; C >= 512 -> a whole warp)
+    int lpp = C / 16;
+    lpp = lpp < 4 ? 4 : (lpp > 32 ? 32 : lpp);
+    while (lpp & (lpp - 1)) lpp &= lpp - 1;              // power of two
+    blocks = (pixels * lpp / 32 + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
     const int nb = static_cast<int>(blocks);
-    if (O <= 8) { if (half) isla_bwd_a_kernel<8, 16><<<nb, 256, 0, stream>>>(p); else isla_bwd_a_kernel<8, 32><<<nb, 256, 0, stream>>>(p); }
-    else if (O <= 16) { if (half) isla_bwd_a_kernel<16, 16><<<nb, 256, 0, stream>>>(p); else isla_bwd_a_kernel<16, 32><<<nb, 256, 0, stream>>>(p); }
-    else { if (half) isla_bwd_a_kernel<48, 16><<<nb, 256, 0, stream>>>(p); else isla_bwd_a_kernel<48, 32><<<nb, 256, 0, stream>>>(p); }
+#define L2I_ISLA_A(OM)                                                                   \
+    switch (lpp) {                                                                       \
+      case 4: isla_bwd_a_kernel<OM, 4><<<nb, 256, 0, stream>>>(p); break;                \
+      case 8: isla_bwd_a_kernel<OM, 8><<<nb, 256, 0, stream>>>(p); break;                \
+      case 16: isla_bwd_a_kernel<OM, 16><<<nb, 256, 0, stream>>>(p); break;              \
+      default: isla_bwd_a_kernel<OM, 32><<<nb, 256, 0, stream>>>(p); break;              \
+    }
+    if (O <= 8) { L2I_ISLA_A(8) } else if (O <= 16) { L2I_ISLA_A(16) } else { L2I_ISLA_A(48) }
+#undef L2I_ISLA_A
     int rc = check_launch("isla_bwd_a_kernel");
     if (rc) return rc;
   }

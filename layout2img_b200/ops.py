@@ -15,7 +15,11 @@ from ._lib import call
 
 
 def pad8(c: int) -> int:
-    return (c + 7) // 8 * 8
+    """Channel count of a tensor-core operand pair: a multiple of 8 (TMA's 16-byte stride rule).  Tiny channel
+    counts (RGB images, 1-channel mask logits) are padded to a full 64-wide K chunk: a TMA box that is mostly
+    out of bounds in the channel dimension runs ~3x slower than the same box over zero-filled memory
+    (measured on D.block1.conv1: 970 us -> 330 us), and the padding costs < 0.3 GB of the 180 GB HBM."""
+    return 64 if c <= 8 else (c + 7) // 8 * 8
 
 
 class Pair(NamedTuple):
