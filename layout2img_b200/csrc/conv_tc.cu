@@ -30,6 +30,7 @@
 // (TMEM -> registers -> global): 8 in the forward/dgrad kernel (two per TMEM lane quarter, each taking half
 // of the tile's columns -- with one warp per SM sub-partition the epilogue, not the tensor core, paced every
 // layer with K <= 2304), 4 in the weight-gradient kernel.
+#include <stdlib.h>
 #include "common.cuh"
 #include "conv_tc.h"
 
@@ -44,12 +45,22 @@ static constexpr int kPassLen = 36;     // k-iterations (of 4 k16 steps) accumul
 // ------------------------------------------------------------------------------------------
 // forward / dgrad
 // ------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool HALO>
 struct FwdCfg {
+  // plain mode: one ring; a stage = the (A hi, A lo, B hi, B lo) tiles of one (tap, 64-channel chunk)
   static constexpr int kStages = (BN == 128) ? 3 : 4;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = 2 * kTileBytes + 2 * kBBytes;
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // halo mode (3x3 on an 8 x 16 pixel patch): ring A holds the (16+2) x 16 pixel halo patch of one 64-channel
+  // chunk ONCE for all nine taps (a tap's A operand is a shifted window into it); ring B streams the nine
+  // weight tiles.  L2 -> SM traffic per chunk: 72 KB + 9 B-tiles instead of 9 x (32 KB + B-tile).
+  static constexpr int kHaloRows = 18 * 16;                         // patch rows of 128 B
+  static constexpr int kHaloBytes = kHaloRows * 128;                // per half (hi or lo): 36 KB
+  static constexpr int kAStages = 2;
+  static constexpr int kBStages = (BN == 128) ? 2 : 4;
+  static constexpr int kBStageBytes = 2 * kBBytes;
+  static constexpr int kRingBytes = HALO ? (kAStages * 2 * kHaloBytes + kBStages * kBStageBytes) : (kStages * kStageBytes);
+  static constexpr int kSmem = kRingBytes + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 512;      // whole TMEM: one CTA per SM (shared memory already enforces it)
 };
 
@@ -72,23 +83,28 @@ __device__ __forceinline__ void add_pass_chunk(uint32_t taddr, bool first, float
 // Persistent kernel: gridDim.x CTAs (one per SM) walk the (m_tile, n_tile) list with stride gridDim.x.
 // The TMA producer and the MMA issuer run ahead across tile boundaries (the smem ring never drains);
 // with two TMEM accumulator buffers the epilogue of tile i overlaps the main loop of tile i+1.
-template <int BN>
+template <int BN, bool HALO>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                 const ConvFwdParams p) {
-  using Cfg = FwdCfg<BN>;
+  using Cfg = FwdCfg<BN, HALO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tfull_bar = empty_bar + Cfg::kStages;     // [2] accumulator buffer complete
+  // barriers: plain: full/empty [kStages]; halo: A full/empty [kAStages] then B full/empty [kBStages]
+  constexpr int kNBarA = HALO ? Cfg::kAStages : Cfg::kStages;
+  constexpr int kNBarB = HALO ? Cfg::kBStages : 0;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kRingBytes);
+  uint64_t* empty_bar = full_bar + kNBarA;
+  uint64_t* bfull_bar = empty_bar + kNBarA;
+  uint64_t* bempty_bar = bfull_bar + kNBarB;
+  uint64_t* tfull_bar = bempty_bar + kNBarB;          // [2] accumulator buffer complete
   uint64_t* tempty_bar = tfull_bar + 2;               // [2] accumulator buffer drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int k_iters = p.taps * p.kchunks;
+  const int k_iters = HALO ? p.kchunks : p.taps * p.kchunks;   // halo: one iteration = one chunk, all nine taps
   const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
@@ -96,9 +112,13 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     tma_prefetch_desc(&tm_a_lo);
     tma_prefetch_desc(&tm_b_hi);
     tma_prefetch_desc(&tm_b_lo);
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < kNBarA; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kNBarB; ++s) {
+      mbar_init(&bfull_bar[s], 1);
+      mbar_init(&bempty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
@@ -113,7 +133,41 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0 && HALO) {
+      // order: A(j+1) is requested before the nine B tiles of chunk j, so the patch of the next chunk (or tile)
+      // lands while the tensor core works on the current one
+      uint8_t* b_ring = smem + Cfg::kAStages * 2 * Cfg::kHaloBytes;
+      int ja = 0, jb = 0;                         // A-ring / B-ring counters, run on across tiles
+      auto load_a = [&](int t, int kc) {
+        const int mt = t / p.n_tiles;
+        const int w0 = (mt % p.tiles_w) * p.TW;
+        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = mt / (p.tiles_w * p.tiles_h);
+        const int s = ja % Cfg::kAStages;
+        mbar_wait(&empty_bar[s], ((ja / Cfg::kAStages) & 1) ^ 1);
+        uint8_t* st = smem + s * 2 * Cfg::kHaloBytes;
+        mbar_expect_tx(&full_bar[s], 2 * Cfg::kHaloBytes);
+        tma_load_4d(st, &tm_a_hi, &full_bar[s], kc * kBK, w0 - 1, h0 - 1, n0);
+        tma_load_4d(st + Cfg::kHaloBytes, &tm_a_lo, &full_bar[s], kc * kBK, w0 - 1, h0 - 1, n0);
+        ++ja;
+      };
+      if (blockIdx.x < total_tiles) load_a(blockIdx.x, 0);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int co0 = (t % p.n_tiles) * BN;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          if (kc + 1 < p.kchunks) load_a(t, kc + 1);
+          else if (t + static_cast<int>(gridDim.x) < total_tiles) load_a(t + gridDim.x, 0);
+          for (int tap = 0; tap < 9; ++tap, ++jb) {
+            const int s = jb % Cfg::kBStages;
+            mbar_wait(&bempty_bar[s], ((jb / Cfg::kBStages) & 1) ^ 1);
+            uint8_t* st = b_ring + s * Cfg::kBStageBytes;
+            mbar_expect_tx(&bfull_bar[s], Cfg::kBStageBytes);
+            tma_load_2d(st, &tm_b_hi, &bfull_bar[s], tap * p.cin_pad + kc * kBK, co0);
+            tma_load_2d(st + Cfg::kBBytes, &tm_b_lo, &bfull_bar[s], tap * p.cin_pad + kc * kBK, co0);
+          }
+        }
+      }
+    } else if (lane == 0) {
       int ring = 0;                               // stage counter, runs on across tiles
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nt = t % p.n_tiles;
@@ -142,7 +196,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-      int ring = 0, pass_i = 0;                   // smem stage counter / accumulator pass counter (run across tiles)
+      int ring = 0, ring_b = 0, pass_i = 0;       // smem stage counters / accumulator pass counter (run across tiles)
+      (void)ring_b;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int it = 0;
         for (int ps = 0; ps < p.n_pass; ++ps, ++pass_i) {
@@ -153,6 +208,40 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           const uint32_t d_cross = d_main + BN;
           const int it_end = min(it + p.pass_len, k_iters);
           uint32_t fresh = 0;                       // 0 for the first MMA into each accumulator of the pass
+          if constexpr (HALO) {
+            const uint32_t b_ring = smem_u32(smem + Cfg::kAStages * 2 * Cfg::kHaloBytes);
+            for (; it < it_end; ++it, ++ring) {     // ring counts chunks here, ring_b the weight tiles
+              const int sa = ring % Cfg::kAStages;
+              mbar_wait(&full_bar[sa], (ring / Cfg::kAStages) & 1);
+              tc_fence_after();
+              const uint32_t a_hi = smem_u32(smem + sa * 2 * Cfg::kHaloBytes);
+              const uint32_t a_lo = a_hi + Cfg::kHaloBytes;
+#pragma unroll 1
+              for (int tap = 0; tap < 9; ++tap, ++ring_b) {
+                const int sb = ring_b % Cfg::kBStages;
+                mbar_wait(&bfull_bar[sb], (ring_b / Cfg::kBStages) & 1);
+                tc_fence_after();
+                // A operand of this tap = rows (h + tap/3) * 16 + (w + tap%3) of the halo patch: an 8-row group per
+                // image row (8 consecutive patch rows), groups 16 rows = 2048 B apart
+                const uint32_t a_off = ((tap / 3) * 16 + (tap % 3)) * 128;
+                const uint32_t b_hi = b_ring + sb * Cfg::kBStageBytes;
+                const uint32_t b_lo = b_hi + Cfg::kBBytes;
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                  const uint64_t dah = umma_desc_sw128(a_hi + a_off + k * 32, 16, 2048) | p.halo_desc_or[tap % 3];
+                  const uint64_t dal = umma_desc_sw128(a_lo + a_off + k * 32, 16, 2048) | p.halo_desc_or[tap % 3];
+                  const uint64_t dbh = umma_desc_sw128(b_hi + k * 32, 16, 1024);
+                  const uint64_t dbl = umma_desc_sw128(b_lo + k * 32, 16, 1024);
+                  umma_bf16(d_cross, dal, dbh, idesc, fresh);
+                  umma_bf16(d_cross, dah, dbl, idesc, 1u);
+                  umma_bf16(d_main, dah, dbh, idesc, fresh);
+                  fresh = 1u;
+                }
+                umma_commit(&bempty_bar[sb]);
+              }
+              umma_commit(&empty_bar[sa]);          // the patch is free once all nine taps have read it
+            }
+          } else
           for (; it < it_end; ++it, ++ring) {
             const int s = ring % Cfg::kStages;
             const uint32_t ph = (ring / Cfg::kStages) & 1;
@@ -586,17 +675,29 @@ static int sm_count() {
   return n;
 }
 
-template <int BN>
+template <int BN, bool HALO>
 static int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                       const CUtensorMap& b_lo, const ConvFwdParams& p, int grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<BN>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel<BN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         FwdCfg<BN, HALO>::kSmem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_fwd): %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
     configured = true;
   }
-  conv_fwd_kernel<BN><<<grid, kFwdThreads, FwdCfg<BN>::kSmem, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
-  return check_launch("conv_fwd_kernel");
+  conv_fwd_kernel<BN, HALO><<<grid, kFwdThreads, FwdCfg<BN, HALO>::kSmem, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  return check_launch(HALO ? "conv_fwd_kernel<halo>" : "conv_fwd_kernel");
+}
+
+// L2I_CONV_HALO=1 enables the halo-patch variant (off by default: measured on B200 it cuts L2 -> SM traffic per
+// tile from 432 KB to 221 KB at Cin = Cout = 64 but is 5-15 % SLOWER than the plain ring -- those layers are paced
+// by shared-memory bandwidth (TMA writes + UMMA operand reads) and the epilogue, not by L2).
+// L2I_CONV_HALO_BASEOFF=1 sets the descriptor's matrix-base-offset field to the patch row phase instead of 0:
+// that is WRONG on sm_100a (the 128B swizzle is a function of the shared-memory address), kept as the switch
+// that established it.
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
 }
 
 int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream) {
@@ -611,14 +712,20 @@ int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream) {
   ConvFwdParams p;
   p.N = a.N; p.H = a.H; p.W = a.W; p.cin_pad = a.cin_pad; p.cout = a.cout; p.taps = a.taps;
   if (pick_tile(a.H, a.W, 128, &p.TW, &p.TH, &p.TN) != L2I_OK) { set_error("conv: H=%d W=%d must be powers of two", a.H, a.W); return L2I_ERR_UNSUPPORTED; }
+  static const int halo_enabled = env_int("L2I_CONV_HALO", 0);
+  static const int halo_baseoff = env_int("L2I_CONV_HALO_BASEOFF", 0);
+  const bool halo = halo_enabled && a.taps == 9 && a.H >= 16 && a.W >= 8 && a.cin_pad >= 64;
+  if (halo) { p.TW = 8; p.TH = 16; p.TN = 1; }
   p.tiles_w = a.W / p.TW; p.tiles_h = a.H / p.TH;
   const int tiles_n = (a.N + p.TN - 1) / p.TN;
   p.kchunks = (a.cin_pad + kBK - 1) / kBK;
   {
-    const int k_iters = a.taps * p.kchunks;
-    p.n_pass = (k_iters + kPassLen - 1) / kPassLen;
+    const int k_iters = halo ? p.kchunks : a.taps * p.kchunks;
+    const int max_len = halo ? kPassLen / 9 : kPassLen;
+    p.n_pass = (k_iters + max_len - 1) / max_len;
     p.pass_len = (k_iters + p.n_pass - 1) / p.n_pass;
   }
+  for (int j = 0; j < 3; ++j) p.halo_desc_or[j] = halo_baseoff ? (static_cast<unsigned long long>(j & 7) << 49) : 0ull;
   p.bias = a.bias; p.residual = a.residual; p.res_shift = a.res_shift; p.res_scale = a.res_scale; p.out = a.out;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(a.out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(a.out_lo);
   p.cout_pad = a.cout_pad; p.relu_split = a.relu_split; p.out_scale = a.out_scale;
@@ -628,14 +735,20 @@ int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream) {
   p.n_tiles = (a.cout + BN - 1) / BN;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
-  if ((rc = make_act_map(&ta_hi, a.x_hi, a.N, a.H, a.W, a.cin_pad, p.TW, p.TH, p.TN))) return rc;
-  if ((rc = make_act_map(&ta_lo, a.x_lo, a.N, a.H, a.W, a.cin_pad, p.TW, p.TH, p.TN))) return rc;
+  // halo mode: the A box is the (16 + 2) x 16 pixel patch around the 8 x 16 output tile (x from w0 - 1)
+  const int bw = halo ? 16 : p.TW, bh = halo ? 18 : p.TH;
+  if ((rc = make_act_map(&ta_hi, a.x_hi, a.N, a.H, a.W, a.cin_pad, bw, bh, p.TN))) return rc;
+  if ((rc = make_act_map(&ta_lo, a.x_lo, a.N, a.H, a.W, a.cin_pad, bw, bh, p.TN))) return rc;
   if ((rc = make_w_map(&tb_hi, a.w_hi, a.cout, a.taps * a.cin_pad, BN))) return rc;
   if ((rc = make_w_map(&tb_lo, a.w_lo, a.cout, a.taps * a.cin_pad, BN))) return rc;
   const long long total = 1LL * p.m_tiles * p.n_tiles;
   const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
-  if (BN == 128) return launch_fwd<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
-  return launch_fwd<64>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
+  if (halo) {
+    if (BN == 128) return launch_fwd<128, true>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
+    return launch_fwd<64, true>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
+  }
+  if (BN == 128) return launch_fwd<128, false>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
+  return launch_fwd<64, false>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
 }
 
 template <int BN>
