@@ -176,7 +176,14 @@ def kernel_breakdown(step_fn):
         e0.record()
         r = orig(name, *a)
         e1.record()
-        rec.append((name, e0, e1, conv_flops(name, a)))
+        shape = None
+        if name == "l2i_conv2d_fwd":
+            N, H, W, cin_pad, cout, taps = a[:6]
+            shape = f"fwd N={N} H={H} cin={cin_pad} cout={cout} k={3 if taps == 9 else 1} pool={a[17]} mask={int(a[15] is not None)}"
+        elif name == "l2i_conv2d_wgrad":
+            N, H, W, cin, cin_pad, cout, cout_pad, taps = a[:8]
+            shape = f"wgrad N={N} H={H} cin={cin} cout={cout} k={3 if taps == 9 else 1}"
+        rec.append((name, e0, e1, conv_flops(name, a), shape))
         return r
 
     import layout2img_b200.ops as ops_mod
@@ -194,12 +201,19 @@ def kernel_breakdown(step_fn):
         _lib.call = orig
         ops_mod.call = orig
         optim_mod.call = orig
-    agg = {}
-    for name, e0, e1, fl in rec:
+    agg, shapes = {}, {}
+    for name, e0, e1, fl, shape in rec:
+        ms = e0.elapsed_time(e1)
         d = agg.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0})
         d["calls"] += 1
-        d["ms"] += e0.elapsed_time(e1)
+        d["ms"] += ms
         d["flops"] += fl
+        if shape:
+            sd = shapes.setdefault(shape, {"calls": 0, "ms": 0.0, "flops": 0.0})
+            sd["calls"] += 1
+            sd["ms"] += ms
+            sd["flops"] += fl
+    agg["_conv_shapes"] = shapes
     return agg, t0.elapsed_time(t1)
 
 
@@ -286,6 +300,13 @@ def run_ours(args, rank, local_rank, world):
     line = None
     # every rank runs the instrumented step (it contains the gradient all-reduces); rank 0 reports it
     agg, step_ms = kernel_breakdown(step_resident)
+    conv_shapes = agg.pop("_conv_shapes")
+    if rank == 0 and args.shapes_file:
+        with open(args.shapes_file, "w") as f:
+            f.write("# per-shape device time of the convolution launches of one G+D step (CUDA events around each C-ABI call)\n")
+            f.write(f"{'shape':64s} {'calls':>5s} {'ms':>8s} {'us/call':>8s} {'alg TFLOP/s':>11s}\n")
+            for k, v in sorted(conv_shapes.items(), key=lambda kv: -kv[1]["ms"]):
+                f.write(f"{k:64s} {v['calls']:5d} {v['ms']:8.3f} {1e3 * v['ms'] / v['calls']:8.1f} {v['flops'] / (v['ms'] / 1e3) / 1e12:11.1f}\n")
     if rank == 0:
         pk = peaks()
         conv = agg.get("l2i_conv2d_fwd", {"calls": 0, "ms": 0.0, "flops": 0.0})
@@ -341,6 +362,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (the metric is quoted at 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--shapes-file", default=None, help="write the per-shape convolution timing table here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))

@@ -444,7 +444,11 @@ struct WgCfg {
   static constexpr int kTmemCols = 4 * BN;   // two (main, cross) buffers
 };
 
-template <int BN>
+// SWAP = false: M = 128 output channels (dy), N = BN input channels (x shifted by this CTA's tap).
+// SWAP = true (chosen when Cout <= 64, where the M = 128 tile would be half padding): the roles are exchanged,
+//   M = 128 rows of x -- two 64-channel atoms that are either the two halves of a 128-channel slice of one tap
+//   (Cin >= 128) or the SAME 64 channels shifted by two different taps (Cin <= 64) -- and N = BN output channels.
+template <int BN, bool SWAP>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_constant__ CUtensorMap tm_dy_lo,
                   const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
@@ -462,10 +466,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_con
   const int lane = threadIdx.x & 31;
   const int co_t = blockIdx.x / p.cin_tiles;
   const int ci_t = blockIdx.x - co_t * p.cin_tiles;
-  const int co0 = co_t * 128, ci0 = ci_t * BN;
-  const int tap = blockIdx.y;
+  const int co0 = co_t * (SWAP ? BN : 128), ci0 = ci_t * (SWAP ? 128 : BN);
+  // taps of the two x atoms (SWAP) / of the CTA (plain); a missing second tap (9 is odd) re-reads the first
+  const int tap = (SWAP && p.tap_pairs) ? 2 * blockIdx.y : blockIdx.y;
+  const int tap1 = (SWAP && p.tap_pairs) ? min(tap + 1, p.taps - 1) : tap;
   const int dr = (p.taps == 9) ? (tap / 3 - 1) : 0;
   const int ds = (p.taps == 9) ? (tap % 3 - 1) : 0;
+  const int dr1 = (p.taps == 9) ? (tap1 / 3 - 1) : 0;
+  const int ds1 = (p.taps == 9) ? (tap1 % 3 - 1) : 0;
   const int pb_begin = blockIdx.z * p.blocks_per_split;
   const int pb_end = min(pb_begin + p.blocks_per_split, p.pix_blocks);
   const int k_iters = pb_end - pb_begin;
@@ -507,16 +515,30 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_con
           const int n0 = (pb / (p.tiles_w * p.tiles_h)) * p.TN;
           uint8_t* st = smem + s * Cfg::kStageBytes;
           mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          if constexpr (SWAP) {
+            // A = x atoms
+            const int cj = p.tap_pairs ? 0 : 64;      // channel step between the two atoms
+            tma_load_4d(st, &tm_x_hi, &full_bar[s], ci0, w0 + ds, h0 + dr, n0);
+            tma_load_4d(st + 8192, &tm_x_hi, &full_bar[s], ci0 + cj, w0 + ds1, h0 + dr1, n0);
+            tma_load_4d(st + Cfg::kABytes, &tm_x_lo, &full_bar[s], ci0, w0 + ds, h0 + dr, n0);
+            tma_load_4d(st + Cfg::kABytes + 8192, &tm_x_lo, &full_bar[s], ci0 + cj, w0 + ds1, h0 + dr1, n0);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            tma_load_4d(st + j * 8192, &tm_dy_hi, &full_bar[s], co0 + j * 64, w0, h0, n0);
-            tma_load_4d(st + Cfg::kABytes + j * 8192, &tm_dy_lo, &full_bar[s], co0 + j * 64, w0, h0, n0);
-          }
+            for (int j = 0; j < BN / 64; ++j) {         // B = dy atoms
+              tma_load_4d(st + 2 * Cfg::kABytes + j * 8192, &tm_dy_hi, &full_bar[s], co0 + j * 64, w0, h0, n0);
+              tma_load_4d(st + 2 * Cfg::kABytes + Cfg::kBBytes + j * 8192, &tm_dy_lo, &full_bar[s], co0 + j * 64, w0, h0, n0);
+            }
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) {
-            tma_load_4d(st + 2 * Cfg::kABytes + j * 8192, &tm_x_hi, &full_bar[s], ci0 + j * 64, w0 + ds, h0 + dr, n0);
-            tma_load_4d(st + 2 * Cfg::kABytes + Cfg::kBBytes + j * 8192, &tm_x_lo, &full_bar[s], ci0 + j * 64,
-                        w0 + ds, h0 + dr, n0);
+            for (int j = 0; j < 2; ++j) {
+              tma_load_4d(st + j * 8192, &tm_dy_hi, &full_bar[s], co0 + j * 64, w0, h0, n0);
+              tma_load_4d(st + Cfg::kABytes + j * 8192, &tm_dy_lo, &full_bar[s], co0 + j * 64, w0, h0, n0);
+            }
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) {
+              tma_load_4d(st + 2 * Cfg::kABytes + j * 8192, &tm_x_hi, &full_bar[s], ci0 + j * 64, w0 + ds, h0 + dr, n0);
+              tma_load_4d(st + 2 * Cfg::kABytes + Cfg::kBBytes + j * 8192, &tm_x_lo, &full_bar[s], ci0 + j * 64,
+                          w0 + ds, h0 + dr, n0);
+            }
           }
         }
       }
@@ -568,12 +590,31 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_con
         const uint32_t t_base = tmem_base + buf * (2 * BN) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
         for (int c = 0; c < BN; c += 32) {
-          if (ci0 + c < p.cin) add_pass_chunk<BN>(t_base + c, ps == 0, acc + c);
+          if ((SWAP ? co0 : ci0) + c < (SWAP ? p.cout : p.cin)) add_pass_chunk<BN>(t_base + c, ps == 0, acc + c);
         }
         tc_fence_before();
         mbar_arrive(&tempty_bar[buf]);
       }
-      if (co < p.cout) {
+      if constexpr (SWAP) {
+        // row m = q * 32 + lane of the accumulator: x atom m / 64 (second tap or second channel half), channel m % 64
+        const int m = q * 32 + lane;
+        const int my_tap = p.tap_pairs ? tap + (m >> 6) : tap;
+        const int ci = p.tap_pairs ? (m & 63) : ci0 + m;
+        if (my_tap < p.taps && ci < p.cin) {
+#pragma unroll
+          for (int c = 0; c < BN; c += 32) {
+            if (co0 + c >= p.cout) continue;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int cc = co0 + c + j;
+              if (cc < p.cout) {
+                float* o = p.dw + (static_cast<size_t>(cc) * p.taps + my_tap) * p.cin + ci;   // lanes: consecutive ci
+                if (p.atomic) atomicAdd(o, acc[c + j]); else *o = acc[c + j];
+              }
+            }
+          }
+        }
+      } else if (co < p.cout) {
 #pragma unroll
         for (int c = 0; c < BN; c += 32) {
           if (ci0 + c >= p.cin) continue;
@@ -751,17 +792,17 @@ int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream) {
   return launch_fwd<64, false>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
 }
 
-template <int BN>
+template <int BN, bool SWAP>
 static int launch_wgrad(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                         const CUtensorMap& b_lo, const ConvWgradParams& p, dim3 grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<BN>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<BN, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<BN>::kSmem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_wgrad): %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
     configured = true;
   }
-  conv_wgrad_kernel<BN><<<grid, kThreads, WgCfg<BN>::kSmem, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
-  return check_launch("conv_wgrad_kernel");
+  conv_wgrad_kernel<BN, SWAP><<<grid, kThreads, WgCfg<BN>::kSmem, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  return check_launch(SWAP ? "conv_wgrad_kernel<swap>" : "conv_wgrad_kernel");
 }
 
 int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t stream) {
@@ -774,10 +815,15 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t stream) {
   p.tiles_w = a.W / p.TW; p.tiles_h = a.H / p.TH;
   const int tiles_n = (a.N + p.TN - 1) / p.TN;
   p.pix_blocks = p.tiles_w * p.tiles_h * tiles_n;
-  const int BN = (a.cin > 64) ? 128 : 64;
-  p.cin_tiles = (a.cin + BN - 1) / BN;
-  const int co_tiles = (a.cout + 127) / 128;
-  const int base_ctas = co_tiles * p.cin_tiles * a.taps;
+  // Cout <= 64: exchange the operand roles (M = 128 rows of x, N = 64 output channels) so that the M = 128 tile is
+  // not half padding; with Cin <= 64 as well, the two x atoms are two taps of the same channels
+  const bool swap = a.cout <= 64;
+  p.tap_pairs = (swap && a.cin <= 64) ? 1 : 0;
+  const int BN = swap ? 64 : ((a.cin > 64) ? 128 : 64);
+  p.cin_tiles = swap ? (p.tap_pairs ? 1 : (a.cin + 127) / 128) : (a.cin + BN - 1) / BN;
+  const int co_tiles = swap ? 1 : (a.cout + 127) / 128;
+  const int tap_groups = p.tap_pairs ? (a.taps + 1) / 2 : a.taps;
+  const int base_ctas = co_tiles * p.cin_tiles * tap_groups;
   // split-K over pixel blocks until the grid covers ~2 waves of 148 SMs (>= 8 blocks per split)
   int splits = (2 * 148 + base_ctas - 1) / base_ctas;
   int max_splits = (p.pix_blocks + 7) / 8;
@@ -797,9 +843,10 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t stream) {
   if ((rc = make_act_map(&ta_lo, a.dy_lo, a.N, a.H, a.W, a.cout_pad, p.TW, p.TH, p.TN))) return rc;
   if ((rc = make_act_map(&tb_hi, a.x_hi, a.N, a.H, a.W, a.cin_pad, p.TW, p.TH, p.TN))) return rc;
   if ((rc = make_act_map(&tb_lo, a.x_lo, a.N, a.H, a.W, a.cin_pad, p.TW, p.TH, p.TN))) return rc;
-  dim3 grid(co_tiles * p.cin_tiles, a.taps, splits);
-  if (BN == 128) return launch_wgrad<128>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
-  return launch_wgrad<64>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
+  dim3 grid(co_tiles * p.cin_tiles, tap_groups, splits);
+  if (swap) return launch_wgrad<64, true>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
+  if (BN == 128) return launch_wgrad<128, false>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
+  return launch_wgrad<64, false>(ta_hi, ta_lo, tb_hi, tb_lo, p, grid, stream);
 }
 
 }  // namespace l2i

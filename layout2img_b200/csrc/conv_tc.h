@@ -43,7 +43,7 @@ struct ConvFwdArgs {            // host-side call
 
 struct ConvWgradParams {
   int N, H, W, cin, cout, taps;
-  int TW, TH, TN, tiles_w, tiles_h, pix_blocks, blocks_per_split, cin_tiles, atomic;
+  int TW, TH, TN, tiles_w, tiles_h, pix_blocks, blocks_per_split, cin_tiles, atomic, tap_pairs;
   float* dw;                    // [cout][taps][cin] fp32
 };
 
