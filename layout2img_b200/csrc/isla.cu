@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(256) isla_fwd_kernel(const IslaFwdParams p) {
     s_bet[o * kIslaCc + c] = __ldg(p.beta + (static_cast<size_t>(b) * p.O + o) * p.C + c0 + c);
   }
   __syncthreads();
-  const int groups = (cc + 7) >> 3;        // 8-channel groups in this chunk
+  // 8-channel groups in this chunk; a pair's padding channels (up to cpad) are written as zeros
+  const int ccp = p.hi ? min(kIslaCc, p.cpad - c0) : cc;
+  const int groups = (max(cc, ccp) + 7) >> 3;
   const int hw = p.H * p.W;
   const int Ho = p.H << p.up, Wo = p.W << p.up;
   const long long items = 1LL * hw * groups;
