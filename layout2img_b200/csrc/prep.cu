@@ -10,35 +10,54 @@
 
 namespace l2i {
 
-__global__ void weight_prep_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int cout, int cin,
-                                   int taps, __nv_bfloat16* __restrict__ f_hi, __nv_bfloat16* __restrict__ f_lo,
-                                   int cin_pad, __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo,
-                                   int cout_pad) {
+// Tile = 32 output channels x 32 input channels x all taps, staged in shared memory: the torch-layout rows
+// are read coalesced (32 * taps contiguous floats per output channel) and both operand layouts are written
+// in 64-byte runs (32 consecutive bf16 along Cin for the forward operand, along Cout for the dgrad operand).
+static constexpr int kWpTile = 32;
+__global__ void __launch_bounds__(256)
+weight_prep_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int cout, int cin, int taps,
+                   __nv_bfloat16* __restrict__ f_hi, __nv_bfloat16* __restrict__ f_lo, int cin_pad,
+                   __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo, int cout_pad) {
+  extern __shared__ float tile[];                         // [32][32 * taps + 1]
+  const int pitch = kWpTile * taps + 1;
+  const int ci0 = blockIdx.x * kWpTile, co0 = blockIdx.y * kWpTile;
   const float inv = sigma ? 1.0f / __ldg(sigma) : 1.0f;
-  const long long n_f = 1LL * cout * taps * cin_pad;
-  const long long n_d = d_hi ? 1LL * cin * taps * cout_pad : 0;
-  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n_f + n_d; i += 1LL * gridDim.x * blockDim.x) {
-    if (i < n_f) {
-      const int ci = static_cast<int>(i % cin_pad);
-      const int tap = static_cast<int>((i / cin_pad) % taps);
-      const int co = static_cast<int>(i / (1LL * cin_pad * taps));
-      float v = 0.f;
-      if (ci < cin) v = __ldg(w + (1LL * co * cin + ci) * taps + tap) * inv;
-      __nv_bfloat16 h, l;
-      split_bf16(v, h, l);
-      f_hi[i] = h;
-      f_lo[i] = l;
-    } else {
-      const long long j = i - n_f;
-      const int co = static_cast<int>(j % cout_pad);
-      const int tap = static_cast<int>((j / cout_pad) % taps);
-      const int ci = static_cast<int>(j / (1LL * cout_pad * taps));
-      float v = 0.f;
-      if (co < cout) v = __ldg(w + (1LL * co * cin + ci) * taps + (taps - 1 - tap)) * inv;
-      __nv_bfloat16 h, l;
-      split_bf16(v, h, l);
-      d_hi[j] = h;
-      d_lo[j] = l;
+  const int nci = max(0, min(kWpTile, cin - ci0));        // valid input channels in this tile
+  for (int i = threadIdx.x; i < kWpTile * kWpTile * taps; i += blockDim.x) {
+    const int co_l = i / (kWpTile * taps), rem = i - co_l * (kWpTile * taps);
+    float v = 0.f;
+    if (co0 + co_l < cout && rem < nci * taps) v = __ldg(w + (static_cast<size_t>(co0 + co_l) * cin + ci0) * taps + rem) * inv;
+    tile[co_l * pitch + rem] = v;                         // rem = ci_l * taps + tap
+  }
+  __syncthreads();
+  // forward operand [cout][tap][cin_pad]: pairs of consecutive input channels per thread
+  for (int i = threadIdx.x; i < kWpTile * taps * (kWpTile / 2); i += blockDim.x) {
+    const int cp = i % (kWpTile / 2);
+    const int tap = (i / (kWpTile / 2)) % taps;
+    const int co_l = i / ((kWpTile / 2) * taps);
+    const int co = co0 + co_l, ci = ci0 + 2 * cp;
+    if (co >= cout || ci >= cin_pad) continue;
+    __nv_bfloat16 ah, al, bh, bl;
+    split_bf16(tile[co_l * pitch + (2 * cp) * taps + tap], ah, al);
+    split_bf16(tile[co_l * pitch + (2 * cp + 1) * taps + tap], bh, bl);
+    const size_t o = (static_cast<size_t>(co) * taps + tap) * cin_pad + ci;
+    *reinterpret_cast<uint32_t*>(f_hi + o) = pack_bf16x2(ah, bh);
+    *reinterpret_cast<uint32_t*>(f_lo + o) = pack_bf16x2(al, bl);
+  }
+  if (d_hi) {
+    // data-gradient operand [cin][taps-1-tap][cout_pad]: pairs of consecutive output channels per thread
+    for (int i = threadIdx.x; i < kWpTile * taps * (kWpTile / 2); i += blockDim.x) {
+      const int cp = i % (kWpTile / 2);
+      const int tap = (i / (kWpTile / 2)) % taps;
+      const int ci_l = i / ((kWpTile / 2) * taps);
+      const int ci = ci0 + ci_l, co = co0 + 2 * cp;
+      if (ci >= cin || co >= cout_pad) continue;
+      __nv_bfloat16 ah, al, bh, bl;
+      split_bf16(tile[(2 * cp) * pitch + ci_l * taps + tap], ah, al);
+      split_bf16(tile[(2 * cp + 1) * pitch + ci_l * taps + tap], bh, bl);
+      const size_t o = (static_cast<size_t>(ci) * taps + (taps - 1 - tap)) * cout_pad + co;
+      *reinterpret_cast<uint32_t*>(d_hi + o) = pack_bf16x2(ah, bh);
+      *reinterpret_cast<uint32_t*>(d_lo + o) = pack_bf16x2(al, bl);
     }
   }
 }
@@ -50,11 +69,11 @@ int weight_prep(const float* w, const float* sigma, int cout, int cin, int taps,
     return L2I_ERR_BAD_ARG;
   }
   if (d_hi && (!d_lo || cout_pad < cout || cout_pad % 8)) { set_error("weight_prep: bad dgrad arguments"); return L2I_ERR_BAD_ARG; }
-  const long long total = 1LL * cout * taps * cin_pad + (d_hi ? 1LL * cin * taps * cout_pad : 0);
-  const int threads = 256;
-  long long blocks = (total + threads - 1) / threads;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  weight_prep_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(
+  // tiles cover the padded extents so that the padding channels of both operands are written (as zeros)
+  const int gx = (cin_pad + kWpTile - 1) / kWpTile;
+  const int gy = ((d_hi ? cout_pad : cout) + kWpTile - 1) / kWpTile;
+  const size_t smem = sizeof(float) * kWpTile * (kWpTile * taps + 1);
+  weight_prep_kernel<<<dim3(gx, gy), 256, smem, stream>>>(
       w, sigma, cout, cin, taps, reinterpret_cast<__nv_bfloat16*>(f_hi), reinterpret_cast<__nv_bfloat16*>(f_lo), cin_pad,
       reinterpret_cast<__nv_bfloat16*>(d_hi), reinterpret_cast<__nv_bfloat16*>(d_lo), cout_pad);
   return check_launch("weight_prep_kernel");

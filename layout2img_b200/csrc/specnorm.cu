@@ -137,39 +137,41 @@ int sn_sigma(const float* W, int R, int Cc, float* u, float* v, int training, fl
   return check_launch("sn_finish_kernel");
 }
 
-// d += sum G[r][tap][ci] * W[r][ci][tap]
+// d += sum G[r][tap][ci] * W[r][ci][tap].  One block per output channel r: both rows are contiguous
+// (taps * cin floats), G is read coalesced and the tap-strided reads of W stay inside the row's L1 lines.
 __global__ void __launch_bounds__(256) sn_bwd_dot_kernel(const float* __restrict__ G, const float* __restrict__ W, int R, int cin,
                                                          int taps, float* __restrict__ d) {
   __shared__ float red[32];
-  const long long total = 1LL * R * cin * taps;
+  const int n = cin * taps;
   float acc = 0.f;
-  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
-    // i indexes G: (r, tap, ci)
-    const int ci = static_cast<int>(i % cin);
-    const int tap = static_cast<int>((i / cin) % taps);
-    const long long r = i / (1LL * cin * taps);
-    acc = fmaf(__ldg(G + i), __ldg(W + (r * cin + ci) * taps + tap), acc);
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    const float* g = G + static_cast<size_t>(r) * n;
+    const float* w = W + static_cast<size_t>(r) * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {     // i indexes G: (tap, ci)
+      const int tap = i / cin, ci = i - tap * cin;
+      acc = fmaf(__ldg(g + i), __ldg(w + ci * taps + tap), acc);
+    }
   }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) atomicAdd(d, acc);
 }
 
-// dW[r][ci][tap] = (G[r][tap][ci] - d / sigma * u[r] * v[ci * taps + tap]) / sigma
+// dW[r][ci][tap] = (G[r][tap][ci] - d / sigma * u[r] * v[ci * taps + tap]) / sigma   (block per r, coalesced writes)
 __global__ void __launch_bounds__(256) sn_bwd_apply_kernel(const float* __restrict__ G, const float* __restrict__ u,
                                                            const float* __restrict__ v, const float* __restrict__ sigma,
                                                            const float* __restrict__ d, int R, int cin, int taps,
                                                            float* __restrict__ dW) {
-  const float sg = __ldg(sigma);
-  const float inv = 1.0f / sg;
+  const float inv = 1.0f / __ldg(sigma);
   const float coef = __ldg(d) * inv;
-  const long long total = 1LL * R * cin * taps;
-  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
-    // i indexes dW (torch layout): (r, ci, tap)
-    const int tap = static_cast<int>(i % taps);
-    const int ci = static_cast<int>((i / taps) % cin);
-    const long long r = i / (1LL * cin * taps);
-    const float g = __ldg(G + (r * taps + tap) * cin + ci);
-    dW[i] = (g - coef * __ldg(u + r) * __ldg(v + ci * taps + tap)) * inv;
+  const int n = cin * taps;
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    const float* g = G + static_cast<size_t>(r) * n;
+    float* o = dW + static_cast<size_t>(r) * n;
+    const float cu = coef * __ldg(u + r);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {     // i indexes dW: (ci, tap)
+      const int ci = i / taps, tap = i - ci * taps;
+      o[i] = (__ldg(g + tap * cin + ci) - cu * __ldg(v + i)) * inv;
+    }
   }
 }
 
@@ -181,16 +183,11 @@ int sn_weight_grad(const float* G, const float* W, const float* u, const float* 
   }
   cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float), stream);
   if (e != cudaSuccess) { set_error("sn_weight_grad: memset: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
-  const long long total = 1LL * R * cin * taps;
-  long long blocks = (total + 256 * 8 - 1) / (256 * 8);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks < 1) blocks = 1;
-  sn_bwd_dot_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(G, W, R, cin, taps, scratch);
+  const int blocks = R < 148 * 8 ? R : 148 * 8;
+  sn_bwd_dot_kernel<<<blocks, 256, 0, stream>>>(G, W, R, cin, taps, scratch);
   int rc = check_launch("sn_bwd_dot_kernel");
   if (rc) return rc;
-  blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  sn_bwd_apply_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(G, u, v, sigma, scratch, R, cin, taps, dW);
+  sn_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(G, u, v, sigma, scratch, R, cin, taps, dW);
   return check_launch("sn_bwd_apply_kernel");
 }
 
