@@ -311,21 +311,39 @@ def run_ours(args, rank, local_rank, world):
         pk = peaks()
         conv = agg.get("l2i_conv2d_fwd", {"calls": 0, "ms": 0.0, "flops": 0.0})
         wg = agg.get("l2i_conv2d_wgrad", {"calls": 0, "ms": 0.0, "flops": 0.0})
-        ach = conv["flops"] / (conv["ms"] / 1e3) / 1e12 if conv["ms"] else None
         peak = pk["bf16_sustained"]
+        tf = lambda d: d["flops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] else None
+        # the dominant launch: the largest single contributor to the step's device time (D.block_obj5.conv2
+        # forward, 3 launches per step), the one profiles/r01_conv_fwd_big_ncu.json captures with ncu --set full
+        prof = {}
+        ppath = os.path.join(ROOT, "profiles", "r01_conv_fwd_big_ncu.json")
+        if os.path.exists(ppath):
+            prof = json.load(open(ppath))
+        dom = conv_shapes.get(prof.get("shape", ""), None)
+        if dom is None:       # other batch sizes: fall back to the most expensive forward shape of this run
+            key = max((k for k in conv_shapes if k.startswith("fwd")), key=lambda k: conv_shapes[k]["ms"], default=None)
+            dom, prof = (conv_shapes[key], {"shape": key}) if key else ({"calls": 0, "ms": 0.0, "flops": 0.0}, {})
+        ach = tf(dom)
+        traffic = (prof["dram_bytes_read"] + prof["dram_bytes_write"]) if "dram_bytes_read" in prof else None
         roofline = {
-            "bound": "tensor", "kernel": "conv_fwd_kernel (tcgen05 implicit GEMM; forward + data-gradient launches)",
+            "bound": "tensor",
+            "kernel": "conv_fwd_kernel<128> (tcgen05 implicit-GEMM conv, persistent, TMA-fed), launch shape: " + str(prof.get("shape")),
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
             "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
-            "note": "achieved counts ALGORITHMIC fp32 conv FLOPs (2*M*N*K, K incl. channel padding); the kernel executes "
-                    "3 bf16 tcgen05.mma passes per algorithmic MAC (hi*hi + lo*hi + hi*lo) to reach fp32-class accuracy, "
-                    "so executed tensor FLOP/s = 3x achieved",
+            "note": "achieved = ALGORITHMIC fp32 conv FLOPs (2*M*N*K per launch) / CUDA-event duration of that launch, "
+                    "averaged over its launches in one step; the kernel executes 3 bf16 tcgen05.mma per algorithmic MAC "
+                    "(hi*hi + lo*hi + hi*lo, fp32-class accuracy), so frac tops out at 1/3 and executed_frac = 3*frac is "
+                    "the tensor pipe's rate against the measured cuBLAS bf16 rate",
             "executed_frac": (3 * ach / peak) if ach else None,
-            "launches_per_step": conv["calls"], "ms_per_step": conv["ms"],
-            "share_of_step": conv["ms"] / step_ms if step_ms else None,
-            "wgrad": {"achieved": wg["flops"] / (wg["ms"] / 1e3) / 1e12 if wg["ms"] else None,
-                      "launches_per_step": wg["calls"], "ms_per_step": wg["ms"]},
-            "traffic": None,
+            "launches_per_step": dom["calls"], "us_per_launch": 1e3 * dom["ms"] / dom["calls"] if dom["calls"] else None,
+            "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
+            "algorithmic_bytes": sum(prof["algorithmic_bytes"].values()) if "algorithmic_bytes" in prof else None,
+            "tensor_pipe_active_pct_ncu": prof.get("sm__pipe_tensor_cycles_active_pct"),
+            "all_conv_fwd_dgrad_launches": {"achieved": tf(conv), "frac": tf(conv) / peak if conv["ms"] else None,
+                                            "launches_per_step": conv["calls"], "ms_per_step": conv["ms"],
+                                            "share_of_step": conv["ms"] / step_ms if step_ms else None},
+            "all_conv_wgrad_launches": {"achieved": tf(wg), "frac": tf(wg) / peak if wg["ms"] else None,
+                                        "launches_per_step": wg["calls"], "ms_per_step": wg["ms"]},
         }
         breakdown = {k: {"calls": v["calls"], "ms": round(v["ms"], 3)} for k, v in
                      sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}

@@ -14,8 +14,9 @@ namespace l2i {
 // are read coalesced (32 * taps contiguous floats per output channel) and both operand layouts are written
 // in 64-byte runs (32 consecutive bf16 along Cin for the forward operand, along Cout for the dgrad operand).
 static constexpr int kWpTile = 32;
+template <int taps>
 __global__ void __launch_bounds__(256)
-weight_prep_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int cout, int cin, int taps,
+weight_prep_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int cout, int cin,
                    __nv_bfloat16* __restrict__ f_hi, __nv_bfloat16* __restrict__ f_lo, int cin_pad,
                    __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo, int cout_pad) {
   extern __shared__ float tile[];                         // [32][32 * taps + 1]
@@ -73,9 +74,14 @@ int weight_prep(const float* w, const float* sigma, int cout, int cin, int taps,
   const int gx = (cin_pad + kWpTile - 1) / kWpTile;
   const int gy = ((d_hi ? cout_pad : cout) + kWpTile - 1) / kWpTile;
   const size_t smem = sizeof(float) * kWpTile * (kWpTile * taps + 1);
-  weight_prep_kernel<<<dim3(gx, gy), 256, smem, stream>>>(
-      w, sigma, cout, cin, taps, reinterpret_cast<__nv_bfloat16*>(f_hi), reinterpret_cast<__nv_bfloat16*>(f_lo), cin_pad,
-      reinterpret_cast<__nv_bfloat16*>(d_hi), reinterpret_cast<__nv_bfloat16*>(d_lo), cout_pad);
+  if (taps == 9)
+    weight_prep_kernel<9><<<dim3(gx, gy), 256, smem, stream>>>(
+        w, sigma, cout, cin, reinterpret_cast<__nv_bfloat16*>(f_hi), reinterpret_cast<__nv_bfloat16*>(f_lo), cin_pad,
+        reinterpret_cast<__nv_bfloat16*>(d_hi), reinterpret_cast<__nv_bfloat16*>(d_lo), cout_pad);
+  else
+    weight_prep_kernel<1><<<dim3(gx, gy), 256, smem, stream>>>(
+        w, sigma, cout, cin, reinterpret_cast<__nv_bfloat16*>(f_hi), reinterpret_cast<__nv_bfloat16*>(f_lo), cin_pad,
+        reinterpret_cast<__nv_bfloat16*>(d_hi), reinterpret_cast<__nv_bfloat16*>(d_lo), cout_pad);
   return check_launch("weight_prep_kernel");
 }
 
