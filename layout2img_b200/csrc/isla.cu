@@ -269,7 +269,7 @@ int isla_fwd(const float* x, const float* mean_invstd, const float* mask, const 
   const int chunks = (C + kIslaCc - 1) / kIslaCc;
   const long long items = 1LL * H * W * ((min(C, kIslaCc) + 7) / 8);
   long long bx = (items + 255) / 256;
-  const long long cap = (148LL * 8 + 1LL * B * chunks - 1) / (1LL * B * chunks);
+  const long long cap = (148LL * 32 + 1LL * B * chunks - 1) / (1LL * B * chunks);   // ~32 CTAs per SM in flight over the launch
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   const size_t smem = sizeof(float) * 2 * O * kIslaCc;
