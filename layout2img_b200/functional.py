@@ -26,44 +26,52 @@ def _sum2x2(t):
 
 class ConvFn(torch.autograd.Function):
     """y = conv(up2?(relu?(x)), W) + bias + residual   (3x3 pad 1 or 1x1, stride 1).
-    reference: conv2d() helpers, resnet_generator_app_v2.py:681-686, rcnn_discriminator_app.py:10-15."""
+    reference: conv2d() helpers, resnet_generator_app_v2.py:681-686, rcnn_discriminator_app.py:10-15.
+    sn = None (weight is the weight itself) or (u, v, eps, training): weight is weight_orig and the spectral
+    normalisation runs in csrc/specnorm.cu."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, relu_in, up2_in, res_up2):
+    def forward(ctx, x, weight, bias, residual, relu_in, up2_in, res_up2, sn):
         x = _c(x)
         cout, cin, kh, kw = weight.shape
         taps = kh * kw
         xp = ops.act_split(x, relu=relu_in, up2=up2_in)
-        wp = ops.conv_weight_prep(_c(weight), need_dgrad=ctx.needs_input_grad[0])
+        st = ops.sn_sigma(_c(weight), sn[0], sn[1], training=sn[3], eps=sn[2]) if sn else None
+        wp = ops.conv_weight_prep(_c(weight), st.sigma if st else None, need_dgrad=ctx.needs_input_grad[0])
         out, _ = ops.conv2d_fwd(xp, wp.f_hi, wp.f_lo, cout, taps, bias=_c(bias), residual=_c(residual), res_up2=res_up2)
-        ctx.save_for_backward(x if relu_in else None, xp.hi, xp.lo, wp.d_hi, wp.d_lo)
+        ctx.save_for_backward(xp.hi, xp.lo, wp.d_hi, wp.d_lo, weight, *(st or (None, None, None)))
         ctx.meta = (cout, cin, taps, relu_in, up2_in, res_up2, bias is not None, residual is not None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, xhi, xlo, dhi, dlo = ctx.saved_tensors
+        xhi, xlo, dhi, dlo, weight, sg, u, v = ctx.saved_tensors
         cout, cin, taps, relu_in, up2_in, res_up2, has_bias, has_res = ctx.meta
         dout = _c(dout)
-        dyp = ops.act_split(dout)
+        # one read of dout: operand pair + per-channel sums (bias gradient)
+        dyp, _, colsum = ops.grad_split(dout, want_lo=True, up=False)
         dx = dw = db = dres = None
         if ctx.needs_input_grad[0]:
-            dx, _ = ops.conv2d_fwd(dyp, dhi, dlo, cin, taps)
-            if up2_in:
-                dx = _sum2x2(dx)
-            if relu_in:
-                dx = dx * (x > 0)
+            # ReLU derivative from the saved (ReLU'd) input pair, 2x2 sum = backward of the nearest x2, both in the epilogue
+            dx, _ = ops.conv2d_fwd(dyp, dhi, dlo, cin, taps, mask_hi=xhi if relu_in else None, pool=2 if up2_in else 0)
         if ctx.needs_input_grad[1]:
-            dw = _dw_to_torch(ops.conv2d_wgrad(dyp, ops.Pair(xhi, xlo, cin), taps), cout, cin, taps)
+            g = ops.conv2d_wgrad(dyp, ops.Pair(xhi, xlo, cin), taps)
+            dw = ops.sn_weight_grad(g, weight, ops.SNState(sg, u, v)) if sg is not None else _dw_to_torch(g, cout, cin, taps)
         if has_bias and ctx.needs_input_grad[2]:
-            db = dout.sum(dim=(0, 1, 2))
+            db = colsum
         if has_res and ctx.needs_input_grad[3]:
             dres = _sum2x2(dout) if res_up2 else dout
-        return dx, dw, db, dres, None, None, None
+        return dx, dw, db, dres, None, None, None, None
 
 
-def conv2d(x, weight, bias=None, residual=None, relu_in=False, up2_in=False, res_up2=False):
-    return ConvFn.apply(x, weight, bias, residual, relu_in, up2_in, res_up2)
+def conv2d(x, weight, bias=None, residual=None, relu_in=False, up2_in=False, res_up2=False, sn=None):
+    return ConvFn.apply(x, weight, bias, residual, relu_in, up2_in, res_up2, sn)
+
+
+def conv2d_module(conv, x, residual=None, relu_in=False, up2_in=False, res_up2=False):
+    """Convolution through a (possibly spectrally normalised) conv module without firing its library hook."""
+    w, b, sn = _sn_of(conv)
+    return ConvFn.apply(x, w, b, residual, relu_in, up2_in, res_up2, sn)
 
 
 class DBlockFn(torch.autograd.Function):
@@ -162,6 +170,47 @@ def _sn_of(conv):
                 raise ValueError("layout2img_b200 implements spectral_norm(n_power_iterations=1, dim=0)")
             return conv.weight_orig, conv.bias, (conv.weight_u, conv.weight_v, hook.eps, conv.training)
     return conv.weight, conv.bias, None
+
+
+class SNLinearFn(torch.autograd.Function):
+    """y = x @ (W_orig / sigma)^T + b for a spectrally normalised nn.Linear (the ISLA gamma/beta projections
+    norm_module.py:158-159, mask_regression.py:64, the generator's fc :409, the discriminator heads).  The power
+    iteration, sigma and the weight_orig gradient are csrc/specnorm.cu (3 + 2 launches instead of the ~15 of the
+    library hook); the two GEMMs are plain library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, w_orig, bias, u, v, eps, training):
+        st = ops.sn_sigma(_c(w_orig), u, v, training, eps)
+        x2 = x.reshape(-1, x.shape[-1])
+        y = (x2 @ w_orig.t()) / st.sigma
+        if bias is not None:
+            y = y + bias
+        ctx.save_for_backward(x2, w_orig, st.sigma, st.u, st.v)
+        ctx.xshape = x.shape
+        ctx.has_bias = bias is not None
+        return y.view(*x.shape[:-1], w_orig.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w_orig, sigma, u, v = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ((dy2 @ w_orig) / sigma).view(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            g = (dy2.t() @ x2).contiguous()                       # dL/d(W/sigma), (R, Cc)
+            dw = ops.sn_weight_grad(g.view(g.shape[0], 1, g.shape[1]), _c(w_orig), ops.SNState(sigma, u, v))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.sum(dim=0)
+        return dx, dw, db, None, None, None, None
+
+
+def sn_linear(module, x):
+    """Apply a (spectrally normalised) nn.Linear through SNLinearFn; plain nn.Linear modules are called as is."""
+    w, b, sn = _sn_of(module)
+    if sn is None:
+        return module(x)
+    return SNLinearFn.apply(x, w, b, sn[0], sn[1], sn[2], sn[3])
 
 
 def d_block(x, conv1, conv2, c_sc=None, down=False, optimized=False):
@@ -289,7 +338,7 @@ class NormConvFn(torch.autograd.Function):
         x, mi, mask_pm, gamma, beta, aff_w, aff_b, ahi, alo, dhi, dlo = ctx.saved_tensors
         cout, cin, taps, training, up2, res_up2, has_bias, has_res = ctx.meta
         dout = _c(dout)
-        dyp = ops.act_split(dout)
+        dyp, _, colsum = ops.grad_split(dout, want_lo=True, up=False)
         da, _ = ops.conv2d_fwd(dyp, dhi, dlo, cin, taps)
         dw = _dw_to_torch(ops.conv2d_wgrad(dyp, ops.Pair(ahi, alo, cin), taps), cout, cin, taps)
         dx, dmask, dgamma, dbeta, csum = ops.isla_bwd(x, mi, mask_pm, gamma, beta, _c(aff_w), _c(aff_b), da,
@@ -298,7 +347,7 @@ class NormConvFn(torch.autograd.Function):
         if aff_w is not None:
             daw = csum[:, 1].float()
             dab = csum[:, 0].float()
-        db = dout.sum(dim=(0, 1, 2)) if has_bias else None
+        db = colsum if has_bias else None
         dres = None
         if has_res:
             dres = _sum2x2(dout) if res_up2 else dout

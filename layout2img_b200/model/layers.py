@@ -40,7 +40,7 @@ class Conv2d(nn.Conv2d):
         if self.stride != (1, 1) or self.kernel_size not in ((3, 3), (1, 1)) or self.dilation != (1, 1) or self.groups != 1:
             raise ValueError("layout2img_b200 Conv2d supports 3x3/pad 1 and 1x1/pad 0, stride 1 only")
         if norm is None:
-            return L.conv2d(x, self.weight, self.bias, residual, relu_in, up2_in, res_up2)
+            return L.conv2d(x, self.weight, self.bias, residual, relu_in, up2_in, res_up2)   # plain (non-SN) use
         bn, mask_pm, gamma, beta = norm
         return L.norm_conv(x, self.weight, self.bias, bn.running_mean, bn.running_var, bn.training,
                            mask_pm=mask_pm, gamma=gamma, beta=beta, aff_w=bn.weight if bn.affine else None,

@@ -80,7 +80,7 @@ class ResnetDiscriminator128_app(nn.Module):
         x = self.block5(x)
         x = self.block6(x)
         x = F.relu(x).sum(dim=(1, 2))
-        out_im = self.l7(x)
+        out_im = L.sn_linear(self.l7, x)
 
         # small / large object paths (:131-146); order = all large then all small
         s_idx = ((bbox[:, 3] - bbox[:, 1]) < 64) * ((bbox[:, 4] - bbox[:, 2]) < 64)
@@ -111,7 +111,7 @@ class ResnetDiscriminator128_app(nn.Module):
         # object head (:160-166)
         obj_feat = self.block_obj5(obj_feat)
         obj_feat = F.relu(obj_feat).sum(dim=(1, 2))                     # (K,1024)
-        out_obj = self.l_obj(obj_feat)
+        out_obj = L.sn_linear(self.l_obj, obj_feat)
         out_obj = out_obj + torch.sum(self.l_y(y) * obj_feat, dim=1, keepdim=True)
         return out_im, out_obj, out_app
 

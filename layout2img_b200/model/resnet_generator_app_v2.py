@@ -135,8 +135,8 @@ class ResBlock(nn.Module):
         # gamma / beta = spectrally normalised linear projections of the object latents
         m1 = L.mask_resize(bbox, h, wd, True)
         m2 = L.mask_resize(bbox, 2 * h, 2 * wd, True)
-        g1, be1 = self.b1.weight_proj(w).view(b, o, -1), self.b1.bias_proj(w).view(b, o, -1)
-        g2, be2 = self.b2.weight_proj(w).view(b, o, -1), self.b2.bias_proj(w).view(b, o, -1)
+        g1, be1 = L.sn_linear(self.b1.weight_proj, w).view(b, o, -1), L.sn_linear(self.b1.bias_proj, w).view(b, o, -1)
+        g2, be2 = L.sn_linear(self.b2.weight_proj, w).view(b, o, -1), L.sn_linear(self.b2.bias_proj, w).view(b, o, -1)
         out_feat = L.g_block(in_feat, m1, g1, be1, m2, g2, be2, self.conv1, self.conv2, self.c_sc,
                              self.b1.batch_norm2d, self.b2.batch_norm2d)
         if not self.predict_mask:
@@ -204,7 +204,7 @@ class _GeneratorBase(nn.Module):
         if z_im is None:
             z_im = torch.randn((b, 128), device=dev)
         hard = bbox_mask(z, bbox, 64, 64)
-        x = to_nhwc(self.fc(z_im).view(b, -1, 4, 4))
+        x = to_nhwc(L.sn_linear(self.fc, z_im).view(b, -1, 4, 4))
         x, stage_mask = self.res1(x, w, bmask)
         stage_bbox = L.stage_mix(stage_mask, self.alpha1, bmask, y, hard)
         x, stage_mask = self.res2(x, w, stage_bbox)
