@@ -123,6 +123,15 @@ int l2i_stage_mix_bwd(const float* stage, const int64_t* y, const float* alpha, 
                       const float* dout, int B, int O, int h, int w, int NC, int S, float* dstage, float* dalpha,
                       float* dsoft, void* stream);
 
+/* ---- mask-regression trunk (reference model/mask_regression.py:66-99): InstanceNorm2d (affine=False, eps) -> ReLU
+ *      -> optional bilinear x2 (align_corners=False) of x [N,H,W,C], written as the next convolution's operand
+ *      pair [N,H<<up2,W<<up2,cpad]; stats [N,C,2] = (mean, 1/sqrt(var+eps)) is kept for the backward. ---------- */
+int l2i_inorm_relu_fwd(const float* x, int N, int H, int W, int C, int up2, float eps, float* stats, void* hi, void* lo,
+                       int cpad, void* stream);
+/* dx [N,H,W,C] from da [N,H<<up2,W<<up2,C], the gradient w.r.t. the (up-sampled) output of l2i_inorm_relu_fwd. */
+int l2i_inorm_relu_bwd(const float* x, const float* stats, const float* da, int N, int H, int W, int C, int up2, float* dx,
+                       void* stream);
+
 /* ---- ROIAlign (the operator of the reference's setup.py:46-54 extension `model.roi_layers._C`;
  *      call sites model/rcnn_discriminator_app.py:98-99,139,143; torchvision semantics, aligned=False,
  *      sampling_ratio=0).  feat [N,H,W,C]; rois [K,5] = (image, x0, y0, x1, y1) px; out [K,P,P,C]. */

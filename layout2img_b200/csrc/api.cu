@@ -129,6 +129,14 @@ int l2i_stage_mix_bwd(const float* stage, const int64_t* y, const float* alpha, 
   return stage_mix_bwd(stage, reinterpret_cast<const long long*>(y), alpha, bmask, hard, dout, B, O, h, w, NC, S, dstage,
                        dalpha, dsoft, ST(stream));
 }
+int l2i_inorm_relu_fwd(const float* x, int N, int H, int W, int C, int up2, float eps, float* stats, void* hi, void* lo,
+                       int cpad, void* stream) {
+  return inorm_relu_fwd(x, N, H, W, C, up2, eps, stats, hi, lo, cpad, ST(stream));
+}
+int l2i_inorm_relu_bwd(const float* x, const float* stats, const float* da, int N, int H, int W, int C, int up2, float* dx,
+                       void* stream) {
+  return inorm_relu_bwd(x, stats, da, N, H, W, C, up2, dx, ST(stream));
+}
 int l2i_roi_align_fwd(const float* feat, const float* rois, int K, int N, int H, int W, int C, int P, float scale,
                       float* out, void* stream) {
   return roi_align_fwd(feat, rois, K, N, H, W, C, P, scale, out, ST(stream));

@@ -47,6 +47,10 @@ int stage_mix_fwd(const float* stage, const long long* y, const float* alpha, co
 int stage_mix_bwd(const float* stage, const long long* y, const float* alpha, const float* bmask, const float* hard,
                   const float* dout, int B, int O, int h, int w, int NC, int S, float* dstage, float* dalpha,
                   float* dsoft, cudaStream_t stream);
+int inorm_relu_fwd(const float* x, int N, int H, int W, int C, int up2, float eps, float* stats, void* hi, void* lo,
+                   int cpad, cudaStream_t stream);
+int inorm_relu_bwd(const float* x, const float* stats, const float* da, int N, int H, int W, int C, int up2, float* dx,
+                   cudaStream_t stream);
 // roi_align.cu
 int roi_align_fwd(const float* feat, const float* rois, int K, int N, int H, int W, int C, int P, float scale, float* out,
                   cudaStream_t stream);

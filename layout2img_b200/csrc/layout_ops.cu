@@ -330,3 +330,162 @@ int stage_mix_bwd(const float* stage, const long long* y, const float* alpha, co
 }
 
 }  // namespace l2i
+
+// ------------------------------------------------------------------------------------------------
+// Mask-regression trunk (reference model/mask_regression.py:66-99): after each 3x3 conv comes
+// InstanceNorm2d(256) (affine=False, biased variance, eps 1e-5) -> ReLU -> [bilinear x2, align_corners=False].
+// inorm_relu_fwd writes the NEXT convolution's bf16 operand pair directly; inorm_relu_bwd takes the gradient
+// w.r.t. that (up-sampled) tensor back to the conv output.  One block per sample, one thread per channel
+// (coalesced over channels), so the per-(sample, channel) statistics never leave the thread.
+// ------------------------------------------------------------------------------------------------
+namespace l2i {
+
+// torch upsample_bilinear2d, align_corners=False, scale 2: src = max((dst + 0.5) / 2 - 0.5, 0)
+__device__ __forceinline__ void up2_taps(int dst, int in, int& i0, int& i1, float& l1) {
+  const float src = fmaxf((static_cast<float>(dst) + 0.5f) * 0.5f - 0.5f, 0.f);
+  i0 = static_cast<int>(src);
+  i1 = min(i0 + 1, in - 1);
+  l1 = src - static_cast<float>(i0);
+}
+
+__global__ void __launch_bounds__(256) inorm_stats_kernel(const float* __restrict__ x, int HW, int C, float eps,
+                                                          float* __restrict__ stats) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* p = x + static_cast<size_t>(n) * HW * C + c;
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < HW; ++i) s += __ldg(p + static_cast<size_t>(i) * C);
+    const float mean = s / HW;
+    for (int i = 0; i < HW; ++i) { const float d = __ldg(p + static_cast<size_t>(i) * C) - mean; q = fmaf(d, d, q); }   // two-pass variance
+    const float var = q / HW;
+    stats[(static_cast<size_t>(n) * C + c) * 2] = mean;
+    stats[(static_cast<size_t>(n) * C + c) * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
+// thread = (sample, output pixel, 8-channel group)
+__global__ void __launch_bounds__(256) inorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                                          int N, int H, int W, int C, int up,
+                                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int cpad) {
+  const int Ho = H << up, Wo = W << up;
+  const int groups = cpad >> 3;
+  const long long total = 1LL * N * Ho * Wo * groups;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    const long long opix = i / groups;
+    const int wo = static_cast<int>(opix % Wo);
+    const int ho = static_cast<int>((opix / Wo) % Ho);
+    const int n = static_cast<int>(opix / (1LL * Wo * Ho));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    int y0 = ho, y1 = ho, x0 = wo, x1 = wo;
+    float ly = 0.f, lx = 0.f;
+    if (up) { up2_taps(ho, H, y0, y1, ly); up2_taps(wo, W, x0, x1, lx); }
+    const float wts[4] = {(1.f - ly) * (1.f - lx), (1.f - ly) * lx, ly * (1.f - lx), ly * lx};
+    const int ys[4] = {y0, y0, y1, y1}, xs[4] = {x0, x1, x0, x1};
+    const int ntap = up ? 4 : 1;
+    for (int t = 0; t < ntap; ++t) {
+      const float* p = x + ((static_cast<size_t>(n) * H + ys[t]) * W + xs[t]) * C + g * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        if (c < C) {
+          const float mean = __ldg(stats + (static_cast<size_t>(n) * C + c) * 2);
+          const float rstd = __ldg(stats + (static_cast<size_t>(n) * C + c) * 2 + 1);
+          const float yv = fmaxf((__ldg(p + j) - mean) * rstd, 0.f);
+          v[j] = fmaf(up ? wts[t] : 1.f, yv, v[j]);
+        }
+      }
+    }
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      __nv_bfloat16 ah, al, bh, bl;
+      split_bf16(v[j], ah, al);
+      split_bf16(v[j + 1], bh, bl);
+      ph[j >> 1] = pack_bf16x2(ah, bh);
+      pl[j >> 1] = pack_bf16x2(al, bl);
+    }
+    *reinterpret_cast<uint4*>(hi + opix * cpad + g * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4*>(lo + opix * cpad + g * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
+// block = sample, thread = channel.  Phase 1: dz = relu'(y) * (transpose of the x2 up-sampling applied to da),
+// stored in dx, with its two per-channel sums; phase 2: dx = rstd * (dz - mean(dz) - xh * mean(dz * xh)).
+__global__ void __launch_bounds__(256) inorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                                        const float* __restrict__ da, int H, int W, int C, int up,
+                                                        float* __restrict__ dx) {
+  const int n = blockIdx.x;
+  const int Ho = H << up, Wo = W << up;
+  const int HW = H * W;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = stats[(static_cast<size_t>(n) * C + c) * 2], rstd = stats[(static_cast<size_t>(n) * C + c) * 2 + 1];
+    const float* xp = x + static_cast<size_t>(n) * HW * C + c;
+    const float* gp = da + static_cast<size_t>(n) * Ho * Wo * C + c;
+    float* op = dx + static_cast<size_t>(n) * HW * C + c;
+    float s1 = 0.f, s2 = 0.f;
+    for (int h = 0; h < H; ++h) {
+      for (int w = 0; w < W; ++w) {
+        float g = 0.f;
+        if (up) {
+          for (int qy = max(2 * h - 1, 0); qy <= min(2 * h + 2, Ho - 1); ++qy) {
+            int y0, y1; float ly;
+            up2_taps(qy, H, y0, y1, ly);
+            const float wy = (y0 == h ? 1.f - ly : 0.f) + (y1 == h ? ly : 0.f);
+            if (wy == 0.f) continue;
+            for (int qx = max(2 * w - 1, 0); qx <= min(2 * w + 2, Wo - 1); ++qx) {
+              int x0, x1; float lx;
+              up2_taps(qx, W, x0, x1, lx);
+              const float wx = (x0 == w ? 1.f - lx : 0.f) + (x1 == w ? lx : 0.f);
+              if (wx != 0.f) g = fmaf(wy * wx, __ldg(gp + (static_cast<size_t>(qy) * Wo + qx) * C), g);
+            }
+          }
+        } else {
+          g = __ldg(gp + (static_cast<size_t>(h) * W + w) * C);
+        }
+        const float xh = (__ldg(xp + (static_cast<size_t>(h) * W + w) * C) - mean) * rstd;
+        const float dz = xh > 0.f ? g : 0.f;
+        op[(static_cast<size_t>(h) * W + w) * C] = dz;
+        s1 += dz;
+        s2 = fmaf(dz, xh, s2);
+      }
+    }
+    const float m1 = s1 / HW, m2 = s2 / HW;
+    for (int i = 0; i < HW; ++i) {
+      const float xh = (__ldg(xp + static_cast<size_t>(i) * C) - mean) * rstd;
+      op[static_cast<size_t>(i) * C] = rstd * (op[static_cast<size_t>(i) * C] - m1 - xh * m2);
+    }
+  }
+}
+
+int inorm_relu_fwd(const float* x, int N, int H, int W, int C, int up2, float eps, float* stats, void* hi, void* lo,
+                   int cpad, cudaStream_t stream) {
+  if (!x || !stats || !hi || !lo || N <= 0 || H <= 0 || W <= 0 || C <= 0 || cpad < C || cpad % 8) {
+    set_error("inorm_relu_fwd: bad arguments");
+    return L2I_ERR_BAD_ARG;
+  }
+  inorm_stats_kernel<<<N, 256, 0, stream>>>(x, H * W, C, eps, stats);
+  int rc = check_launch("inorm_stats_kernel");
+  if (rc) return rc;
+  const int up = up2 ? 1 : 0;
+  const long long total = 1LL * N * (H << up) * (W << up) * (cpad >> 3);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  inorm_apply_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, stats, N, H, W, C, up, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                                  reinterpret_cast<__nv_bfloat16*>(lo), cpad);
+  return check_launch("inorm_apply_kernel");
+}
+
+int inorm_relu_bwd(const float* x, const float* stats, const float* da, int N, int H, int W, int C, int up2, float* dx,
+                   cudaStream_t stream) {
+  if (!x || !stats || !da || !dx || N <= 0 || H <= 0 || W <= 0 || C <= 0) {
+    set_error("inorm_relu_bwd: bad arguments");
+    return L2I_ERR_BAD_ARG;
+  }
+  inorm_bwd_kernel<<<N, 256, 0, stream>>>(x, stats, da, H, W, C, up2 ? 1 : 0, dx);
+  return check_launch("inorm_bwd_kernel");
+}
+
+}  // namespace l2i

@@ -360,6 +360,81 @@ def norm_conv(x, weight, bias, running_mean, running_var, training, mask_pm=None
                             training, momentum, eps, up2, res_up2)
 
 
+class MaskTrunkFn(torch.autograd.Function):
+    """The convolutional trunk of MaskRegressNetv2 (reference model/mask_regression.py:66-99) as one autograd node:
+
+        x (N,4,4,256) -> [conv3x3 -> InstanceNorm -> ReLU -> bilinear x2] x 2 -> conv3x3 -> InstanceNorm -> ReLU
+                      -> conv1x1 (256 -> 1) -> logits (N,16,16,1)
+
+    Each InstanceNorm/ReLU/up-sampling stage writes the next convolution's operand pair directly
+    (csrc/layout_ops.cu inorm_*); the backward reads every gradient tensor once."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3, w4, b4, sn1, sn2, sn3, sn4):
+        x = _c(x)
+        ws, bs, sns = (w1, w2, w3, w4), (b1, b2, b3, b4), (sn1, sn2, sn3, sn4)
+        sts = [ops.sn_sigma(_c(w), sn[0], sn[1], training=sn[3], eps=sn[2]) if sn else None for w, sn in zip(ws, sns)]
+        wps = [ops.conv_weight_prep(_c(w), st.sigma if st else None, need_dgrad=True) for w, st in zip(ws, sts)]
+        pair = ops.act_split(x)
+        saved_pairs, hs, stats = [pair], [], []
+        for i in range(3):
+            h, _ = ops.conv2d_fwd(pair, wps[i].f_hi, wps[i].f_lo, ws[i].shape[0], 9, bias=_c(bs[i]))
+            pair, st = ops.inorm_relu_fwd(h, up2=i < 2)
+            hs.append(h); stats.append(st); saved_pairs.append(pair)
+        logit, _ = ops.conv2d_fwd(pair, wps[3].f_hi, wps[3].f_lo, ws[3].shape[0], 1, bias=_c(bs[3]))
+        flat = []
+        for st in sts:
+            flat += list(st) if st else [None, None, None]
+        ctx.save_for_backward(*[t for p in saved_pairs for t in (p.hi, p.lo)], *hs, *stats,
+                              *[t for wp in wps for t in (wp.d_hi, wp.d_lo)], *ws, *flat)
+        ctx.chans = [p.C for p in saved_pairs]
+        return logit
+
+    @staticmethod
+    def backward(ctx, dlogit):
+        t = list(ctx.saved_tensors)
+        pairs = [ops.Pair(t[2 * i], t[2 * i + 1], ctx.chans[i]) for i in range(4)]
+        hs, stats = t[8:11], t[11:14]
+        dws = [(t[14 + 2 * i], t[15 + 2 * i]) for i in range(4)]
+        ws = t[22:26]
+        sts = [ops.SNState(*t[26 + 3 * i:29 + 3 * i]) if t[26 + 3 * i] is not None else None for i in range(4)]
+        need = ctx.needs_input_grad
+
+        def wgrad(dy, xin, taps, i):
+            g = ops.conv2d_wgrad(dy, xin, taps)
+            return ops.sn_weight_grad(g, ws[i], sts[i]) if sts[i] is not None else _dw_to_torch(g, g.shape[0], g.shape[2], taps)
+
+        grads_w, grads_b = [None] * 4, [None] * 4
+        dyp, _, colsum = ops.grad_split(_c(dlogit), want_lo=True, up=False)
+        grads_b[3] = colsum
+        if need[7]:
+            grads_w[3] = wgrad(dyp, pairs[3], 1, 3)
+        da, _ = ops.conv2d_fwd(dyp, dws[3][0], dws[3][1], ctx.chans[3], 1)
+        dx = None
+        for i in (2, 1, 0):
+            dh = ops.inorm_relu_bwd(hs[i], stats[i], da, up2=i < 2)
+            dyp, _, colsum = ops.grad_split(dh, want_lo=True, up=False)
+            grads_b[i] = colsum
+            if need[1 + 2 * i]:
+                grads_w[i] = wgrad(dyp, pairs[i], 9, i)
+            if i > 0 or need[0]:
+                da, _ = ops.conv2d_fwd(dyp, dws[i][0], dws[i][1], ctx.chans[i], 9)
+                if i == 0:
+                    dx = da
+        return (dx, grads_w[0], grads_b[0], grads_w[1], grads_b[1], grads_w[2], grads_b[2], grads_w[3], grads_b[3],
+                None, None, None, None)
+
+
+def mask_trunk(x, conv1, conv2, conv3, conv4):
+    """x (N,4,4,256) NHWC -> mask logits (N,16,16,1) through the four conv modules of MaskRegressNetv2."""
+    args, sns = [], []
+    for m in (conv1, conv2, conv3, conv4):
+        w, b, sn = _sn_of(m)
+        args += [w, b]
+        sns.append(sn)
+    return MaskTrunkFn.apply(x, *args, *sns)
+
+
 class PspPoolFn(torch.autograd.Function):
     """The four AdaptiveAvgPool2d of PSPModule (resnet_generator_app_v2.py:741-746) in one pass: (B,H,W,C) -> (B,50,C)."""
 

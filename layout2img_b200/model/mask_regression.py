@@ -35,11 +35,7 @@ class MaskRegressNetv2(nn.Module):
         b, num_o, _ = bbox.size()
         x = L.sn_linear(self.fc, obj_feat.view(b * num_o, -1))
         x = to_nhwc(x.view(b * num_o, 256, 4, 4))
-        x = _instance_norm_relu(L.conv2d_module(self.conv1[0], x))
-        x = _bilinear(x, 8)
-        x = _instance_norm_relu(L.conv2d_module(self.conv2[0], x))
-        x = _bilinear(x, 16)
-        x = _instance_norm_relu(L.conv2d_module(self.conv3[0], x))
-        x = torch.sigmoid(L.conv2d_module(self.conv3[3], x))                   # (b*o,16,16,1)
+        # three (conv3x3 -> InstanceNorm -> ReLU [-> bilinear x2]) stages + the 1x1 logit conv: one fused node
+        x = torch.sigmoid(L.mask_trunk(x, self.conv1[0], self.conv2[0], self.conv3[0], self.conv3[3]))   # (b*o,16,16,1)
         x = x.view(b, num_o, self.mask_size, self.mask_size)
         return L.masks_to_layout(x, bbox.to(x.device).float(), self.map_size)

@@ -310,6 +310,25 @@ def stage_mix_bwd(stage, y, alpha, bmask, hard, dout):
     return dstage, dalpha, dsoft
 
 
+def inorm_relu_fwd(x, up2: bool, eps: float = 1e-5):
+    """InstanceNorm (no affine) -> ReLU -> [bilinear x2] of x (N,H,W,C) -> (Pair at the output resolution, stats)."""
+    _chk(x)
+    n, h, w, c = x.shape
+    s = 2 if up2 else 1
+    stats = torch.empty((n, c, 2), dtype=torch.float32, device=x.device)
+    buf = torch.empty((2, n, h * s, w * s, pad8(c)), dtype=torch.bfloat16, device=x.device)
+    call("l2i_inorm_relu_fwd", x, n, h, w, c, int(up2), float(eps), stats, buf[0], buf[1], pad8(c))
+    return Pair(buf[0], buf[1], c), stats
+
+
+def inorm_relu_bwd(x, stats, da, up2: bool):
+    _chk(x); _chk(da)
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    call("l2i_inorm_relu_bwd", x, stats, da, n, h, w, c, int(up2), dx)
+    return dx
+
+
 # --------------------------------------------------------------------------------------------
 # pyramid pooling (PSPModule)
 # --------------------------------------------------------------------------------------------

@@ -483,3 +483,25 @@ def test_spectral_norm_kernels_match_torch(dev, shape, training):
     g_ours = gy.float().permute(0, 2, 3, 1).reshape(shape[0], taps, shape[1]).contiguous().to(dev)
     dw = ops.sn_weight_grad(g_ours, w_orig, st)
     close(dw, conv.weight_orig.grad, 1e-4, 1e-5 * conv.weight_orig.grad.abs().max().item(), "d weight_orig")
+
+
+@pytest.mark.parametrize("H,up2", [(4, True), (8, True), (16, False)])
+def test_inorm_relu_upsample_matches_torch(dev, H, up2):
+    """csrc/layout_ops.cu inorm_* vs InstanceNorm2d -> ReLU -> F.interpolate(bilinear, x2) of
+    mask_regression.py:66-99 in fp64, forward (as the operand pair) and backward."""
+    from layout2img_b200 import ops
+    g = torch.Generator().manual_seed(H)
+    N, C = 5, 256
+    x = torch.randn(N, C, H, H, generator=g) * 2 + 0.5
+    xr = x.double().requires_grad_()
+    y = F.relu(F.instance_norm(xr, eps=1e-5))
+    if up2:
+        y = F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=False)
+    da = torch.randn(y.shape, generator=g)
+    y.backward(da.double())
+    xg = nhwc(x).to(dev)
+    pair, stats = ops.inorm_relu_fwd(xg, up2)
+    got = (pair.hi.float() + pair.lo.float()).permute(0, 3, 1, 2)
+    close(got, y, 1e-3, 1e-4, "inorm fwd pair")
+    dx = ops.inorm_relu_bwd(xg, stats, nhwc(da).to(dev), up2)
+    close(dx.permute(0, 3, 1, 2), xr.grad, 1e-3, 1e-4 * max(1.0, xr.grad.abs().max().item()), "inorm bwd")
