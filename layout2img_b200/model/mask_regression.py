@@ -3,21 +3,9 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import functional as L
 from .layers import Conv2d, to_nchw_view, to_nhwc
-
-
-def _instance_norm_relu(x, eps=1e-5):
-    """nn.InstanceNorm2d (affine=False, no running stats) + ReLU on an NHWC tensor."""
-    mean = x.mean(dim=(1, 2), keepdim=True)
-    var = x.var(dim=(1, 2), unbiased=False, keepdim=True)
-    return F.relu((x - mean) * torch.rsqrt(var + eps))
-
-
-def _bilinear(x, size):
-    return F.interpolate(to_nchw_view(x), size=size, mode='bilinear', align_corners=False).permute(0, 2, 3, 1).contiguous()
 
 
 class MaskRegressNetv2(nn.Module):

@@ -232,3 +232,19 @@ def test_full_size_batch_independence():
                 if i > 0:      # per-object outputs come back as [all large ROIs, all small ROIs] of the call: compare as sets
                     got, want = got.flatten().sort().values, want.flatten().sort().values
                 close(want, got, 1e-4, 1e-5 * max(1.0, got.abs().max().item()), nm + " full batch vs halves")
+
+
+def test_sampler_shape_batch_one():
+    """The reference's samplers run the generator in eval mode one layout at a time with a data-dependent number
+    of objects and truncated latents (test_context_app_v2.py:60-80): batch 1, 3 objects, against the oracle."""
+    dev = torch.device("cuda:0")
+    z, meta = load_case("C")
+    G, _, PG, _ = _build(meta, dev)
+    G.eval()
+    data = synthetic_layout(1, 3, meta["num_classes"], seed=9)
+    zt = data["z"].clamp(-2.0, 2.0)                      # truncted_random(thres=2.0) support
+    with torch.no_grad():
+        got = G.forward(zt.to(dev), data["bbox"], data["z_im"].to(dev), data["label"].to(dev))
+        want = O.g_forward(PG, zt, data["bbox"], data["z_im"], data["label"], False)
+    assert got.shape == (1, 3, 128, 128)
+    close(got, want, what="batch-1 eval forward")
