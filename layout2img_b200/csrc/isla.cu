@@ -306,7 +306,7 @@ struct IslaBwdParams {
 
 // pass A: LPP lanes per pixel (32, or 16 when C <= 64), lanes stride the channels (float4 per lane per step)
 template <int OM, int LPP>
-__global__ void __launch_bounds__(256) isla_bwd_a_kernel(const IslaBwdParams p) {
+__global__ void __launch_bounds__(256, OM <= 8 ? 3 : 2) isla_bwd_a_kernel(const IslaBwdParams p) {
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPP, l = lane % LPP;
   constexpr int PPW = 32 / LPP;
@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(256) isla_bwd_a_kernel(const IslaBwdParams p) 
     for (int o = 0; o < p.O; ++o) S += __ldg(mp + o);
     const float invS = 1.0f / S;
     float dm[OM];
+    float common = 0.f;
 #pragma unroll
     for (int o = 0; o < OM; ++o) dm[o] = 0.f;
     for (int c = l * 4; c < p.C; c += LPP * 4) {
@@ -352,21 +353,22 @@ __global__ void __launch_bounds__(256) isla_bwd_a_kernel(const IslaBwdParams p) 
           Bt[0] = fmaf(m, b4.x, Bt[0]); Bt[1] = fmaf(m, b4.y, Bt[1]); Bt[2] = fmaf(m, b4.z, Bt[2]); Bt[3] = fmaf(m, b4.w, Bt[3]);
         }
       }
-      float gv[4], xh[4], Gn[4], Bn[4];
+      // d m_o * S = sum_c g xh gamma_oc + sum_c g beta_oc - sum_c g (xh (Gamma - 1) + B), and
+      // xh (Gamma - 1) + B = out - xh: the subtracted term is the same for every object (`common`)
+      float gv[4], gx[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        xh[j] = (xv[j] - __ldg(p.mean_invstd + c + j)) * __ldg(p.mean_invstd + p.C + c + j);
+        const float xh = (xv[j] - __ldg(p.mean_invstd + c + j)) * __ldg(p.mean_invstd + p.C + c + j);
         float outv;
         if (p.O > 0) {
-          Gn[j] = G[j] * invS;            // Gamma - 1
-          Bn[j] = Bt[j] * invS;
-          outv = (Gn[j] + 1.0f) * xh[j] + Bn[j];
+          outv = (G[j] * invS + 1.0f) * xh + Bt[j] * invS;
         } else {
-          Gn[j] = 0.f; Bn[j] = 0.f;
-          outv = xh[j];
+          outv = xh;
           if (p.aff_w) outv = outv * __ldg(p.aff_w + c + j) + __ldg(p.aff_b + c + j);
         }
         gv[j] = (p.relu && !(outv > 0.f)) ? 0.f : dsum[j];
+        gx[j] = gv[j] * xh;
+        common = fmaf(gv[j], outv - xh, common);
       }
       if (pok) *reinterpret_cast<float4*>(p.gbuf + gp * p.C + c) = make_float4(gv[0], gv[1], gv[2], gv[3]);
 #pragma unroll
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(256) isla_bwd_a_kernel(const IslaBwdParams p) 
           const float go[4] = {g4.x, g4.y, g4.z, g4.w}, bo[4] = {b4.x, b4.y, b4.z, b4.w};
           float acc = 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc += gv[j] * (xh[j] * (go[j] - Gn[j]) + (bo[j] - Bn[j]));
+          for (int j = 0; j < 4; ++j) acc = fmaf(gx[j], go[j], fmaf(gv[j], bo[j], acc));
           dm[o] += acc;
         }
       }
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(256) isla_bwd_a_kernel(const IslaBwdParams p) 
 #pragma unroll
       for (int o = 0; o < OM; ++o) {
         if (o < p.O) {
-          float v = dm[o];
+          float v = dm[o] - common;
 #pragma unroll
           for (int off = LPP / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
           if (l == 0 && pok) p.dmask[gp * p.O + o] = v * invS;
