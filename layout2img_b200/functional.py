@@ -168,8 +168,8 @@ def _sn_of(conv):
         if isinstance(hook, SpectralNorm):
             if hook.n_power_iterations != 1 or hook.dim != 0:
                 raise ValueError("layout2img_b200 implements spectral_norm(n_power_iterations=1, dim=0)")
-            return conv.weight_orig, conv.bias, (conv.weight_u, conv.weight_v, hook.eps, conv.training)
-    return conv.weight, conv.bias, None
+            return conv.weight_orig, getattr(conv, "bias", None), (conv.weight_u, conv.weight_v, hook.eps, conv.training)
+    return conv.weight, getattr(conv, "bias", None), None
 
 
 class SNLinearFn(torch.autograd.Function):
@@ -203,6 +203,33 @@ class SNLinearFn(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy2.sum(dim=0)
         return dx, dw, db, None, None, None, None
+
+
+class SNWeightFn(torch.autograd.Function):
+    """W_orig / sigma as a tensor, for the small spectrally normalised weights that are consumed by library ops
+    (the discriminator's class embeddings and appearance projection, rcnn_discriminator_app.py:104-109; the
+    generator's RGB conv :418): power iteration / sigma / gradient in csrc/specnorm.cu, one division here."""
+
+    @staticmethod
+    def forward(ctx, w_orig, u, v, eps, training):
+        st = ops.sn_sigma(_c(w_orig), u, v, training, eps)
+        ctx.save_for_backward(w_orig, st.sigma, st.u, st.v)
+        return w_orig / st.sigma
+
+    @staticmethod
+    def backward(ctx, dw):
+        w_orig, sigma, u, v = ctx.saved_tensors
+        r = w_orig.shape[0]
+        g = _c(dw).reshape(r, 1, -1)                      # taps = 1: torch layout == kernel layout
+        return ops.sn_weight_grad(g, _c(w_orig), ops.SNState(sigma, u, v)).view_as(w_orig), None, None, None, None
+
+
+def sn_weight(module):
+    """The (normalised) weight of a module without firing its library spectral-norm hook."""
+    w, _, sn = _sn_of(module)
+    if sn is None:
+        return w
+    return SNWeightFn.apply(w, sn[0], sn[1], sn[2], sn[3])
 
 
 def sn_linear(module, x):

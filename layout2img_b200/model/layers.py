@@ -42,7 +42,7 @@ class Conv2d(nn.Conv2d):
         if norm is None:
             return L.conv2d(x, self.weight, self.bias, residual, relu_in, up2_in, res_up2)   # plain (non-SN) use
         bn, mask_pm, gamma, beta = norm
-        return L.norm_conv(x, self.weight, self.bias, bn.running_mean, bn.running_var, bn.training,
+        return L.norm_conv(x, L.sn_weight(self), self.bias, bn.running_mean, bn.running_var, bn.training,
                            mask_pm=mask_pm, gamma=gamma, beta=beta, aff_w=bn.weight if bn.affine else None,
                            aff_b=bn.bias if bn.affine else None, residual=residual, up2=up2_in, res_up2=res_up2,
                            momentum=bn.momentum, eps=bn.eps)

@@ -8,7 +8,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import functional as L
-from .layers import avg_pool2, conv2d, fire_param_hooks, to_nhwc
+from .layers import conv2d, to_nhwc
 
 __all__ = ["CombineDiscriminator128_app", "ResnetDiscriminator128_app", "OptimizedBlock", "ResBlock", "conv2d"]
 
@@ -100,11 +100,11 @@ class ResnetDiscriminator128_app(nn.Module):
         app_feat = F.relu(self.app_conv(obj_feat))
         k_, hh, ww_, c = app_feat.shape
         feat = app_feat.view(k_, hh * ww_, c)
-        fire_param_hooks(self.app)
-        w1, w2 = self.app.weight[0, :c], self.app.weight[0, c:]
+        w_app = L.sn_weight(self.app)                                   # (1, 2c), spectrally normalised
+        w1, w2 = w_app[0, :c], w_app[0, c:]
         colsum = feat.sum(dim=2)                                        # (K, P)
         proj = feat @ w1                                                # (K, P)
-        app_y = self.l_y_app(y)                                         # (K, C)
+        app_y = F.embedding(y, L.sn_weight(self.l_y_app))               # (K, C)
         out_app = ((colsum * proj).sum(dim=1, keepdim=True) / (c * c)
                    + (app_y @ w2).unsqueeze(1) + self.app.bias)
 
@@ -112,7 +112,7 @@ class ResnetDiscriminator128_app(nn.Module):
         obj_feat = self.block_obj5(obj_feat)
         obj_feat = F.relu(obj_feat).sum(dim=(1, 2))                     # (K,1024)
         out_obj = L.sn_linear(self.l_obj, obj_feat)
-        out_obj = out_obj + torch.sum(self.l_y(y) * obj_feat, dim=1, keepdim=True)
+        out_obj = out_obj + torch.sum(F.embedding(y, L.sn_weight(self.l_y)) * obj_feat, dim=1, keepdim=True)
         return out_im, out_obj, out_app
 
 

@@ -214,7 +214,8 @@ class _GeneratorBase(nn.Module):
         x, stage_mask = self.res4(x, w, stage_bbox)
         stage_bbox = L.stage_mix(stage_mask, self.alpha4, bmask, y, hard)
         x, _ = self.res5(x, w, stage_bbox)
-        x = self.final[2](x, norm=(self.final[0], None, None, None))      # BN -> ReLU -> conv fused
+        x = self.final[2].forward(x, norm=(self.final[0], None, None, None))   # BN -> ReLU -> conv fused (.forward: the
+        # spectral-norm hook is bypassed, the normalisation runs in csrc/specnorm.cu via L.sn_weight)
         return to_nchw_view(torch.tanh(x))
 
     def init_parameter(self):
