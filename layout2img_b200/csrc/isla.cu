@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(256, OM <= 8 ? 3 : 2) isla_bwd_a_kernel(const 
       }
       // d m_o * S = sum_c g xh gamma_oc + sum_c g beta_oc - sum_c g (xh (Gamma - 1) + B), and
       // xh (Gamma - 1) + B = out - xh: the subtracted term is the same for every object (`common`)
-      float gv[4], gx[4];
+      float gv[4], gx[4], dxh[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float xh = (xv[j] - __ldg(p.mean_invstd + c + j)) * __ldg(p.mean_invstd + p.C + c + j);
@@ -369,8 +369,13 @@ __global__ void __launch_bounds__(256, OM <= 8 ? 3 : 2) isla_bwd_a_kernel(const 
         gv[j] = (p.relu && !(outv > 0.f)) ? 0.f : dsum[j];
         gx[j] = gv[j] * xh;
         common = fmaf(gv[j], outv - xh, common);
+        // d xh = Gamma * g (ISLA) or aff_w * g (affine BN): parked in dx for passes B and C
+        dxh[j] = gv[j] * ((p.O > 0) ? (G[j] * invS + 1.0f) : (p.aff_w ? __ldg(p.aff_w + c + j) : 1.0f));
       }
-      if (pok) *reinterpret_cast<float4*>(p.gbuf + gp * p.C + c) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+      if (pok) {
+        *reinterpret_cast<float4*>(p.gbuf + gp * p.C + c) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+        *reinterpret_cast<float4*>(p.dx + gp * p.C + c) = make_float4(dxh[0], dxh[1], dxh[2], dxh[3]);
+      }
 #pragma unroll
       for (int o = 0; o < OM; ++o) {
         if (o < p.O) {
@@ -407,12 +412,9 @@ __global__ void __launch_bounds__(128) isla_bwd_b_kernel(const IslaBwdParams p) 
   const int hw = p.H * p.W;
   const int seg = (hw + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * seg, p1 = min(hw, p0 + seg);
-  float gam[OM], accg[OM], accb[OM];
+  float accg[OM], accb[OM];
 #pragma unroll
-  for (int o = 0; o < OM; ++o) {
-    gam[o] = (o < p.O) ? __ldg(p.gamma + (static_cast<size_t>(b) * p.O + o) * p.C + c) : 0.f;
-    accg[o] = 0.f; accb[o] = 0.f;
-  }
+  for (int o = 0; o < OM; ++o) { accg[o] = 0.f; accb[o] = 0.f; }
   const float mean = __ldg(p.mean_invstd + c), invstd = __ldg(p.mean_invstd + p.C + c);
   const float aw = (p.O == 0 && p.aff_w) ? __ldg(p.aff_w + c) : 1.0f;
   float s1 = 0.f, s2 = 0.f;
@@ -423,18 +425,17 @@ __global__ void __launch_bounds__(128) isla_bwd_b_kernel(const IslaBwdParams p) 
     const float xh = (__ldg(p.x + gp * p.C + c) - mean) * invstd;
     if (p.O > 0) {
       float m[OM];
-      float S = kMaskEps, G = 0.f;
+      float S = kMaskEps;
 #pragma unroll
       for (int o = 0; o < OM; ++o) {
         m[o] = (o < p.O) ? __ldg(p.mask + gp * p.O + o) : 0.f;   // warp-uniform address: one broadcast load
         S += m[o];
-        G = fmaf(m[o], gam[o], G);
       }
       const float invS = 1.0f / S;
       const float gx = g * xh * invS, gs = g * invS;
 #pragma unroll
       for (int o = 0; o < OM; ++o) { accg[o] = fmaf(gx, m[o], accg[o]); accb[o] = fmaf(gs, m[o], accb[o]); }
-      const float dxh = (G * invS + 1.0f) * g;
+      const float dxh = __ldg(p.dx + gp * p.C + c);            // Gamma * g, written by pass A
       s1 += dxh; s2 += dxh * xh;
     } else {
       s1 += g; s2 += g * xh;           // dbias, dweight of the affine form
@@ -453,42 +454,30 @@ __global__ void __launch_bounds__(128) isla_bwd_b_kernel(const IslaBwdParams p) 
   (void)aw;
 }
 
-// pass C: dx.  thread <-> (pixel, 4 channels)
+// pass C: dx = (dxh - mean(dxh) - xh * mean(dxh * xh)) * invstd in place (dx holds dxh from pass A).
+// thread <-> (pixel, 4 channels); a pure streaming pass.
 __global__ void __launch_bounds__(256) isla_bwd_c_kernel(const IslaBwdParams p) {
   const int cg = p.C >> 2;
   const long long items = 1LL * p.B * p.H * p.W * cg;
-  const int hw = p.H * p.W;
   for (long long it = 1LL * blockIdx.x * blockDim.x + threadIdx.x; it < items; it += 1LL * gridDim.x * blockDim.x) {
     const int g4 = static_cast<int>(it % cg);
     const long long gp = it / cg;
-    const int b = static_cast<int>(gp / hw);
     const int c = g4 * 4;
     const float4 xv4 = __ldg(reinterpret_cast<const float4*>(p.x + gp * p.C + c));
-    const float4 gv4 = __ldg(reinterpret_cast<const float4*>(p.gbuf + gp * p.C + c));
-    const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w}, gv[4] = {gv4.x, gv4.y, gv4.z, gv4.w};
-    float G[4] = {0, 0, 0, 0};
-    float S = kMaskEps;
-    if (p.O > 0) {
-      const float* mp = p.mask + gp * p.O;
-      for (int o = 0; o < p.O; ++o) {
-        const float m = __ldg(mp + o);
-        S += m;
-        const float4 q = __ldg(reinterpret_cast<const float4*>(p.gamma + (static_cast<size_t>(b) * p.O + o) * p.C + c));
-        G[0] = fmaf(m, q.x, G[0]); G[1] = fmaf(m, q.y, G[1]); G[2] = fmaf(m, q.z, G[2]); G[3] = fmaf(m, q.w, G[3]);
-      }
-    }
+    const float4 dv4 = *reinterpret_cast<const float4*>(p.dx + gp * p.C + c);
+    const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w}, dv[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
     float r[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float mean = __ldg(p.mean_invstd + c + j), invstd = __ldg(p.mean_invstd + p.C + c + j);
       const float xh = (xv[j] - mean) * invstd;
-      float scale = 1.0f;
-      if (p.O > 0) scale = G[j] / S + 1.0f;
-      else if (p.aff_w) scale = __ldg(p.aff_w + c + j);
-      float dxh = scale * gv[j];
+      float dxh = dv[j];
       if (p.train) {
         double m1 = p.csum[2 * (c + j)], m2 = p.csum[2 * (c + j) + 1];
-        if (p.O == 0) { m1 *= scale; m2 *= scale; }
+        if (p.O == 0) {                  // csum holds (sum g, sum g*xh) = (d bias, d weight) of the affine form
+          const float scale = p.aff_w ? __ldg(p.aff_w + c + j) : 1.0f;
+          m1 *= scale; m2 *= scale;
+        }
         dxh = dxh - static_cast<float>(m1 / p.count) - xh * static_cast<float>(m2 / p.count);
       }
       r[j] = dxh * invstd;
