@@ -419,6 +419,7 @@ __global__ void __launch_bounds__(128) isla_bwd_b_kernel(const IslaBwdParams p) 
   const float aw = (p.O == 0 && p.aff_w) ? __ldg(p.aff_w + c) : 1.0f;
   float s1 = 0.f, s2 = 0.f;
   double d1 = 0, d2 = 0;
+#pragma unroll 4
   for (int pix = p0; pix < p1; ++pix) {
     const size_t gp = static_cast<size_t>(b) * hw + pix;
     const float g = __ldg(p.gbuf + gp * p.C + c);
