@@ -251,3 +251,19 @@ def test_sampler_shape_batch_one():
         want = O.g_forward(PG, zt, data["bbox"], data["z_im"], data["label"], False)
     assert got.shape == (1, 3, 128, 128)
     close(got, want, what="batch-1 eval forward")
+
+
+def test_generator_without_context_attention():
+    """ResnetGenerator128 (reference :299-397): the same network without the object-context attention."""
+    from layout2img_b200.model.resnet_generator_app_v2 import ResnetGenerator128
+    dev = torch.device("cuda:0")
+    z, meta = load_case("Cpad")
+    data = _data(meta)
+    PG = make_state(load_schema("G_nocontext", meta["num_classes"]), meta["seed_g"])
+    G = ResnetGenerator128(num_classes=meta["num_classes"], output_dim=3)
+    G.load_state_dict(PG)
+    G.to(dev).eval()
+    with torch.no_grad():
+        got = G(data["z"].to(dev), data["bbox"].to(dev), data["z_im"].to(dev), data["label"].to(dev))
+        want = O.g_forward(PG, data["z"], data["bbox"], data["z_im"], data["label"], False, context=False)
+    close(got, want, what="G (no context) eval forward")
