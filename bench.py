@@ -95,6 +95,7 @@ def workload_config(n):
                         "(BASELINE.json configs[2]; configs[3] data-parallel at N>1)",
             "per_gpu_batch": 64, "global_batch": 64 * n, "num_obj": NUM_OBJ, "img": IMG,
             "parallelism": f"dp{n}" if n > 1 else "single",
+            "batch_norm": "per-rank statistics (default; --sync-bn = global-batch statistics, 2 small all-reduces per norm layer)",
             "l2": "no explicit flush: each step streams ~0.4 GB of weights and >2 GB of activations, "
                   "far beyond the 126 MB L2"}
 
@@ -232,6 +233,9 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        if args.sync_bn:
+            from layout2img_b200 import ops
+            ops.set_sync_bn(True)
     lib = _lib.lib()
 
     B = args.batch
@@ -381,6 +385,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (the metric is quoted at 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--shapes-file", default=None, help="write the per-shape convolution timing table here")
+    ap.add_argument("--sync-bn", action="store_true",
+                    help="N>1: batch-norm statistics over the global batch (the reference's multi-GPU SynchronizedBatchNorm2d) "
+                         "instead of per-rank statistics")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))

@@ -97,11 +97,14 @@ int l2i_isla_fwd(const float* x, const float* mean_invstd, const float* mask, co
 /* Backward of l2i_isla_fwd followed by (relu) and (nearest x2): dout [B,H<<up2,W<<up2,C].
  * Writes dx [B,H,W,C]; for O > 0 dmask [B,H,W,O], dgamma, dbeta [B,O,C]; csum [2C] fp64 receives
  * (sum dxhat, sum dxhat*xhat) for O > 0 or (dbias, dweight) of the affine form for O == 0.
- * gbuf [B,H,W,C] is scratch.  train = 0 skips the batch-statistics terms (eval-mode BN). */
+ * gbuf [B,H,W,C] is scratch.  train = 0 skips the batch-statistics terms (eval-mode BN).
+ * phase 0 runs everything; for a batch norm whose statistics span several ranks (the reference's multi-GPU
+ * SynchronizedBatchNorm2d, sync_batchnorm/batchnorm.py:90-111) call phase 1 (all reductions; dx is left holding
+ * d xhat), all-reduce csum, then phase 2 (dx) with count = the global pixel count (count <= 0: B*H*W). */
 int l2i_isla_bwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
                  const float* aff_w, const float* aff_b, const float* dout, int B, int H, int W, int C, int O,
                  int relu, int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum,
-                 float* dx, void* stream);
+                 float* dx, int phase, double count, void* stream);
 
 /* ---- layout maps (reference model/resnet_generator_app_v2.py:466-470,697-721, utils/bilinear.py:137-192)
  *      bbox [B*O,4] xywh in [0,1]; maps are [B,O,S,S] unless stated ------------------------------- */

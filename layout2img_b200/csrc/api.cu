@@ -98,9 +98,9 @@ int l2i_isla_fwd(const float* x, const float* mean_invstd, const float* mask, co
 int l2i_isla_bwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
                  const float* aff_w, const float* aff_b, const float* dout, int B, int H, int W, int C, int O,
                  int relu, int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum,
-                 float* dx, void* stream) {
+                 float* dx, int phase, double count, void* stream) {
   return isla_bwd(x, mean_invstd, mask, gamma, beta, aff_w, aff_b, dout, B, H, W, C, O, relu, up2, train, gbuf, dmask,
-                  dgamma, dbeta, csum, dx, ST(stream));
+                  dgamma, dbeta, csum, dx, phase, count, ST(stream));
 }
 int l2i_bbox_mask(const float* bbox, int BO, int H, int W, float* out, void* stream) {
   return bbox_mask(bbox, BO, H, W, out, ST(stream));

@@ -490,20 +490,28 @@ __global__ void __launch_bounds__(256) isla_bwd_c_kernel(const IslaBwdParams p) 
 int isla_bwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
              const float* aff_w, const float* aff_b, const float* dout, int B, int H, int W, int C, int O, int relu,
              int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum, float* dx,
-             cudaStream_t stream) {
+             int phase, double count, cudaStream_t stream) {
   if (!x || !mean_invstd || !dout || !gbuf || !csum || !dx || B <= 0 || C <= 0 || (C & 3)) { set_error("isla_bwd: bad arguments (C must be a multiple of 4)"); return L2I_ERR_BAD_ARG; }
   if (O > 0 && (!mask || !gamma || !beta || !dmask || !dgamma || !dbeta)) { set_error("isla_bwd: null ISLA operand"); return L2I_ERR_BAD_ARG; }
   if (O > 48) { set_error("isla_bwd: at most 48 objects per image supported"); return L2I_ERR_UNSUPPORTED; }
   IslaBwdParams p;
   p.x = x; p.mean_invstd = mean_invstd; p.mask = mask; p.gamma = gamma; p.beta = beta; p.aff_w = aff_w; p.aff_b = aff_b;
   p.dout = dout; p.gbuf = gbuf; p.dmask = dmask; p.dgamma = dgamma; p.dbeta = dbeta; p.csum = csum; p.dx = dx;
-  p.count = static_cast<double>(B) * H * W;
+  p.count = count > 0 ? count : static_cast<double>(B) * H * W;   // > 0: global count of a cross-rank batch norm
+  if (phase < 0 || phase > 2) { set_error("isla_bwd: phase must be 0 (all), 1 (reductions) or 2 (dx)"); return L2I_ERR_BAD_ARG; }
   p.B = B; p.H = H; p.W = W; p.C = C; p.O = O; p.relu = relu; p.up = up2 ? 1 : 0; p.train = train;
+  const long long pixels = 1LL * B * H * W;
+  if (phase == 2) {            // csum has been reduced across ranks by the caller; dx holds Gamma * g from phase 1
+    const long long items = pixels * (C >> 2);
+    long long blocks = (items + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    isla_bwd_c_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p);
+    return check_launch("isla_bwd_c_kernel");
+  }
   cudaError_t e = cudaMemsetAsync(csum, 0, sizeof(double) * 2 * C, stream);
   if (e == cudaSuccess && O > 0) e = cudaMemsetAsync(dgamma, 0, sizeof(float) * B * O * C, stream);
   if (e == cudaSuccess && O > 0) e = cudaMemsetAsync(dbeta, 0, sizeof(float) * B * O * C, stream);
   if (e != cudaSuccess) { set_error("isla_bwd: memset: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
-  const long long pixels = 1LL * B * H * W;
   {
     long long blocks = (pixels + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -543,6 +551,7 @@ int isla_bwd(const float* x, const float* mean_invstd, const float* mask, const 
     int rc = check_launch("isla_bwd_b_kernel");
     if (rc) return rc;
   }
+  if (phase == 1) return L2I_OK;
   {
     const long long items = pixels * (C >> 2);
     long long blocks = (items + 255) / 256;

@@ -32,7 +32,7 @@ int isla_fwd(const float* x, const float* mean_invstd, const float* mask, const 
 int isla_bwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
              const float* aff_w, const float* aff_b, const float* dout, int B, int H, int W, int C, int O, int relu,
              int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum, float* dx,
-             cudaStream_t stream);
+             int phase, double count, cudaStream_t stream);
 
 // layout_ops.cu
 int bbox_mask(const float* bbox, int BO, int H, int W, float* out, cudaStream_t stream);

@@ -56,6 +56,25 @@ class BoxMultiHeadedAttention(nn.Module):
         return self.layer_norm(output + new_residual)
 
 
+def _sync_batch_norm(x, bn):
+    """Affine batch norm of an NHWC tensor with statistics over ALL ranks (sum / sum of squares all-reduced with
+    the differentiable collective, as sync_batchnorm/batchnorm.py:90-125 does across DataParallel replicas)."""
+    import torch.distributed.nn.functional as dfn
+    c = x.shape[-1]
+    x2 = x.reshape(-1, c)
+    world = ops._SYNC_BN["world"]
+    stats = torch.stack([x2.sum(0), (x2 * x2).sum(0)]).double()
+    stats = dfn.all_reduce(stats, group=ops._SYNC_BN["group"])
+    n = x2.shape[0] * world
+    mean = stats[0] / n
+    var = (stats[1] / n - mean * mean).clamp_min(0)
+    with torch.no_grad():
+        bn.running_mean.mul_(1 - bn.momentum).add_(bn.momentum * mean.float())
+        bn.running_var.mul_(1 - bn.momentum).add_(bn.momentum * (var * n / max(n - 1, 1)).float())
+    y = (x2 - mean.float()) * torch.rsqrt(var.float() + bn.eps) * bn.weight + bn.bias
+    return y.view_as(x)
+
+
 class PSPModule(nn.Module):
     """reference :724-752.  Tiny pooled branches stay library ops; the 528->100 3x3 bottleneck conv is ours."""
 
@@ -87,8 +106,11 @@ class PSPModule(nn.Module):
             off += s * s
         x = L.psp_bottleneck(feats, torch.cat(priors, dim=1), self.bottleneck[0].weight)   # (b,h,w,100)
         bn = self.bottleneck[1]
-        x = F.batch_norm(x.view(-1, x.shape[-1]), bn.running_mean, bn.running_var, bn.weight, bn.bias,
-                         bn.training, bn.momentum, bn.eps).view_as(x)
+        if bn.training and ops._SYNC_BN["world"] > 1:
+            x = _sync_batch_norm(x, bn)                  # global-batch statistics (reference multi-GPU semantics)
+        else:
+            x = F.batch_norm(x.view(-1, x.shape[-1]), bn.running_mean, bn.running_var, bn.weight, bn.bias,
+                             bn.training, bn.momentum, bn.eps).view_as(x)
         x = F.relu(x)
         if self.training:
             if self.dropout_mask is not None:

@@ -190,16 +190,41 @@ def conv2d_wgrad(dy: Pair, x: Pair, taps: int) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # batch-norm statistics / ISLA
 # --------------------------------------------------------------------------------------------
+# Cross-rank batch statistics (the reference's multi-GPU SynchronizedBatchNorm2d, sync_batchnorm/batchnorm.py:90-111:
+# sum and sum-of-squares reduced over all replicas).  Off by default: every rank normalises with its own shard,
+# which is what the reference does on one GPU with the per-GPU batch.  set_sync_bn(True) turns the batch-norm
+# layers that the reference synchronises (the ISLA norms and the affine norms of the mask heads / RGB head) into
+# global-batch norms: one all-reduce of 2*C doubles in the forward and one in the backward of each layer.
+_SYNC_BN = {"group": None, "world": 1}
+
+
+def set_sync_bn(enabled, group=None):
+    import torch.distributed as dist
+    if enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        _SYNC_BN["group"], _SYNC_BN["world"] = (group if group is not None else dist.group.WORLD), dist.get_world_size(group)
+    else:
+        _SYNC_BN["group"], _SYNC_BN["world"] = None, 1
+
+
+def _sync_sum(t: torch.Tensor):
+    if _SYNC_BN["world"] > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_SYNC_BN["group"])
+
+
 def bn_batch_stats(x: torch.Tensor, running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor],
                    eps: float, momentum: float) -> torch.Tensor:
-    """x (..., C) fp32 -> mean_invstd (2, C); updates the running statistics in place (train mode)."""
+    """x (..., C) fp32 -> mean_invstd (2, C); updates the running statistics in place (train mode).  With
+    set_sync_bn the sums are all-reduced first, so mean / variance are those of the global batch."""
     _chk(x)
     c = x.shape[-1]
     pixels = x.numel() // c
     sums = torch.empty((c, 2), dtype=torch.float64, device=x.device)
     call("l2i_bn_stats", x, pixels, c, sums)
+    _sync_sum(sums)
     mi = torch.empty((2, c), dtype=torch.float32, device=x.device)
-    call("l2i_bn_finalize", sums, float(pixels), c, float(eps), float(momentum), running_mean, running_var, mi)
+    call("l2i_bn_finalize", sums, float(pixels * _SYNC_BN["world"]), c, float(eps), float(momentum), running_mean,
+         running_var, mi)
     return mi
 
 
@@ -238,8 +263,19 @@ def isla_bwd(x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, dout, relu: boo
     dmask = torch.empty_like(mask_pm) if o else None
     dgamma = torch.empty_like(gamma) if o else None
     dbeta = torch.empty_like(beta) if o else None
-    call("l2i_isla_bwd", x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, dout, b, h, w, c, o, int(relu), int(up2),
-         int(train), gbuf, dmask, dgamma, dbeta, csum, dx)
+    args = (x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, dout, b, h, w, c, o, int(relu), int(up2), int(train),
+            gbuf, dmask, dgamma, dbeta, csum, dx)
+    if train and _SYNC_BN["world"] > 1:
+        # global-batch norm: reduce (sum d xhat, sum d xhat * xhat) over the ranks between the two phases.  For the
+        # affine form (O == 0) csum also carries the LOCAL (d bias, d weight); keep a copy for the caller.
+        call("l2i_isla_bwd", *args, 1, 0.0)
+        local = csum.clone() if o == 0 else None
+        _sync_sum(csum)
+        call("l2i_isla_bwd", *args, 2, float(b * h * w * _SYNC_BN["world"]))
+        if local is not None:
+            csum = local
+    else:
+        call("l2i_isla_bwd", *args, 0, 0.0)
     return dx, dmask, dgamma, dbeta, csum
 
 
