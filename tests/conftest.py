@@ -11,6 +11,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# libl2i.so is a build artefact (git-ignored): make sure it exists and is current before any test imports it.
+# nvcc cross-compiles sm_100a without a GPU; a no-op when the library is newer than its sources.
+try:
+    from layout2img_b200 import build as _l2i_build
+    _l2i_build.build()
+except Exception as _e:          # the ABI tests will then fail with the loader's own message
+    sys.stderr.write(f"conftest: building libl2i.so failed: {_e}\n")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
