@@ -824,11 +824,19 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t stream) {
   const int co_tiles = swap ? 1 : (a.cout + 127) / 128;
   const int tap_groups = p.tap_pairs ? (a.taps + 1) / 2 : a.taps;
   const int base_ctas = co_tiles * p.cin_tiles * tap_groups;
-  // split-K over pixel blocks until the grid covers ~2 waves of 148 SMs (>= 8 blocks per split)
-  int splits = (2 * 148 + base_ctas - 1) / base_ctas;
+  // split-K over pixel blocks: choose the split count that minimises (waves of 148 CTAs) x (K iterations per CTA +
+  // a fixed per-CTA cost of ~12 iterations for prologue, pipeline fill and the atomic epilogue), >= 8 blocks per split
   int max_splits = (p.pix_blocks + 7) / 8;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  if (max_splits < 1) max_splits = 1;
+  int cap = (4 * 148 + base_ctas - 1) / base_ctas;
+  if (cap > max_splits) cap = max_splits;
+  int splits = 1;
+  long long best = -1;
+  for (int sp = 1; sp <= cap; ++sp) {
+    const long long waves = (1LL * base_ctas * sp + 147) / 148;
+    const long long cost = waves * ((p.pix_blocks + sp - 1) / sp + 12);
+    if (best < 0 || cost < best) { best = cost; splits = sp; }
+  }
   p.blocks_per_split = (p.pix_blocks + splits - 1) / splits;
   splits = (p.pix_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
   p.atomic = splits > 1;
