@@ -186,10 +186,16 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           const int ds = (p.taps == 9) ? (tap % 3 - 1) : 0;
           uint8_t* st = smem + s * Cfg::kStageBytes;
           mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-          tma_load_4d(st, &tm_a_hi, &full_bar[s], kc * kBK, w0 + ds, h0 + dr, n0);
-          tma_load_4d(st + kTileBytes, &tm_a_lo, &full_bar[s], kc * kBK, w0 + ds, h0 + dr, n0);
-          tma_load_2d(st + 2 * kTileBytes, &tm_b_hi, &full_bar[s], tap * p.cin_pad + kc * kBK, co0);
-          tma_load_2d(st + 2 * kTileBytes + Cfg::kBBytes, &tm_b_lo, &full_bar[s], tap * p.cin_pad + kc * kBK, co0);
+          if (p.pair_maps) {
+            // (hi, lo) are the two slices of one buffer: one 5-D / 3-D box fetches both halves of an operand tile
+            tma_load_5d(st, &tm_a_hi, &full_bar[s], kc * kBK, w0 + ds, h0 + dr, n0, 0);
+            tma_load_3d(st + 2 * kTileBytes, &tm_b_hi, &full_bar[s], tap * p.cin_pad + kc * kBK, co0, 0);
+          } else {
+            tma_load_4d(st, &tm_a_hi, &full_bar[s], kc * kBK, w0 + ds, h0 + dr, n0);
+            tma_load_4d(st + kTileBytes, &tm_a_lo, &full_bar[s], kc * kBK, w0 + ds, h0 + dr, n0);
+            tma_load_2d(st + 2 * kTileBytes, &tm_b_hi, &full_bar[s], tap * p.cin_pad + kc * kBK, co0);
+            tma_load_2d(st + 2 * kTileBytes + Cfg::kBBytes, &tm_b_lo, &full_bar[s], tap * p.cin_pad + kc * kBK, co0);
+          }
         }
       }
     }
@@ -676,6 +682,37 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int N, int H, int W, in
   return L2I_OK;
 }
 
+// (hi, lo) pair of NHWC maps as ONE 5-D map: dims (C, W, H, N, 2), the last stride = distance between the halves
+static int make_act_pair_map(CUtensorMap* m, const void* hi, long long pair_stride, int N, int H, int W, int Cpad, int bw,
+                             int bh, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return L2I_ERR_DRIVER; }
+  cuuint64_t dims[5] = {(cuuint64_t)Cpad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, 2};
+  cuuint64_t strides[4] = {(cuuint64_t)Cpad * 2, (cuuint64_t)W * Cpad * 2, (cuuint64_t)H * W * Cpad * 2, (cuuint64_t)pair_stride};
+  cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, 2};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(hi), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(act pair) failed: %d", (int)r); return L2I_ERR_DRIVER; }
+  return L2I_OK;
+}
+
+// (hi, lo) pair of weight maps as ONE 3-D map: dims (K, rows, 2)
+static int make_w_pair_map(CUtensorMap* m, const void* hi, long long pair_stride, int rows, int K, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return L2I_ERR_DRIVER; }
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)pair_stride};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 2};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(hi), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weight pair) failed: %d", (int)r); return L2I_ERR_DRIVER; }
+  return L2I_OK;
+}
+
 // weight map: [rows][K] bf16 K-major, box (64, box_rows)
 static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int K, int box_rows) {
   EncodeTiledFn enc = get_encode();
@@ -778,10 +815,24 @@ int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream) {
   int rc;
   // halo mode: the A box is the (16 + 2) x 16 pixel patch around the 8 x 16 output tile (x from w0 - 1)
   const int bw = halo ? 16 : p.TW, bh = halo ? 18 : p.TH;
-  if ((rc = make_act_map(&ta_hi, a.x_hi, a.N, a.H, a.W, a.cin_pad, bw, bh, p.TN))) return rc;
-  if ((rc = make_act_map(&ta_lo, a.x_lo, a.N, a.H, a.W, a.cin_pad, bw, bh, p.TN))) return rc;
-  if ((rc = make_w_map(&tb_hi, a.w_hi, a.cout, a.taps * a.cin_pad, BN))) return rc;
-  if ((rc = make_w_map(&tb_lo, a.w_lo, a.cout, a.taps * a.cin_pad, BN))) return rc;
+  // when both operands' halves are slices of one buffer each (they are, for every pair this library's callers
+  // build), one tensor map per operand covers (hi, lo) and a k-iteration is 2 TMA instructions instead of 4
+  static const int pair_enabled = env_int("L2I_CONV_PAIR_MAPS", 1);
+  const long long sx = reinterpret_cast<const char*>(a.x_lo) - reinterpret_cast<const char*>(a.x_hi);
+  const long long sw = reinterpret_cast<const char*>(a.w_lo) - reinterpret_cast<const char*>(a.w_hi);
+  const long long x_bytes = 2LL * a.N * a.H * a.W * a.cin_pad, w_bytes = 2LL * a.cout * a.taps * a.cin_pad;
+  p.pair_maps = (pair_enabled && !halo && sx >= x_bytes && sw >= w_bytes && (sx % 16) == 0 && (sw % 16) == 0 &&
+                 sx < (1LL << 40) && sw < (1LL << 40)) ? 1 : 0;
+  if (p.pair_maps) {
+    if ((rc = make_act_pair_map(&ta_hi, a.x_hi, sx, a.N, a.H, a.W, a.cin_pad, bw, bh, p.TN))) return rc;
+    if ((rc = make_w_pair_map(&tb_hi, a.w_hi, sw, a.cout, a.taps * a.cin_pad, BN))) return rc;
+    ta_lo = ta_hi; tb_lo = tb_hi;
+  } else {
+    if ((rc = make_act_map(&ta_hi, a.x_hi, a.N, a.H, a.W, a.cin_pad, bw, bh, p.TN))) return rc;
+    if ((rc = make_act_map(&ta_lo, a.x_lo, a.N, a.H, a.W, a.cin_pad, bw, bh, p.TN))) return rc;
+    if ((rc = make_w_map(&tb_hi, a.w_hi, a.cout, a.taps * a.cin_pad, BN))) return rc;
+    if ((rc = make_w_map(&tb_lo, a.w_lo, a.cout, a.taps * a.cin_pad, BN))) return rc;
+  }
   const long long total = 1LL * p.m_tiles * p.n_tiles;
   const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
   if (halo) {
