@@ -15,10 +15,14 @@ backward, Adam; D(fake), g_loss (hinge + L1), backward, Adam -- on batch 64 per 
              losses are inside the timed region of every step
   roofline   dominant kernel (tcgen05 implicit-GEMM conv, fwd+dgrad launches): algorithmic
              2*M*N*K FLOPs / CUDA-event time of those launches, against MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle (oracle/l2i_oracle.py, a port of the reference's PyTorch path)
-             timed on this host's cores on a bounded sample of the same workload
-`--impl reference` times that CPU path alone (the reference is pure Python/PyTorch and cannot be
-shipped to the GPU box; the oracle is its pinned restatement).
+  cpu_baseline  the reference's own CPU path -- the UNMODIFIED reference modules staged in the git-ignored
+             baseline/_ref/ by oracle/make_ref.py (kind "reference"), or the oracle port when they are not
+             staged (kind "port") -- timed on this host's cores on a bounded sample of the same workload
+  library_baseline  the same unmodified reference modules under PyTorch eager (cuDNN / cuBLAS / ATen) on the
+             same B200 at the same batch 64, with cudnn/matmul TF32 on ("tf32") and off ("fp32"): the GPU
+             library bar.  Measured in a subprocess (`--impl reference-gpu`).
+`--impl reference` times the CPU path alone; each step is a bounded sample (a smaller batch, stated in the
+line) of the batch-64 workload.
 """
 from __future__ import annotations
 
@@ -50,43 +54,144 @@ def peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's PyTorch path on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(batch: int, steps: int, warmup: int, seed: int = 0):
-    """images/sec of one oracle G+D iteration at (batch, 8 objects) with all host threads."""
+def cpu_reference_rate(batch: int, steps: int, warmup: int, seed: int = 0):
+    """images/sec of one G+D iteration on the host cores at (batch, 8 objects): the unmodified reference modules from
+    baseline/_ref when staged (kind "reference"), else the oracle port (kind "port")."""
     from layout2img_b200.synth import make_state, synthetic_layout
-    from oracle import l2i_oracle as O
     schema = lambda k: {n: tuple(s) for n, s in json.load(open(os.path.join(ROOT, "tests", "golden", f"schema_{k}.json"))).items()}
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    PG, PD = make_state(schema("G"), 1), make_state(schema("D"), 2)
-    O.set_requires_grad(PG); O.set_requires_grad(PD)
-    g_opt, d_opt = O.make_adam(PG, 1e-4), O.make_adam(PD, 1e-4)
     data = synthetic_layout(batch, NUM_OBJ, NUM_CLASSES, seed=seed)
+    from oracle import ref_harness as R
+    if R.available():
+        kind = "reference"
+        Gc, Dc = R.import_reference(cpu=True)
+        G, D = Gc(num_classes=NUM_CLASSES, output_dim=3), Dc(num_classes=NUM_CLASSES)
+        G.load_state_dict(make_state(schema("G"), 1)); D.load_state_dict(make_state(schema("D"), 2))
+        G.train(); D.train()
+        g_opt, d_opt = R.make_optimizers(G, D)
+        step = lambda: R.train_step(G, D, g_opt, d_opt, data["real"], data["label"], data["bbox"], data["z"], data["z_im"])
+    else:
+        kind = "port"
+        from oracle import l2i_oracle as O
+        PG, PD = make_state(schema("G"), 1), make_state(schema("D"), 2)
+        O.set_requires_grad(PG); O.set_requires_grad(PD)
+        g_opt, d_opt = O.make_adam(PG, 1e-4), O.make_adam(PD, 1e-4)
+        step = lambda: O.train_step(PG, PD, g_opt, d_opt, data["real"], data["label"], data["bbox"], data["z"], data["z_im"])
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.train_step(PG, PD, g_opt, d_opt, data["real"], data["label"], data["bbox"], data["z"], data["z_im"])
+        step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    return batch * len(times) / total, cores, total / len(times)
+    return batch * len(times) / total, cores, total / len(times), kind
 
 
 def run_reference(args, rank: int):
+    """The reference's own CPU implementation on the box's host cores.  A step = one G+D iteration on a bounded sample
+    of the batch-64 workload (batch 8, or 16 for short runs), so that `--steps K --warmup W` ends within minutes."""
     if rank != 0:
         return
-    batch = 4 if args.steps + args.warmup <= 16 else 2
-    rate, cores, s_per_step = cpu_oracle_rate(batch, args.steps, args.warmup)
-    sample = f"{args.steps} oracle iterations at batch {batch}, 8 objects, 128x128 (of the batch-64 workload)"
+    batch = args.ref_batch or (16 if args.steps + args.warmup <= 8 else 8)
+    rate, cores, s_per_step, kind = cpu_reference_rate(batch, args.steps, args.warmup)
+    what = "unmodified reference modules (baseline/_ref)" if kind == "reference" else "oracle port of the reference"
+    sample = (f"{args.steps} timed G+D iterations of the {what} at batch {batch}, 8 objects, 128x128, {cores} host threads "
+              f"(a bounded sample of the batch-64 workload: {s_per_step:.1f} s per step)")
+    cfg = workload_config(args.gpus)
+    cfg.update(per_gpu_batch=batch, global_batch=batch, workload_batch=64, parallelism="host cores",
+               batch_norm="single process", l2="n/a (CPU)")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/sec", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": cfg,
+        "same_config": False, "same_config_note": f"CPU sample runs batch {batch} per step, the GPU arm batch 64; "
+                                                  "images/sec is the common unit",
+        "cpu_baseline": {"value": rate, "unit": "images/sec", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def run_reference_gpu(args):
+    """The GPU library bar: the unmodified reference modules under PyTorch eager on cuda:0 at the metric's batch, TF32 on
+    and off.  Prints one JSON line {"tf32": {...}, "fp32": {...}}; run as a subprocess of the main arm."""
+    from layout2img_b200.synth import make_state, schema_of, synthetic_layout
+    from oracle import ref_harness as R
+    if not R.available():
+        print(json.dumps({"unavailable": "baseline/_ref not staged"}), flush=True)
+        return
+    Gc, Dc = R.import_reference(cpu=False)
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    out = {"batch": args.batch, "torch": torch.__version__, "cudnn": torch.backends.cudnn.version(),
+           "how": "unmodified reference nn.Modules (baseline/_ref), PyTorch eager, same step (train_context_app_v2.py:155-189 "
+                  "without VGG), same synthetic batch, CUDA events over `steps` iterations after `warmup`"}
+    data = synthetic_layout(args.batch, NUM_OBJ, NUM_CLASSES, seed=0)
+    for name, tf32 in (("tf32", True), ("fp32", False)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.benchmark = True
+        G, D = Gc(num_classes=NUM_CLASSES, output_dim=3), Dc(num_classes=NUM_CLASSES)
+        G.load_state_dict(make_state(schema_of(G), 1)); D.load_state_dict(make_state(schema_of(D), 2))
+        G.to(dev).train(); D.to(dev).train()
+        g_opt, d_opt = R.make_optimizers(G, D)
+        d = {k: v.to(dev) for k, v in data.items()}
+        step = lambda: R.train_step(G, D, g_opt, d_opt, d["real"], d["label"], data["bbox"], d["z"], d["z_im"])
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out[name] = {"value": args.batch / (ms / 1e3), "unit": "images/sec", "ms_per_step": ms, "steps": args.steps,
+                     "warmup": args.warmup, "allow_tf32": tf32,
+                     "accuracy_class": "TF32 convolutions/GEMMs (10-bit mantissa products; fails the north-star tolerance on "
+                                       "G, SURVEY.md section 0.4)" if tf32 else "fp32 (the north-star accuracy class; ours matches it)",
+                     "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        del G, D, g_opt, d_opt, d, step
+        torch.cuda.empty_cache()
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline_subprocess():
+    """cpu_baseline of the main line: `--impl reference` for 2 timed steps in a subprocess (same isolation reason)."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1", "--ref-batch", "8"]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    return {"unavailable": "no JSON from the reference subprocess"}
+
+
+def library_baseline(batch: int):
+    """Run `--impl reference-gpu` in a subprocess (the reference's package is called `model`; it must not meet this
+    repository's own modules in one interpreter) and return its JSON."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-gpu", "--batch", str(batch), "--steps", "5", "--warmup", "3"]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": "no JSON from the reference-gpu subprocess", "stderr_tail": r.stderr[-400:]}
+    except Exception as e:       # the bench line must still be printed
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def workload_config(n):
@@ -224,7 +329,7 @@ def run_ours(args, rank, local_rank, world):
     from layout2img_b200.model.rcnn_discriminator_app import CombineDiscriminator128_app
     from layout2img_b200.model.resnet_generator_app_v2 import ResnetGenerator128_context
     from layout2img_b200.synth import make_state, schema_of, synthetic_layout
-    from layout2img_b200.train import GradAllReducer, make_optimizers, train_step
+    from layout2img_b200.train import GradBuckets, make_optimizers, train_step
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
@@ -245,8 +350,9 @@ def run_ours(args, rank, local_rank, world):
     D.load_state_dict(make_state(schema_of(D), 2))
     G.to(dev).train(); D.to(dev).train()
     g_opt, d_opt = make_optimizers(G, D)
-    sync_g = GradAllReducer(G) if world > 1 else None
-    sync_d = GradAllReducer(D) if world > 1 else None
+    # zero-copy gradient buckets, all-reduced on a side stream while the backward pass is still running
+    sync_g = GradBuckets(G) if world > 1 else None
+    sync_d = GradBuckets(D) if world > 1 else None
 
     host = synthetic_layout(B, NUM_OBJ, NUM_CLASSES, seed=rank)
     host = {k: v.pin_memory() for k, v in host.items()}
@@ -354,9 +460,11 @@ def run_ours(args, rank, local_rank, world):
         breakdown["_instrumented_step_ms"] = round(step_ms, 3)
         cpu = None
         if world == 1 and not args.no_cpu:
-            rate, cores, s_per = cpu_oracle_rate(4, 2, 1)
-            cpu = {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
-                   "sample": f"2 timed oracle iterations (after 1 warm-up) at batch 4, 8 objects, 128x128; {s_per:.1f} s each"}
+            cpu = cpu_baseline_subprocess()
+        lib = None
+        if world == 1 and not args.no_library:
+            torch.cuda.empty_cache()
+            lib = library_baseline(B)
         d2h = 8
         line = {
             "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
@@ -365,10 +473,12 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu,
+            "library_baseline": lib,
             "kernel_ms_per_step": breakdown,
         }
         if world > 1:
             line.pop("cpu_baseline")
+            line.pop("library_baseline")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -381,7 +491,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--ref-batch", type=int, default=0, help="--impl reference: images per CPU step (default 8, 16 for short runs)")
+    ap.add_argument("--no-library", action="store_true", help="skip the library_baseline leg (reference modules, PyTorch eager, same GPU)")
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (the metric is quoted at 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--shapes-file", default=None, help="write the per-shape convolution timing table here")
@@ -395,6 +507,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.impl == "reference-gpu":
+        run_reference_gpu(args)
         return
     if world != args.gpus:
         if args.gpus > 1 and world == 1:

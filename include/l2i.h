@@ -186,11 +186,13 @@ int l2i_sn_weight_grad(const float* G, const float* W, const float* u, const flo
 
 /* ---- optimizer (reference train_context_app_v2.py:113-127,174,189: torch.optim.Adam(betas=(0, 0.999)),
  *      one parameter group per tensor).  One launch updates every tensor of a network.
- *      tensors: device array of { float* p; const float* g; float* m; float* v; int64 n; float lr; int pad; }
- *      (48 bytes each); chunks: device array of n_chunks (tensor index, chunk index) int pairs, each
- *      covering chunk_elems (multiple of 4) consecutive elements.  Arithmetic = torch's Adam step. ---- */
+ *      tensors: device array of { float* p; const float* g; float* m; float* v; int64 n; float step_size;
+ *      float bc2_sqrt; } (48 bytes each) with step_size = lr / (1 - beta1^step), bc2_sqrt = sqrt(1 - beta2^step) for
+ *      the tensor's OWN step count (torch keeps one per parameter) and n = 0 for a tensor without a gradient
+ *      (skipped); chunks: device array of n_chunks (tensor index, chunk index) int pairs, each covering
+ *      chunk_elems (multiple of 4) consecutive elements.  Arithmetic = torch's Adam step. ---- */
 int l2i_adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, double beta1, double beta2,
-                  double eps, double bias_correction1, double bias_correction2_sqrt, void* stream);
+                  double eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -187,9 +187,8 @@ int l2i_sn_weight_grad(const float* G, const float* W, const float* u, const flo
   return sn_weight_grad(G, W, u, v, sigma, R, cin, taps, dW, scratch, ST(stream));
 }
 int l2i_adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, double beta1, double beta2,
-                  double eps, double bias_correction1, double bias_correction2_sqrt, void* stream) {
-  return adam_step(tensors, chunks, n_chunks, chunk_elems, beta1, beta2, eps, bias_correction1, bias_correction2_sqrt,
-                   ST(stream));
+                  double eps, void* stream) {
+  return adam_step(tensors, chunks, n_chunks, chunk_elems, beta1, beta2, eps, ST(stream));
 }
 
 }  // extern "C"

@@ -19,6 +19,23 @@ namespace l2i {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// Per-device one-time setup (function attributes belong to a device's context: a process that drives several GPUs --
+// the reference's own DataParallel mode -- must configure each kernel once per device, not once per process).
+// One bit per device ordinal; safe to race (the guarded calls are idempotent).
+struct DeviceOnce {
+  unsigned long long bits = 0;
+  bool need() const {
+    int d = 0;
+    cudaGetDevice(&d);
+    return ((__atomic_load_n(&bits, __ATOMIC_ACQUIRE) >> (d & 63)) & 1ull) == 0;
+  }
+  void done() {
+    int d = 0;
+    cudaGetDevice(&d);
+    __atomic_fetch_or(&bits, 1ull << (d & 63), __ATOMIC_RELEASE);
+  }
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -234,8 +234,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const uint32_t b_lo = b_hi + Cfg::kBBytes;
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) {
-                  const uint64_t dah = umma_desc_sw128(a_hi + a_off + k * 32, 16, 2048) | p.halo_desc_or[tap % 3];
-                  const uint64_t dal = umma_desc_sw128(a_lo + a_off + k * 32, 16, 2048) | p.halo_desc_or[tap % 3];
+                  const uint64_t dah = umma_desc_sw128(a_hi + a_off + k * 32, 16, 2048);
+                  const uint64_t dal = umma_desc_sw128(a_lo + a_off + k * 32, 16, 2048);
                   const uint64_t dbh = umma_desc_sw128(b_hi + k * 32, 16, 1024);
                   const uint64_t dbl = umma_desc_sw128(b_lo + k * 32, 16, 1024);
                   umma_bf16(d_cross, dal, dbh, idesc, fresh);
@@ -744,11 +744,14 @@ static int pick_tile(int H, int W, int pixels, int* tw, int* th, int* tn) {
 }
 
 static int sm_count() {
-  static int n = 0;
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = cache[dev & 63];
   if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n = v;
   }
   return n;
 }
@@ -756,12 +759,12 @@ static int sm_count() {
 template <int BN, bool HALO>
 static int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                       const CUtensorMap& b_lo, const ConvFwdParams& p, int grid, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel<BN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          FwdCfg<BN, HALO>::kSmem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_fwd): %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
-    configured = true;
+    configured.done();
   }
   conv_fwd_kernel<BN, HALO><<<grid, kFwdThreads, FwdCfg<BN, HALO>::kSmem, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
   return check_launch(HALO ? "conv_fwd_kernel<halo>" : "conv_fwd_kernel");
@@ -770,9 +773,8 @@ static int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
 // L2I_CONV_HALO=1 enables the halo-patch variant (off by default: measured on B200 it cuts L2 -> SM traffic per
 // tile from 432 KB to 221 KB at Cin = Cout = 64 but is 5-15 % SLOWER than the plain ring -- those layers are paced
 // by shared-memory bandwidth (TMA writes + UMMA operand reads) and the epilogue, not by L2).
-// L2I_CONV_HALO_BASEOFF=1 sets the descriptor's matrix-base-offset field to the patch row phase instead of 0:
-// that is WRONG on sm_100a (the 128B swizzle is a function of the shared-memory address), kept as the switch
-// that established it.
+// (The descriptor's matrix-base-offset field stays 0 for the shifted windows: on sm_100a the 128B swizzle is a
+// function of the shared-memory address.)
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -791,7 +793,6 @@ int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream) {
   p.N = a.N; p.H = a.H; p.W = a.W; p.cin_pad = a.cin_pad; p.cout = a.cout; p.taps = a.taps;
   if (pick_tile(a.H, a.W, 128, &p.TW, &p.TH, &p.TN) != L2I_OK) { set_error("conv: H=%d W=%d must be powers of two", a.H, a.W); return L2I_ERR_UNSUPPORTED; }
   static const int halo_enabled = env_int("L2I_CONV_HALO", 0);
-  static const int halo_baseoff = env_int("L2I_CONV_HALO_BASEOFF", 0);
   const bool halo = halo_enabled && a.taps == 9 && a.H >= 16 && a.W >= 8 && a.cin_pad >= 64;
   if (halo) { p.TW = 8; p.TH = 16; p.TN = 1; }
   p.tiles_w = a.W / p.TW; p.tiles_h = a.H / p.TH;
@@ -803,7 +804,6 @@ int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream) {
     p.n_pass = (k_iters + max_len - 1) / max_len;
     p.pass_len = (k_iters + p.n_pass - 1) / p.n_pass;
   }
-  for (int j = 0; j < 3; ++j) p.halo_desc_or[j] = halo_baseoff ? (static_cast<unsigned long long>(j & 7) << 49) : 0ull;
   p.bias = a.bias; p.residual = a.residual; p.res_shift = a.res_shift; p.res_scale = a.res_scale; p.out = a.out;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(a.out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(a.out_lo);
   p.cout_pad = a.cout_pad; p.relu_split = a.relu_split; p.out_scale = a.out_scale;
@@ -846,11 +846,11 @@ int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream) {
 template <int BN, bool SWAP>
 static int launch_wgrad(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                         const CUtensorMap& b_lo, const ConvWgradParams& p, dim3 grid, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<BN, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<BN>::kSmem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv_wgrad): %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
-    configured = true;
+    configured.done();
   }
   conv_wgrad_kernel<BN, SWAP><<<grid, kThreads, WgCfg<BN>::kSmem, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
   return check_launch(SWAP ? "conv_wgrad_kernel<swap>" : "conv_wgrad_kernel");

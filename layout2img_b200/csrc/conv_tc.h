@@ -15,7 +15,6 @@ struct ConvFwdParams {          // device-side view
   int pool;                     // 0 none, 1 = 2x2 average, 2 = 2x2 sum of the conv output (stored at H/2 x W/2)
   float res_scale;
   int pair_maps;                // 1: tm_a_hi / tm_b_hi are (hi, lo) pair maps (one TMA instruction per operand tile)
-  unsigned long long halo_desc_or[3];   // OR-ed into the halo-mode A descriptors, indexed by the tap's column (experiment switch)
   const float* bias;            // [cout] or null
   const float* residual;        // [N,H,W,cout] (res_shift=0) or [N,H/2,W/2,cout] nearest-x2 (res_shift=1), or null
   int res_shift;

@@ -273,10 +273,10 @@ int isla_fwd(const float* x, const float* mean_invstd, const float* mask, const 
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   const size_t smem = sizeof(float) * 2 * O * kIslaCc;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     cudaFuncSetAttribute(isla_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 2 * kIslaCc * 4);
-    configured = true;
+    configured.done();
   }
   dim3 grid(static_cast<int>(bx), chunks, B);
   isla_fwd_kernel<<<grid, 256, smem, stream>>>(p);

@@ -86,11 +86,11 @@ struct AdamTensor {       // one entry of the device-resident tensor table (48 b
   const float* g;
   float* m;
   float* v;
-  long long n;
-  float lr;
-  int pad_;
+  long long n;            // 0: no gradient this step, the tensor is skipped
+  float step_size;        // lr / (1 - beta1^step), step = this tensor's own update count
+  float bc2_sqrt;         // sqrt(1 - beta2^step)
 };
 int adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, double beta1, double beta2, double eps,
-              double bc1, double bc2_sqrt, cudaStream_t stream);
+              cudaStream_t stream);
 
 }  // namespace l2i

@@ -16,26 +16,27 @@ __device__ __forceinline__ float torch_lerp(float a, float b, float w) {
   return (fabsf(w) < 0.5f) ? a + w * d : b - d * (1.0f - w);
 }
 
-struct AdamConsts { float beta2, omb1, omb2, eps, bc2_sqrt; };   // omb = 1 - beta, rounded from double like torch's scalars
+struct AdamConsts { float beta2, omb1, omb2, eps; };   // omb = 1 - beta, rounded from double like torch's scalars
 
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float lr_over_bc1, const AdamConsts& c) {
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float lr_over_bc1, float bc2_sqrt,
+                                         const AdamConsts& c) {
   m = torch_lerp(m, g, c.omb1);
   v = __fmul_rn(v, c.beta2);
   v = __fadd_rn(v, __fmul_rn(__fmul_rn(c.omb2, g), g));            // addcmul_: v + value * g * g
-  const float eps = c.eps, bc2_sqrt = c.bc2_sqrt;
+  const float eps = c.eps;
   const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), eps);
   p = __fadd_rn(p, __fmul_rn(-lr_over_bc1, __fdiv_rn(m, denom)));  // addcdiv_: p + value * (m / denom)
 }
 
 __global__ void __launch_bounds__(256)
-adam_kernel(const AdamTensor* __restrict__ tensors, const int2* __restrict__ chunks, int chunk_elems, AdamConsts c,
-            float bc1) {
+adam_kernel(const AdamTensor* __restrict__ tensors, const int2* __restrict__ chunks, int chunk_elems, AdamConsts c) {
   const int2 ck = chunks[blockIdx.x];
   const AdamTensor t = tensors[ck.x];
   const long long begin = 1LL * ck.y * chunk_elems;
   long long end = begin + chunk_elems;
   if (end > t.n) end = t.n;
-  const float lr1 = t.lr / bc1;
+  if (t.n <= 0) return;                              // parameter without a gradient this step: skipped, as torch does
+  const float lr1 = t.step_size, b2 = t.bc2_sqrt;   // lr / (1 - beta1^step) and sqrt(1 - beta2^step) of THIS tensor's step
   float* __restrict__ p = t.p + begin;
   const float* __restrict__ g = t.g + begin;
   float* __restrict__ m = t.m + begin;
@@ -50,22 +51,22 @@ adam_kernel(const AdamTensor* __restrict__ tensors, const int2* __restrict__ chu
       const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
       float4 mm = reinterpret_cast<float4*>(m)[i];
       float4 vv = reinterpret_cast<float4*>(v)[i];
-      adam_one(pp.x, gg.x, mm.x, vv.x, lr1, c);
-      adam_one(pp.y, gg.y, mm.y, vv.y, lr1, c);
-      adam_one(pp.z, gg.z, mm.z, vv.z, lr1, c);
-      adam_one(pp.w, gg.w, mm.w, vv.w, lr1, c);
+      adam_one(pp.x, gg.x, mm.x, vv.x, lr1, b2, c);
+      adam_one(pp.y, gg.y, mm.y, vv.y, lr1, b2, c);
+      adam_one(pp.z, gg.z, mm.z, vv.z, lr1, b2, c);
+      adam_one(pp.w, gg.w, mm.w, vv.w, lr1, b2, c);
       reinterpret_cast<float4*>(p)[i] = pp;
       reinterpret_cast<float4*>(m)[i] = mm;
       reinterpret_cast<float4*>(v)[i] = vv;
     }
-    for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) adam_one(p[i], g[i], m[i], v[i], lr1, c);
+    for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) adam_one(p[i], g[i], m[i], v[i], lr1, b2, c);
   } else {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) adam_one(p[i], g[i], m[i], v[i], lr1, c);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) adam_one(p[i], g[i], m[i], v[i], lr1, b2, c);
   }
 }
 
 int adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, double beta1, double beta2, double eps,
-              double bc1, double bc2_sqrt, cudaStream_t stream) {
+              cudaStream_t stream) {
   if (!tensors || !chunks || n_chunks <= 0 || chunk_elems <= 0 || (chunk_elems & 3)) {
     set_error("adam_step: bad arguments (n_chunks=%d chunk_elems=%d)", n_chunks, chunk_elems);
     return L2I_ERR_BAD_ARG;
@@ -73,9 +74,7 @@ int adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_el
   adam_kernel<<<n_chunks, 256, 0, stream>>>(reinterpret_cast<const AdamTensor*>(tensors),
                                             reinterpret_cast<const int2*>(chunks), chunk_elems,
                                             AdamConsts{static_cast<float>(beta2), static_cast<float>(1.0 - beta1),
-                                                       static_cast<float>(1.0 - beta2), static_cast<float>(eps),
-                                                       static_cast<float>(bc2_sqrt)},
-                                            static_cast<float>(bc1));
+                                                       static_cast<float>(1.0 - beta2), static_cast<float>(eps)});
   return check_launch("adam_kernel");
 }
 

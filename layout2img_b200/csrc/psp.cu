@@ -228,10 +228,10 @@ int psp_concat_bwd(const float* dcat, int B, int H, int W, int CP, int cstride, 
   if (e != cudaSuccess) { set_error("psp_concat_bwd: memset: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
   const int threads = 416;
   const size_t smem = sizeof(float) * 36 * threads;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     cudaFuncSetAttribute(psp_concat_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    configured = true;
+    configured.done();
   }
   const int rows = 4;
   psp_concat_bwd_kernel<<<dim3((H + rows - 1) / rows, B), threads, smem, stream>>>(dcat, H, W, CP, cstride, rows, dpriors);

@@ -110,10 +110,10 @@ int sn_sigma(const float* W, int R, int Cc, float* u, float* v, int training, fl
   float* t = work;
   float* s = work + Cc;
   const size_t smem_v = sizeof(float) * (Cc + 32);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     cudaFuncSetAttribute(sn_w_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40032 * 4);
-    configured = true;
+    configured.done();
   }
   if (training) {
     cudaError_t e = cudaMemsetAsync(t, 0, sizeof(float) * Cc, stream);

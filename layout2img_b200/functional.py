@@ -68,12 +68,6 @@ def conv2d(x, weight, bias=None, residual=None, relu_in=False, up2_in=False, res
     return ConvFn.apply(x, weight, bias, residual, relu_in, up2_in, res_up2, sn)
 
 
-def conv2d_module(conv, x, residual=None, relu_in=False, up2_in=False, res_up2=False):
-    """Convolution through a (possibly spectrally normalised) conv module without firing its library hook."""
-    w, b, sn = _sn_of(conv)
-    return ConvFn.apply(x, w, b, residual, relu_in, up2_in, res_up2, sn)
-
-
 class DBlockFn(torch.autograd.Function):
     """A whole discriminator residual block (reference rcnn_discriminator_app.py:294-344) as one autograd node:
 

@@ -7,7 +7,6 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import functional as L
 
@@ -18,13 +17,6 @@ def to_nhwc(x: torch.Tensor) -> torch.Tensor:
 
 def to_nchw_view(x: torch.Tensor) -> torch.Tensor:
     return x.permute(0, 3, 1, 2)
-
-
-def fire_param_hooks(module: nn.Module) -> None:
-    """Run the module's forward-pre hooks (nn.utils.spectral_norm's power iteration + W/sigma)
-    without calling its forward -- for modules whose weight is consumed by a fused kernel."""
-    for hook in module._forward_pre_hooks.values():
-        hook(module, None)
 
 
 class Conv2d(nn.Conv2d):
@@ -66,10 +58,3 @@ def conv2d(in_feat, out_feat, kernel_size=3, stride=1, pad=1, spectral_norm=True
     if spectral_norm:
         return nn.utils.spectral_norm(conv, eps=1e-4)
     return conv
-
-
-def avg_pool2(x: torch.Tensor) -> torch.Tensor:
-    if x.shape[-1] % 4 == 0:
-        return L.avgpool2(x)
-    # 3-channel images only (OptimizedBlock shortcut): torch's pooling on the NCHW view
-    return to_nhwc(F.avg_pool2d(to_nchw_view(x), 2))

@@ -1,11 +1,11 @@
 """The G+D training iteration the hot path serves, restated from the reference's
-train_context_app_v2.py:148-189 (VGG perceptual term excluded: its weights need network access),
-plus the one-process-per-GPU data-parallel wrapper (batch shard + one gradient all-reduce per
-network per step).
+train_context_app_v2.py:148-189 (VGG perceptual term optional: its weights need network access),
+plus the one-process-per-GPU data-parallel plumbing (batch shard + bucketed, overlapped gradient
+all-reduce per network per step).
 """
 from __future__ import annotations
 
-from typing import Optional
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist
@@ -15,10 +15,12 @@ LAMB_OBJ, LAMB_IMG, LAMB_APP = 1.0, 0.1, 1.0       # train_context_app_v2.py:40-
 
 
 def make_optimizers(netG, netD, g_lr: float = 1e-4, d_lr: float = 1e-4):
-    """Adam(betas=(0, 0.999)) with one param group per tensor (train_context_app_v2.py:113-127), executed as
-    one multi-tensor kernel per network (optim.FusedAdam -> csrc/optim.cu)."""
+    """Adam(betas=(0, 0.999)) with one param group per tensor (train_context_app_v2.py:113-127; 'mapping' parameters
+    would get 0.1 x lr there -- the app_v2 generator's mapping is an empty nn.Sequential), executed as one multi-tensor
+    kernel per network (optim.FusedAdam -> csrc/optim.cu)."""
     from .optim import FusedAdam
-    g_opt = FusedAdam([{"params": [p], "lr": g_lr} for p in netG.parameters()], betas=(0.0, 0.999))
+    g_opt = FusedAdam([{"params": [p], "lr": g_lr * (0.1 if "mapping" in n else 1.0)} for n, p in netG.named_parameters()],
+                      betas=(0.0, 0.999))
     d_opt = FusedAdam([{"params": [p], "lr": d_lr} for p in netD.parameters()], betas=(0.0, 0.999))
     return g_opt, d_opt
 
@@ -40,77 +42,189 @@ class _frozen:
             p.requires_grad_(True)
 
 
-def d_loss_fn(real_out, fake_out):
+def _obj_mean(x, obj_scale):
+    """Mean over the objects of the GLOBAL batch.  Single process: x.mean().  Data parallel: the reference's DataParallel
+    gathers every replica's (K_r, 1) outputs and takes one mean over sum_r K_r rows (train_context_app_v2.py:159-161);
+    with per-rank losses followed by a gradient AVERAGE over W ranks that is sum_local * W / sum_r K_r
+    (obj_scale = W / sum_r K_r, a device scalar) -- identical to the plain mean when every rank has the same K."""
+    return x.mean() if obj_scale is None else x.sum() * obj_scale
+
+
+def d_loss_fn(real_out, fake_out, obj_scale=None):
     r_im, r_obj, r_app = real_out
     f_im, f_obj, f_app = fake_out
-    return (LAMB_OBJ * (F.relu(1.0 - r_obj).mean() + F.relu(1.0 + f_obj).mean())
+    return (LAMB_OBJ * (_obj_mean(F.relu(1.0 - r_obj), obj_scale) + _obj_mean(F.relu(1.0 + f_obj), obj_scale))
             + LAMB_IMG * (F.relu(1.0 - r_im).mean() + F.relu(1.0 + f_im).mean())
-            + LAMB_APP * (F.relu(1.0 - r_app).mean() + F.relu(1.0 + f_app).mean()))
+            + LAMB_APP * (_obj_mean(F.relu(1.0 - r_app), obj_scale) + _obj_mean(F.relu(1.0 + f_app), obj_scale)))
 
 
-def g_loss_fn(g_out, fake, real):
+def g_loss_fn(g_out, fake, real, obj_scale=None, feat_loss=None):
     g_im, g_obj, g_app = g_out
-    return (-g_obj.mean() * LAMB_OBJ - g_im.mean() * LAMB_IMG + (fake - real).abs().mean()
-            - LAMB_APP * g_app.mean())
+    loss = (-_obj_mean(g_obj, obj_scale) * LAMB_OBJ - g_im.mean() * LAMB_IMG + (fake - real).abs().mean()
+            - LAMB_APP * _obj_mean(g_app, obj_scale))
+    if feat_loss is not None:                            # train_context_app_v2.py:185-187 (VGGLoss, utils/util.py:49-94)
+        loss = loss + feat_loss(fake, real).mean()
+    return loss
 
 
-class GradAllReducer:
-    """Flat-bucket gradient all-reduce (mean) over the default process group: one NCCL collective per
-    network per step.  No-op on a single process."""
+def global_object_scale(label: torch.Tensor, group=None) -> Optional[torch.Tensor]:
+    """W / (number of label != 0 objects over all ranks) as a device scalar; None on a single process."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    k = (label != 0).sum().to(torch.float32).reshape(1)
+    dist.all_reduce(k, op=dist.ReduceOp.SUM, group=group)
+    return (float(dist.get_world_size(group)) / k.clamp_min(1.0)).squeeze(0)
 
-    def __init__(self, module: torch.nn.Module):
-        self.params = [p for p in module.parameters() if p.requires_grad]
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        self.flat: Optional[torch.Tensor] = None
 
-    def __call__(self):
-        if self.world == 1:
-            return
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-        n = sum(g.numel() for g in grads)
-        if self.flat is None or self.flat.numel() != n or self.flat.device != grads[0].device:
-            self.flat = torch.empty(n, dtype=torch.float32, device=grads[0].device)
-        off = 0
-        views = []
-        for g in grads:
-            v = self.flat[off:off + g.numel()]
-            v.copy_(g.reshape(-1))
-            views.append(v)
-            off += g.numel()
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        self.flat.div_(self.world)
-        for p, v in zip(self.params, views):
-            if p.grad is None:
-                p.grad = v.view_as(p).clone()
-            else:
-                p.grad.copy_(v.view_as(p))
+class GradBuckets:
+    """Data-parallel gradient plumbing of one network (one process per GPU, replicated weights):
+
+    * every parameter's .grad is a VIEW into one flat fp32 buffer -- autograd accumulates into it in place, the
+      optimizer kernel reads it in place; there are no flatten / unflatten copies;
+    * the flat buffer is cut into buckets in reverse parameter order (the order in which backward finishes them); a
+      bucket's all-reduce (average) is launched on a side stream from the post-accumulate hook of its last parameter,
+      so it overlaps the rest of the backward pass; `finish()` reduces whatever is left and makes the compute stream
+      wait for the side stream;
+    * parameters and buffers (spectral-norm u / v, batch-norm running statistics) are broadcast from rank 0 at
+      construction, so the replicas start identical even if their initialisation was not.
+
+    On a single process it only provides the flat gradient buffer (zero_grad = one memset).  Works with NCCL (streams,
+    ReduceOp.AVG) and with gloo on CPU tensors (synchronous; used by the CPU tests)."""
+
+    def __init__(self, module: torch.nn.Module, bucket_mb: float = 48.0, group=None, broadcast: bool = True):
+        self.params: List[torch.nn.Parameter] = [p for p in module.parameters() if p.requires_grad]
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        dev = self.params[0].device
+        self.cuda = dev.type == "cuda"
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4                  # 16-byte aligned slices
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, self.params)]
+        # buckets: contiguous ranges of the flat buffer, filled from the LAST parameter backwards
+        limit = int(bucket_mb * (1 << 20) / 4)
+        self.buckets, self.bucket_of = [], {}
+        end = total
+        members: List[int] = []
+        for i in range(len(self.params) - 1, -1, -1):
+            members.append(i)
+            if end - offs[i] >= limit or i == 0:
+                self.buckets.append({"range": (offs[i], end), "members": members, "pending": 0, "launched": False})
+                for m in members:
+                    self.bucket_of[m] = len(self.buckets) - 1
+                end, members = offs[i], []
+        self.comm_stream = torch.cuda.Stream(device=dev) if (self.cuda and self.world > 1) else None
+        self.works = []
+        self._attach()
+        if self.world > 1:
+            for i, p in enumerate(self.params):
+                p.register_post_accumulate_grad_hook(lambda _p, i=i: self._ready(i))
+            if broadcast:
+                with torch.no_grad():
+                    for t in list(module.parameters()) + list(module.buffers()):
+                        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self._reset()
+
+    def _attach(self):
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                p.grad = v
+
+    def _reset(self):
+        for b in self.buckets:
+            b["pending"], b["launched"] = len(b["members"]), False
+        self.works = []
+
+    def zero_grad(self):
+        """Replaces module.zero_grad(): one memset of the flat buffer; the .grad views stay attached."""
+        self.flat.zero_()
+        self._attach()
+
+    def _launch(self, b):
+        b["launched"] = True
+        s, e = b["range"]
+        chunk = self.flat[s:e]
+        if self.comm_stream is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+            chunk.div_(self.world)
+
+    def _ready(self, i: int):
+        b = self.buckets[self.bucket_of[i]]
+        b["pending"] -= 1
+        if b["pending"] == 0 and not b["launched"]:
+            self._launch(b)
+
+    def finish(self):
+        """Call after backward(): reduce the buckets whose hooks did not all fire (parameters without a gradient in this
+        pass count as zeros), then order the compute stream after the side stream."""
+        if self.world > 1:
+            for b in self.buckets:
+                if not b["launched"]:
+                    self._launch(b)
+            if self.comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self._reset()
+
+    __call__ = finish
+
+
+# Backwards-compatible name (round 1 exposed the post-backward flat all-reduce under it).
+GradAllReducer = GradBuckets
+
+
+def setup_data_parallel(netG, netD, sync_bn: bool = True, group=None):
+    """One call for a rank of a data-parallel job: gradient buckets for both networks (with the rank-0 broadcast) and,
+    by default, batch-norm statistics over the GLOBAL batch -- the reference's multi-GPU semantics
+    (SynchronizedBatchNorm2d under DataParallelWithCallback, sync_batchnorm/batchnorm.py:90-125).  sync_bn=False keeps
+    per-rank statistics (= the reference run with the per-GPU batch on one GPU)."""
+    from . import ops
+    ops.set_sync_bn(bool(sync_bn), group)
+    return GradBuckets(netG, group=group), GradBuckets(netD, group=group)
 
 
 def train_step(netG, netD, g_opt, d_opt, real, label, bbox, z, z_im=None, sync_g=None, sync_d=None,
-               record=None):
+               record=None, feat_loss=None):
     """One D step then one G step; returns (d_loss, g_loss, fake) as detached tensors (no host sync).
-    `record(tag)` is an optional callback used by the parity tests to snapshot gradients."""
+    sync_g / sync_d: GradBuckets of the two networks (data parallel, or single process for the flat gradient buffer).
+    `record(tag)` is an optional callback used by the parity tests to snapshot gradients; feat_loss an optional
+    perceptual loss module (VGGLoss)."""
     lab3 = label.unsqueeze(-1) if label.dim() == 2 else label
+    obj_scale = global_object_scale(label, sync_d.group if sync_d is not None else None) \
+        if (sync_d is not None and sync_d.world > 1) else None
     # ---- D step (:155-174)
-    netD.zero_grad()
+    if sync_d is not None:
+        sync_d.zero_grad()
+    else:
+        netD.zero_grad()
     real_out = netD(real, bbox, lab3)
     fake = netG(z, bbox, z_im, y=label.view(label.shape[0], -1))
     fake_out = netD(fake.detach(), bbox, lab3)
-    d_loss = d_loss_fn(real_out, fake_out)
+    d_loss = d_loss_fn(real_out, fake_out, obj_scale)
     d_loss.backward()
     if sync_d is not None:
-        sync_d()
+        sync_d.finish()
     if record is not None:
         record("d")
     d_opt.step()
     # ---- G step (:177-189); D's gradients produced here are discarded by the next zero_grad
-    netG.zero_grad()
+    if sync_g is not None:
+        sync_g.zero_grad()
+    else:
+        netG.zero_grad()
     with _frozen(netD):
         g_out = netD(fake, bbox, lab3)
-        g_loss = g_loss_fn(g_out, fake, real)
+        g_loss = g_loss_fn(g_out, fake, real, obj_scale, feat_loss)
         g_loss.backward()
     if sync_g is not None:
-        sync_g()
+        sync_g.finish()
     if record is not None:
         record("g")
     g_opt.step()

@@ -20,8 +20,8 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference"
-sys.path.insert(0, ROOT)
-sys.path.insert(1, REF)
+sys.path.insert(0, REF)       # the reference's `model` / `utils` packages must win over this repository's `model` shim
+sys.path.insert(1, ROOT)
 
 torch.Tensor.cuda = lambda self, *a, **k: self      # the one shim
 import warnings

@@ -8,9 +8,9 @@ import torch
 from conftest import assert_summary_close, dropout_keep_mask, load_case, load_schema
 from layout2img_b200.synth import make_state, synthetic_layout
 from oracle import l2i_oracle as O
+from parity_utils import ATOL, RTOL, close, grad_close, oracle_step
 
 pytestmark = pytest.mark.gpu
-RTOL, ATOL = 1e-3, 1e-4          # north_star tolerance (fp32)
 
 
 def _build(meta, dev):
@@ -29,70 +29,9 @@ def _data(meta):
     return synthetic_layout(meta["batch"], meta["num_obj"], meta["num_classes"], seed=meta["seed"], n_pad=meta["n_pad"])
 
 
-def close(got, want, rtol=RTOL, atol=ATOL, what=""):
-    got, want = got.detach().double().cpu(), want.detach().double().cpu()
-    err = (got - want).abs()
-    bad = err > atol + rtol * want.abs()
-    assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} outside tol, max err {err.max().item():.3e} (ref max {want.abs().max().item():.3e})"
-
-
 def _oracle_step(meta, data, keep, dtype):
-    """One oracle iteration in `dtype`; returns grads ("d.<name>" after d_loss.backward, "g.<name>" after
-    g_loss.backward), losses, fake and the post-step states."""
-    PG = make_state(load_schema("G", meta["num_classes"]), meta["seed_g"])
-    PD = make_state(load_schema("D", meta["num_classes"]), meta["seed_d"])
-    cv = lambda t: t.to(dtype) if t.is_floating_point() else t
-    PG, PD = {k: cv(v) for k, v in PG.items()}, {k: cv(v) for k, v in PD.items()}
-    O.set_requires_grad(PG); O.set_requires_grad(PD)
-    og, od = O.make_adam(PG, 1e-4), O.make_adam(PD, 1e-4)
-    out = {}
-    od_step, og_step = od.step, og.step
-
-    def d_step(*a, **k):
-        for n in O.param_names(PD):
-            out["d." + n] = PD[n].grad.detach().clone()
-        return od_step(*a, **k)
-
-    def g_step(*a, **k):
-        for n in O.param_names(PG):
-            out["g." + n] = PG[n].grad.detach().clone()
-        return og_step(*a, **k)
-
-    od.step, og.step = d_step, g_step
-    rd, rg, rfake = O.train_step(PG, PD, og, od, cv(data["real"]), data["label"], cv(data["bbox"]), cv(data["z"]),
-                                 cv(data["z_im"]), dropout_mask=keep.to(dtype))
-    out.update(d_loss=rd, g_loss=rg, fake=rfake, PG=PG, PD=PD)
-    return out
-
-
-def grad_close(got, want32, want64, what):
-    """End-to-end gradient parity against the fp32 oracle.
-
-    tol1 = 2e-3 * |ref| + 1e-5 + 2e-4 * max|ref| + 4 * (the fp32 oracle's own max deviation from the fp64
-    oracle on this tensor -- gradients that pass through 1/(sum_o m + 1e-6) are only good to ~3e-3 of their
-    max in the reference's own fp32 arithmetic).
-
-    A ReLU whose input is within rounding distance of 0 may land on the other side in any implementation
-    that is not bit-identical to the reference (the fp32 and fp64 oracles disagree with each other the same
-    way, tools/grad_diag.py); every such kink crossing adds or removes one pixel's contribution to the
-    gradients upstream of it.  So on top of tol1: all but 1 % of a tensor's elements must be within
-    5e-3 * max|ref|, every element within 5e-2 * max|ref|, and the relative L2 error below 1e-2.  A wrong
-    formula or index moves most elements by O(max|ref|) and fails all three.  (The tight, kink-free
-    comparisons of every kernel's backward are the per-operator tests in test_gpu_ops.py.)"""
-    got, w32, w64 = got.detach().double().cpu(), want32.detach().double(), want64.detach().double()
-    m = w32.abs().max().item()
-    if m == 0.0:
-        assert got.abs().max().item() <= 1e-12, f"{what}: reference gradient is exactly zero"
-        return
-    noise = (w32 - w64).abs().max().item()
-    err = (got - w32).abs()
-    tol1 = 2e-3 * w32.abs() + 1e-5 + 2e-4 * m + 4 * noise
-    n_loose = int((err > tol1 + 5e-3 * m).sum())
-    msg = (f"{what}: max err {err.max().item():.3e}, ref max {m:.3e}, fp32-ref noise {noise:.3e}, "
-           f"{int((err > tol1).sum())}/{err.numel()} outside tol1, {n_loose} outside tol1 + 5e-3 max")
-    assert n_loose <= max(1, int(0.01 * err.numel())), msg
-    assert bool((err <= tol1 + 5e-2 * m).all()), msg
-    assert err.norm().item() <= 1e-2 * w32.norm().item() + 8 * noise * err.numel() ** 0.5, msg
+    return oracle_step(load_schema("G", meta["num_classes"]), load_schema("D", meta["num_classes"]), meta["seed_g"],
+                       meta["seed_d"], data, keep, dtype)
 
 
 @pytest.mark.parametrize("name", ["C", "Cpad", "V"])
@@ -267,3 +206,50 @@ def test_generator_without_context_attention():
         got = G(data["z"].to(dev), data["bbox"].to(dev), data["z_im"].to(dev), data["label"].to(dev))
         want = O.g_forward(PG, data["z"], data["bbox"], data["z_im"], data["label"], False, context=False)
     close(got, want, what="G (no context) eval forward")
+
+
+def test_checkpoint_round_trip_forward_equal(tmp_path):
+    """Save G in the authors' `module.`-prefixed format, load it the reference's way (strip k[7:], intersect keys,
+    train_context_app_v2.py:77-103) into a fresh model: bit-identical eval forward."""
+    import os
+    from layout2img_b200.checkpoint import load_checkpoint, save_checkpoint
+    from layout2img_b200.model.resnet_generator_app_v2 import ResnetGenerator128_context
+    dev = torch.device("cuda:0")
+    z, meta = load_case("C")
+    data = _data(meta)
+    G, _, _, _ = _build(meta, dev)
+    path = os.path.join(tmp_path, "G_55.pth")
+    save_checkpoint(G, path)
+    G2 = ResnetGenerator128_context(num_classes=meta["num_classes"], output_dim=3).to(dev)
+    rep = load_checkpoint(G2, path)
+    assert not rep["missing"] and not rep["ignored"]
+    G.eval(); G2.eval()
+    with torch.no_grad():
+        a = G(data["z"].to(dev), data["bbox"], data["z_im"].to(dev), data["label"].to(dev))
+        b = G2(data["z"].to(dev), data["bbox"], data["z_im"].to(dev), data["label"].to(dev))
+    assert torch.equal(a, b)
+
+
+def test_pinned_feeder_delivers_loader_batches():
+    """data.PinnedFeeder: batches in the loader's format (cocostuff_loader.py:222-380) arrive on the device unchanged,
+    in order, with the reference loop's casts (label.long(), bbox.float(), train_context_app_v2.py:153)."""
+    from layout2img_b200.data import PinnedFeeder, collate, pack_layout
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(4)
+    batches = []
+    for i in range(5):
+        items = []
+        for j in range(3):
+            n = 1 + (i + j) % 8
+            wh = torch.rand(n, 2, generator=g) * 0.5 + 0.1
+            xy = torch.rand(n, 2, generator=g) * (1 - wh)
+            items.append(pack_layout(torch.rand(3, 128, 128, generator=g) * 2 - 1, torch.randint(1, 184, (n,), generator=g).tolist(),
+                                     torch.cat([xy, wh], 1).numpy(), 8))
+        batches.append(collate(items))
+    feeder = PinnedFeeder(batches, dev, depth=2)
+    seen = 0
+    for (real, label, bbox), want in zip(feeder, batches):
+        assert real.is_cuda and label.dtype == torch.int64 and bbox.dtype == torch.float32
+        assert torch.equal(real.cpu(), want[0]) and torch.equal(label.cpu(), want[1]) and torch.equal(bbox.cpu(), want[2])
+        seen += 1
+    assert seen == 5 and feeder.bytes_per_batch == sum(t.numel() * t.element_size() for t in batches[0])

@@ -371,6 +371,48 @@ def test_fused_adam_matches_torch_adam(dev):
         close(a.state[pa]["exp_avg_sq"], b.state[pb]["exp_avg_sq"], rtol=1e-6, atol=1e-12, what="exp_avg_sq")
 
 
+def test_fused_adam_per_tensor_step_rebuild_and_state_dict(dev):
+    """(i) a parameter whose gradient is missing in some steps keeps its OWN step count (torch's per-parameter bias
+    correction); (ii) un-freezing a parameter later rebuilds the flat buffers WITHOUT wiping the other tensors' moments;
+    (iii) state_dict()/load_state_dict() interoperate with torch.optim.Adam in both directions; (iv) the raw-pointer
+    update bumps autograd's version counter."""
+    from layout2img_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(5)
+    shapes = [(33,), (17, 9), (4, 4, 3, 3)]
+    mk = lambda: [torch.randn(s, generator=torch.Generator().manual_seed(7 + i)).to(dev).requires_grad_() for i, s in enumerate(shapes)]
+    ps_a, ps_b = mk(), mk()
+    ps_a[2].requires_grad_(False); ps_b[2].requires_grad_(False)          # frozen at first
+    a = FusedAdam([{"params": [p], "lr": 1e-3} for p in ps_a], betas=(0.0, 0.999))
+    b = torch.optim.Adam([{"params": [p], "lr": 1e-3} for p in ps_b], betas=(0.0, 0.999))
+    v0 = ps_a[0]._version
+    for step in range(6):
+        if step == 3:
+            ps_a[2].requires_grad_(True); ps_b[2].requires_grad_(True)  # joins later: plan rebuild
+        for i, (pa, pb) in enumerate(zip(ps_a, ps_b)):
+            pa.grad = pb.grad = None
+            if not pa.requires_grad or (i == 1 and step in (1, 2)):       # tensor 1 skips two steps
+                continue
+            gr = torch.randn(pa.shape, generator=g).to(dev)
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        a.step(); b.step()
+    assert ps_a[0]._version > v0
+    for pa, pb in zip(ps_a, ps_b):
+        close(pa, pb, rtol=1e-6, atol=1e-7, what="adam param after rebuild / skipped steps")
+        assert a.state[pa]["step"] == int(b.state[pb]["step"])
+    # torch -> ours and ours -> torch
+    ps_c, ps_d = [p.detach().clone().requires_grad_() for p in ps_a], [p.detach().clone().requires_grad_() for p in ps_a]
+    c = FusedAdam([{"params": [p], "lr": 1e-3} for p in ps_c], betas=(0.0, 0.999))
+    d = torch.optim.Adam([{"params": [p], "lr": 1e-3} for p in ps_d], betas=(0.0, 0.999))
+    c.load_state_dict(b.state_dict())
+    d.load_state_dict(a.state_dict())
+    for pc, pd in zip(ps_c, ps_d):
+        gr = torch.randn(pc.shape, generator=g).to(dev)
+        pc.grad, pd.grad = gr.clone(), gr.clone()
+    c.step(); d.step()
+    for pc, pd in zip(ps_c, ps_d):
+        close(pc, pd, rtol=1e-6, atol=1e-7, what="adam param after state_dict round trip")
+
+
 @pytest.mark.parametrize("cin,cout,H,down,optimized", [(3, 64, 32, True, True), (64, 128, 16, True, False),
                                                       (128, 256, 8, False, False), (72, 72, 8, False, False),
                                                       (512, 1024, 8, True, False)])

@@ -1,5 +1,6 @@
-"""Host-side logic of the data-parallel path on CPU: the flat-bucket gradient all-reduce over a
-world_size-2 gloo group (the NCCL path on the B200 box uses the same code)."""
+"""Host-side logic of the data-parallel path on CPU: zero-copy gradient buckets with hook-driven all-reduces, the
+rank-0 broadcast and the global-object-count loss normalisation over a world_size-2 gloo group (the NCCL path on the
+B200 box uses the same code with a side stream)."""
 import os
 import socket
 
@@ -20,36 +21,66 @@ def _free_port():
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from layout2img_b200.train import GradAllReducer
-    torch.manual_seed(0)
+    from layout2img_b200.train import GradBuckets, _obj_mean, global_object_scale
+    # ---- 1. bucketed all-reduce driven by the post-accumulate hooks; replicas start DIFFERENT and are broadcast from rank 0
+    torch.manual_seed(rank)
     net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
-    # rank-dependent gradients; one parameter left without a gradient on rank 1
-    for i, p in enumerate(net.parameters()):
-        if rank == 1 and i == 3:
-            continue
-        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
-    GradAllReducer(net)()
-    out = [p.grad.clone() for p in net.parameters()]
-    q.put((rank, out))
+    net.add_module("unused", torch.nn.Linear(2, 2))            # never receives a gradient: its bucket is reduced as zeros
+    buckets = GradBuckets(net, bucket_mb=1e-4)                  # tiny buckets: several all-reduces per backward
+    params0 = [p.detach().clone() for p in net.parameters()]
+    x = torch.arange(10, dtype=torch.float32).view(2, 5) / 10.0
+    for _ in range(2):                                          # two iterations: views stay attached, counters reset
+        buckets.zero_grad()
+        ((rank + 1.0) * net[1](net[0](x))).sum().backward()
+        buckets.finish()
+    grads = [p.grad.clone() for p in net.parameters()]
+    is_view = all(p.grad.untyped_storage().data_ptr() == buckets.flat.untyped_storage().data_ptr() for p in net.parameters())
+    # ---- 2. object-loss normalisation over the GLOBAL object count (ranks hold different numbers of valid objects)
+    k_r = 3 if rank == 0 else 5
+    label = torch.cat([torch.ones(k_r, dtype=torch.long), torch.zeros(8 - k_r, dtype=torch.long)]).view(1, 8)
+    scale = global_object_scale(label)
+    w = torch.nn.Parameter(torch.tensor([0.5, -0.25]))
+    feats = torch.arange(16, dtype=torch.float32).view(8, 2)[rank * 3: rank * 3 + k_r] / 7.0
+    _obj_mean(torch.relu(1.0 - feats @ w), scale).backward()
+    gw = w.grad.clone()
+    dist.all_reduce(gw)
+    gw /= world                                                 # what the gradient average over the ranks yields
+    q.put((rank, params0, grads, is_view, gw))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_grad_allreduce_world2_gloo():
+def test_grad_buckets_world2_gloo():
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=120) for _ in range(world))
+    res = {r: rest for r, *rest in (q.get(timeout=120) for _ in range(world))}
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for i in range(4):
-        want = (1 * (i + 1) + (0 if i == 3 else 2 * (i + 1))) / 2.0     # mean over ranks; missing grad counts as 0
-        for r in range(world):
-            assert torch.allclose(res[r][i], torch.full_like(res[r][i], want)), (r, i)
+    # replicas were broadcast from rank 0
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
+    # expected: mean over ranks of (rank + 1) * g = 1.5 * g, g = the single-process gradient on rank 0's weights
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    x = torch.arange(10, dtype=torch.float32).view(2, 5) / 10.0
+    net(x).sum().backward()
+    want = [1.5 * p.grad for p in net.parameters()] + [torch.zeros(2, 2), torch.zeros(2)]
+    for r in range(world):
+        assert res[r][2], "gradients must be views into the flat buffer"
+        for got, w in zip(res[r][1], want):
+            assert torch.allclose(got, w, rtol=1e-5, atol=1e-6), (r, got, w)
+    # K-weighted object loss: equals the gradient of ONE mean over all 8 valid objects of both ranks
+    w = torch.nn.Parameter(torch.tensor([0.5, -0.25]))
+    allf = torch.arange(16, dtype=torch.float32).view(8, 2) / 7.0
+    feats = torch.cat([allf[0:3], allf[3:8]])
+    torch.relu(1.0 - feats @ w).mean().backward()
+    for r in range(world):
+        assert torch.allclose(res[r][3], w.grad, rtol=1e-5, atol=1e-7), (res[r][3], w.grad)
 
 
 def test_shards_are_disjoint_and_deterministic():

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 from layout2img_b200.model.rcnn_discriminator_app import CombineDiscriminator128_app
 from layout2img_b200.synth import make_state, schema_of, synthetic_layout
-from layout2img_b200.train import GradAllReducer, d_loss_fn
+from layout2img_b200.train import GradBuckets, d_loss_fn
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
@@ -26,10 +26,11 @@ def grads(sl, sync):
     D.load_state_dict(make_state(schema_of(D), 2))
     D.to(dev).train()
     d = {k: v[sl].to(dev) for k, v in data.items()}
+    buckets = GradBuckets(D, broadcast=False) if sync else None     # .grad = views into the flat bucket buffer
     loss = d_loss_fn(D(d["real"], d["bbox"], d["label"].unsqueeze(-1)), D(fake[sl].to(dev), d["bbox"], d["label"].unsqueeze(-1)))
     loss.backward()
     if sync:
-        GradAllReducer(D)()
+        buckets.finish()
     return {n: p.grad.detach().clone() for n, p in D.named_parameters()}, D
 
 g_dp, _ = grads(slice(rank * B, (rank + 1) * B), True)          # each rank: its shard, then all-reduce (mean)
@@ -58,10 +59,11 @@ def g_run(sl, sync, perturb=0.0):
     n = sl.stop - sl.start
     G.res4.conv_mask[0].dropout_mask = torch.ones(n, 100)
     d = {k: v[sl].to(dev) for k, v in data.items()}
+    buckets = GradBuckets(G, broadcast=False) if sync else None
     fake = G(d["z"], d["bbox"], d["z_im"] * (1.0 + perturb), d["label"])
     (fake * proj[sl].to(dev)).mean().backward()
     if sync:
-        GradAllReducer(G)()
+        buckets.finish()
     ops.set_sync_bn(False)
     return fake.detach(), {k: p.grad.detach().clone() for k, p in G.named_parameters() if p.grad is not None}, \
         {k: v.detach().clone() for k, v in G.state_dict().items() if "running_" in k}
