@@ -379,13 +379,17 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = {}
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
+        host_ms[fn.__name__] = (time.perf_counter() - t0) * 1e3 / steps     # host time to ENQUEUE a step (no sync)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
@@ -472,6 +476,7 @@ def run_ours(args, rank, local_rank, world):
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
+            "host_enqueue_ms_per_step": host_ms.get("step_resident"),
             "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "library_baseline": lib,
             "kernel_ms_per_step": breakdown,

@@ -97,10 +97,11 @@ int l2i_isla_fwd(const float* x, const float* mean_invstd, const float* mask, co
 /* Backward of l2i_isla_fwd followed by (relu) and (nearest x2): dout [B,H<<up2,W<<up2,C].
  * Writes dx [B,H,W,C]; for O > 0 dmask [B,H,W,O], dgamma, dbeta [B,O,C]; csum [2C] fp64 receives
  * (sum dxhat, sum dxhat*xhat) for O > 0 or (dbias, dweight) of the affine form for O == 0.
- * gbuf [B,H,W,C] is scratch.  train = 0 skips the batch-statistics terms (eval-mode BN).
+ * gbuf is unused (may be NULL; the backward writes no intermediate tensor: two passes over x and dout, 20 B per
+ * element).  train = 0 skips the batch-statistics terms (eval-mode BN).  At most 32 objects per image.
  * phase 0 runs everything; for a batch norm whose statistics span several ranks (the reference's multi-GPU
- * SynchronizedBatchNorm2d, sync_batchnorm/batchnorm.py:90-111) call phase 1 (all reductions; dx is left holding
- * d xhat), all-reduce csum, then phase 2 (dx) with count = the global pixel count (count <= 0: B*H*W). */
+ * SynchronizedBatchNorm2d, sync_batchnorm/batchnorm.py:90-111) call phase 1 (all reductions; dx untouched),
+ * all-reduce csum, then phase 2 (dx) with count = the global pixel count (count <= 0: B*H*W). */
 int l2i_isla_bwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
                  const float* aff_w, const float* aff_b, const float* dout, int B, int H, int W, int C, int O,
                  int relu, int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum,
@@ -183,6 +184,24 @@ int l2i_sn_sigma(const float* W, int R, int Cc, float* u, float* v, int training
  * weight gradient G [R][taps][cin] (l2i_conv2d_wgrad's layout).  scratch: 1 float. */
 int l2i_sn_weight_grad(const float* G, const float* W, const float* u, const float* v, const float* sigma, int R, int cin,
                        int taps, float* dW, float* scratch, void* stream);
+
+/* Grouped form of the two calls above plus l2i_conv_weight_prep: ONE call runs the power iteration / sigma of every
+ * spectrally normalised module of a network forward and writes the tensor-core operand pairs of every convolution
+ * weight (6 launches instead of ~4 per module).  Power iterations depend on the weights only, so running them all
+ * before the first layer is the same arithmetic as torch's per-module pre-forward hooks.
+ *   table: device array of n_modules entries { const float* W; float* u; float* v; int64 f32_off; int64 bf_off;
+ *     int R, Cc; float eps; int training, has_sn; int cin, taps; int pad; } (72 bytes).  has_sn = 0: plain conv weight
+ *     (operand pairs only).  bf_off < 0: no operand pairs (linear / embedding weights).
+ *   f32 (f32_floats floats, zeroed by the call): per module at f32_off: sigma [4], u_used [pad4(R)], v_used [pad4(Cc)]
+ *     and 2 scratch vectors (pad4(Cc), pad4(R)).
+ *   bf16: per module at bf_off: forward pair hi, lo ([R][taps][pad(cin)] each, rounded up to 64 elements), then, when
+ *     want_dgrad, the data-gradient pair hi, lo ([cin][taps][pad(R)] each); pad() as in l2i_conv_weight_prep's callers.
+ *   work lists (device, static per network): wt_items int4 (module, column block of 256, r0, r1), wv_items int2 (module,
+ *     block of 8 rows), prep9_items / prep1_items int4 (module, tile_x, tile_y, 0) for 3x3 / 1x1 weights in 32 x 32 tiles;
+ *     wt_smem_floats = max (r1 - r0), max_cc = max Cc over the modules. */
+int l2i_sn_prepare_group(const void* table, int n_modules, const int* wt_items, int n_wt, int wt_smem_floats,
+                         const int* wv_items, int n_wv, int max_cc, const int* prep9_items, int n9, const int* prep1_items,
+                         int n1, float* f32, long long f32_floats, void* bf16, int want_dgrad, void* stream);
 
 /* ---- optimizer (reference train_context_app_v2.py:113-127,174,189: torch.optim.Adam(betas=(0, 0.999)),
  *      one parameter group per tensor).  One launch updates every tensor of a network.

@@ -186,6 +186,14 @@ int l2i_sn_weight_grad(const float* G, const float* W, const float* u, const flo
                        int taps, float* dW, float* scratch, void* stream) {
   return sn_weight_grad(G, W, u, v, sigma, R, cin, taps, dW, scratch, ST(stream));
 }
+int l2i_sn_prepare_group(const void* table, int n_modules, const int* wt_items, int n_wt, int wt_smem_floats,
+                         const int* wv_items, int n_wv, int max_cc, const int* prep9_items, int n9, const int* prep1_items,
+                         int n1, float* f32, long long f32_floats, void* bf16, int want_dgrad, void* stream) {
+  int rc = sn_group_sigma(table, n_modules, wt_items, n_wt, wt_smem_floats, wv_items, n_wv, max_cc, f32, f32_floats, ST(stream));
+  if (rc) return rc;
+  if (n9 + n1 > 0) rc = weight_prep_group(table, prep9_items, n9, prep1_items, n1, f32, bf16, want_dgrad, ST(stream));
+  return rc;
+}
 int l2i_adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, double beta1, double beta2,
                   double eps, void* stream) {
   return adam_step(tensors, chunks, n_chunks, chunk_elems, beta1, beta2, eps, ST(stream));

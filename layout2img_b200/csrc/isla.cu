@@ -130,12 +130,19 @@ int bn_eval_stats(const float* rm, const float* rv, int C, float eps, float* mea
 }
 
 // ------------------------------------------------------------------------------------------
-// forward apply.  grid = (pixel chunks, channel chunks, images); gamma/beta of this image and
-// channel chunk live in shared memory; thread <-> (pixel, 8 consecutive channels).
-// O == 0 : plain affine batch norm  out = xh * aff_w + aff_b   (final.0, mask heads)
+// ISLA apply and its backward.  One layout for all three kernels: a WARP owns 32 * CPT consecutive channels of one
+// pixel (CPT = 1 or 2 channels per lane: 128- / 256-byte coalesced loads, bf16x2 stores), a block is
+// warps_c (channel direction) x warps_p (pixel lanes) warps and walks the pixels of ONE image; each lane keeps the
+// image's gamma / beta of its channels in registers, the O mask values of a pixel are warp-uniform (broadcast) loads.
+//   forward   y = (G/S + 1) xh + Bt/S -> [fp32] and/or ReLU'd bf16 pair (nearest x2 optional): x read once
+//   backward  2 passes, nothing but the results is written:
+//     reduce  g = relu'(y) dout (y recomputed from x with the forward's exact instruction sequence);
+//             dgamma, dbeta (sum over pixels), sum dxh, sum dxh*xh (per channel), dmask (sum over channels: a
+//             transposed warp butterfly turns 32 per-lane partials into one total per lane in 31 shuffles)
+//     dx      dx = (dxh - mean(dxh) - xh mean(dxh xh)) invstd   [train]   |   dxh invstd   [eval]
+//   traffic per element: forward 4 B + pair; backward 2 x (x + dout) + dx = 20 B (the 3-pass form moved 40 B).
+// O == 0 : plain / affine batch norm  y = xh * aff_w + aff_b   (final.0, mask heads)
 // ------------------------------------------------------------------------------------------
-static constexpr int kIslaCc = 256;   // channels per block (shared memory = O * 256 * 2 floats)
-
 struct IslaFwdParams {
   const float* x;           // [B,H,W,C]
   const float* mean_invstd; // [2C]
@@ -148,111 +155,156 @@ struct IslaFwdParams {
   __nv_bfloat16* hi;        // [B,H<<up,W<<up,cpad] or null
   __nv_bfloat16* lo;
   int B, H, W, C, O, cpad, relu, up;
+  int warps_c, warps_p;
 };
 
-__global__ void __launch_bounds__(256) isla_fwd_kernel(const IslaFwdParams p) {
-  extern __shared__ float sh[];
-  const int b = blockIdx.z;
-  const int c0 = blockIdx.y * kIslaCc;
-  const int cc = min(kIslaCc, p.C - c0);
-  float* s_gam = sh;                       // [O][cc]
-  float* s_bet = sh + p.O * kIslaCc;
-  for (int i = threadIdx.x; i < p.O * cc; i += blockDim.x) {
-    const int o = i / cc, c = i - o * cc;
-    s_gam[o * kIslaCc + c] = __ldg(p.gamma + (static_cast<size_t>(b) * p.O + o) * p.C + c0 + c);
-    s_bet[o * kIslaCc + c] = __ldg(p.beta + (static_cast<size_t>(b) * p.O + o) * p.C + c0 + c);
+struct IslaBwdParams {
+  const float* x; const float* mean_invstd; const float* mask; const float* gamma; const float* beta;
+  const float* aff_w; const float* aff_b;
+  const float* dout;        // [B,H<<up,W<<up,C]
+  float* dmask;             // [B,H,W,O]  (zero-initialised when the channels span several blocks)
+  float* dgamma;            // [B,O,C]  (zero-initialised, atomics)
+  float* dbeta;
+  double* csum;             // [2C] sum dxh, sum dxh*xh  (zero-initialised);  O == 0: dbias, dweight sums
+  float* dx;                // [B,H,W,C]
+  double count;
+  int B, H, W, C, O, relu, up, train;
+  int warps_c, warps_p, seg;   // seg: pixels per block (reduce pass)
+};
+
+// the one expression of the modulation; every kernel below must produce bit-identical y for the ReLU mask
+__device__ __forceinline__ float isla_y(float G, float Bt, float invS, float xh) {
+  return fmaf(fmaf(G, invS, 1.0f), xh, Bt * invS);
+}
+
+// per-lane constants of the lane's CPT channels for image b
+template <int OM, int CPT>
+struct IslaLane {
+  static constexpr int OMX = OM > 0 ? OM : 1;
+  float mean[CPT], invstd[CPT], gam[OMX][CPT], bet[OMX][CPT], aw[CPT], ab[CPT];
+  __device__ __forceinline__ void load(const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float* __restrict__ aff_w,
+                                       const float* __restrict__ aff_b, int b, int c, int C, int O) {
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const bool ok = c + j < C;
+      mean[j] = ok ? __ldg(mean_invstd + c + j) : 0.f;
+      invstd[j] = ok ? __ldg(mean_invstd + C + c + j) : 0.f;
+      aw[j] = (ok && aff_w) ? __ldg(aff_w + c + j) : 1.f;
+      ab[j] = (ok && aff_b) ? __ldg(aff_b + c + j) : 0.f;
+#pragma unroll
+      for (int o = 0; o < OMX; ++o) {
+        const bool oo = OM > 0 && ok && o < O;
+        gam[o][j] = oo ? __ldg(gamma + (static_cast<size_t>(b) * O + o) * C + c + j) : 0.f;
+        bet[o][j] = oo ? __ldg(beta + (static_cast<size_t>(b) * O + o) * C + c + j) : 0.f;
+      }
+    }
   }
-  __syncthreads();
-  // 8-channel groups in this chunk; a pair's padding channels (up to cpad) are written as zeros
-  const int ccp = p.hi ? min(kIslaCc, p.cpad - c0) : cc;
-  const int groups = (max(cc, ccp) + 7) >> 3;
-  const int hw = p.H * p.W;
-  const int Ho = p.H << p.up, Wo = p.W << p.up;
-  const long long items = 1LL * hw * groups;
-  for (long long it = 1LL * blockIdx.x * blockDim.x + threadIdx.x; it < items; it += 1LL * gridDim.x * blockDim.x) {
-    const int g = static_cast<int>(it % groups);
-    const int pix = static_cast<int>(it / groups);
-    const int c = g * 8;                   // within chunk
-    const size_t gp = static_cast<size_t>(b) * hw + pix;
-    const float* xp = p.x + gp * p.C + c0 + c;
-    float xv[8], gm[8], bt[8];
-    const bool full = (c + 8 <= cc) && ((p.C & 3) == 0);
-    if (full) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(xp));
-      const float4 d = __ldg(reinterpret_cast<const float4*>(xp) + 1);
-      xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = d.x; xv[5] = d.y; xv[6] = d.z; xv[7] = d.w;
+};
+
+// the O mask values of one pixel (warp-uniform address) and 1 / (sum + 1e-6)
+template <int OM>
+__device__ __forceinline__ float isla_masks(const float* __restrict__ mp, int O, float (&m)[OM > 0 ? OM : 1]) {
+  float S = kMaskEps;
+  if constexpr (OM > 0) {
+    if ((O & 3) == 0) {
+#pragma unroll
+      for (int o = 0; o < OM; o += 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o < O) v = __ldg(reinterpret_cast<const float4*>(mp + o));
+        m[o] = v.x; m[o + 1] = v.y; m[o + 2] = v.z; m[o + 3] = v.w;
+      }
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xv[j] = (c + j < cc) ? __ldg(xp + j) : 0.f;
+      for (int o = 0; o < OM; ++o) m[o] = (o < O) ? __ldg(mp + o) : 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { gm[j] = 0.f; bt[j] = 0.f; }
-    float S = kMaskEps;
-    if (p.O > 0) {
-      const float* mp = p.mask + gp * p.O;
-      for (int o = 0; o < p.O; ++o) {
-        const float m = __ldg(mp + o);
-        S += m;
-        const float* sg = s_gam + o * kIslaCc + c;
-        const float* sb = s_bet + o * kIslaCc + c;
+    for (int o = 0; o < OM; ++o) S += m[o];
+  }
+  return 1.0f / S;
+}
+
+template <int CPT>
+__device__ __forceinline__ void load_cpt(const float* __restrict__ p, bool ok, float (&v)[CPT]) {
+  if constexpr (CPT == 2) {
+    float2 t = make_float2(0.f, 0.f);
+    if (ok) t = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    v[0] = ok ? __ldg(p) : 0.f;
+  }
+}
+
+template <int OM, int CPT>
+__global__ void __launch_bounds__(256) isla_fwd_kernel(const IslaFwdParams p) {
+  using Lane = IslaLane<OM, CPT>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wc = warp % p.warps_c, wp = warp / p.warps_c;
+  const int b = blockIdx.z;
+  const int c = ((blockIdx.y * p.warps_c + wc) * 32 + lane) * CPT;
+  const bool c_ok = c < p.C;                        // C is a multiple of CPT
+  const bool c_pad = p.hi && c < p.cpad;            // a pair's padding channels are written as zeros
+  Lane L;
+  L.load(p.mean_invstd, p.gamma, p.beta, p.aff_w, p.aff_b, b, c, p.C, p.O);
+  const int hw = p.H * p.W;
+  const int Ho = p.H << p.up, Wo = p.W << p.up;
+  const int rep = 1 << p.up;
+  const float* __restrict__ xb = p.x + static_cast<size_t>(b) * hw * p.C + c;
+  const float* __restrict__ mb = p.mask ? p.mask + static_cast<size_t>(b) * hw * p.O : nullptr;
+#pragma unroll 2
+  for (int pix = blockIdx.x * p.warps_p + wp; pix < hw; pix += gridDim.x * p.warps_p) {
+    float xv[CPT];
+    load_cpt<CPT>(xb + static_cast<size_t>(pix) * p.C, c_ok, xv);
+    float m[Lane::OMX];
+    float invS = 1.0f;
+    if constexpr (OM > 0) invS = isla_masks<OM>(mb + static_cast<size_t>(pix) * p.O, p.O, m);
+    float y[CPT];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          gm[j] = fmaf(m, sg[j], gm[j]);
-          bt[j] = fmaf(m, sb[j], bt[j]);
-        }
-      }
-    }
-    float y[8];
+    for (int j = 0; j < CPT; ++j) {
+      const float xh = (xv[j] - L.mean[j]) * L.invstd[j];
+      if constexpr (OM > 0) {
+        float G = 0.f, Bt = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ch = c0 + c + j;
-      float v = 0.f;
-      if (c + j < cc) {
-        const float xh = (xv[j] - __ldg(p.mean_invstd + ch)) * __ldg(p.mean_invstd + p.C + ch);
-        if (p.O > 0) {
-          v = (gm[j] / S + 1.0f) * xh + bt[j] / S;
-        } else {
-          v = xh;
-          if (p.aff_w) v = v * __ldg(p.aff_w + ch) + __ldg(p.aff_b + ch);
-        }
-      }
-      y[j] = v;
-    }
-    if (p.out) {
-      float* op = p.out + gp * p.C + c0 + c;
-      if (full) {
-        *reinterpret_cast<float4*>(op) = make_float4(y[0], y[1], y[2], y[3]);
-        *(reinterpret_cast<float4*>(op) + 1) = make_float4(y[4], y[5], y[6], y[7]);
+        for (int o = 0; o < OM; ++o) { G = fmaf(m[o], L.gam[o][j], G); Bt = fmaf(m[o], L.bet[o][j], Bt); }
+        y[j] = isla_y(G, Bt, invS, xh);
       } else {
-        for (int j = 0; j < 8 && c + j < cc; ++j) op[j] = y[j];
+        y[j] = fmaf(xh, L.aw[j], L.ab[j]);
       }
+      if (!c_ok) y[j] = 0.f;
     }
-    if (p.hi) {
-      uint32_t ph[4], pl[4];
+    if (p.out && c_ok) {
+      float* op = p.out + (static_cast<size_t>(b) * hw + pix) * p.C + c;
+      if constexpr (CPT == 2) *reinterpret_cast<float2*>(op) = make_float2(y[0], y[1]); else op[0] = y[0];
+    }
+    if (c_pad) {
+      __nv_bfloat16 h[CPT], l[CPT];
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        float a = y[j], d = y[j + 1];
-        if (p.relu) { a = fmaxf(a, 0.f); d = fmaxf(d, 0.f); }
-        __nv_bfloat16 ah, al, dh, dl;
-        split_bf16(a, ah, al);
-        split_bf16(d, dh, dl);
-        ph[j >> 1] = pack_bf16x2(ah, dh);
-        pl[j >> 1] = pack_bf16x2(al, dl);
-      }
-      if (c0 + c < p.cpad) {
-        const int h = pix / p.W, w = pix - h * p.W;
-        const uint4 vh = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-        const uint4 vl = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-        const int rep = 1 << p.up;
-        for (int dy = 0; dy < rep; ++dy)
-          for (int dx = 0; dx < rep; ++dx) {
-            const size_t op = ((static_cast<size_t>(b) * Ho + (h << p.up) + dy) * Wo + (w << p.up) + dx) * p.cpad + c0 + c;
-            *reinterpret_cast<uint4*>(p.hi + op) = vh;
-            *reinterpret_cast<uint4*>(p.lo + op) = vl;
+      for (int j = 0; j < CPT; ++j) split_bf16(p.relu ? fmaxf(y[j], 0.f) : y[j], h[j], l[j]);
+      const int hh = pix / p.W, ww = pix - hh * p.W;
+      for (int dy = 0; dy < rep; ++dy)
+        for (int dx = 0; dx < rep; ++dx) {
+          const size_t op = ((static_cast<size_t>(b) * Ho + (hh << p.up) + dy) * Wo + (ww << p.up) + dx) * p.cpad + c;
+          if constexpr (CPT == 2) {
+            *reinterpret_cast<uint32_t*>(p.hi + op) = pack_bf16x2(h[0], h[1]);
+            *reinterpret_cast<uint32_t*>(p.lo + op) = pack_bf16x2(l[0], l[1]);
+          } else {
+            p.hi[op] = h[0];
+            p.lo[op] = l[0];
           }
-      }
+        }
     }
   }
+}
+
+// block shape for a channel extent: warps along the channels (<= 8), pixel lanes, channel chunks (grid.y)
+static void isla_shape(int cext, int cpt, int* warps_c, int* warps_p, int* chunks) {
+  const int need = (cext + 32 * cpt - 1) / (32 * cpt);
+  int wc = need < 8 ? need : 8;
+  if (wc > 4 && wc < 8) wc = 4;                   // 5..7 -> 4 warps x 2 chunks (keeps 8 warps per block busy)
+  if (wc == 3) wc = 4;
+  *warps_c = wc;
+  *warps_p = 8 / wc;
+  *chunks = (need + wc - 1) / wc;
 }
 
 int isla_fwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
@@ -261,229 +313,287 @@ int isla_fwd(const float* x, const float* mean_invstd, const float* mask, const 
   if (!x || !mean_invstd || B <= 0 || H <= 0 || W <= 0 || C <= 0 || O < 0 || (!out && !hi)) { set_error("isla_fwd: bad arguments"); return L2I_ERR_BAD_ARG; }
   if (O > 0 && (!mask || !gamma || !beta)) { set_error("isla_fwd: mask/gamma/beta required when O > 0"); return L2I_ERR_BAD_ARG; }
   if (hi && (!lo || cpad % 8 || cpad < C)) { set_error("isla_fwd: bad pair arguments"); return L2I_ERR_BAD_ARG; }
-  if (O > 48) { set_error("isla_fwd: at most 48 objects per image supported (got %d)", O); return L2I_ERR_UNSUPPORTED; }
+  if (O > 32) { set_error("isla_fwd: at most 32 objects per image supported (got %d)", O); return L2I_ERR_UNSUPPORTED; }
   IslaFwdParams p;
   p.x = x; p.mean_invstd = mean_invstd; p.mask = mask; p.gamma = gamma; p.beta = beta; p.aff_w = aff_w; p.aff_b = aff_b;
   p.out = out; p.hi = reinterpret_cast<__nv_bfloat16*>(hi); p.lo = reinterpret_cast<__nv_bfloat16*>(lo);
   p.B = B; p.H = H; p.W = W; p.C = C; p.O = O; p.cpad = cpad; p.relu = relu; p.up = up2 ? 1 : 0;
-  const int chunks = (C + kIslaCc - 1) / kIslaCc;
-  const long long items = 1LL * H * W * ((min(C, kIslaCc) + 7) / 8);
-  long long bx = (items + 255) / 256;
-  const long long cap = (148LL * 32 + 1LL * B * chunks - 1) / (1LL * B * chunks);   // ~32 CTAs per SM in flight over the launch
+  const int cpt = ((C & 1) == 0 && O <= 16) ? 2 : 1;
+  int chunks;
+  isla_shape(hi ? (cpad > C ? cpad : C) : C, cpt, &p.warps_c, &p.warps_p, &chunks);
+  const int hw = H * W;
+  long long bx = (hw + p.warps_p * 4 - 1) / (p.warps_p * 4);          // >= 4 pixels per warp
+  const long long cap = (148LL * 12 + 1LL * B * chunks - 1) / (1LL * B * chunks);
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
-  const size_t smem = sizeof(float) * 2 * O * kIslaCc;
-  static DeviceOnce configured;
-  if (configured.need()) {
-    cudaFuncSetAttribute(isla_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 2 * kIslaCc * 4);
-    configured.done();
-  }
   dim3 grid(static_cast<int>(bx), chunks, B);
-  isla_fwd_kernel<<<grid, 256, smem, stream>>>(p);
+  const int threads = 32 * p.warps_c * p.warps_p;
+  if (O == 0) {
+    if (cpt == 2) isla_fwd_kernel<0, 2><<<grid, threads, 0, stream>>>(p); else isla_fwd_kernel<0, 1><<<grid, threads, 0, stream>>>(p);
+  } else if (O <= 8) {
+    if (cpt == 2) isla_fwd_kernel<8, 2><<<grid, threads, 0, stream>>>(p); else isla_fwd_kernel<8, 1><<<grid, threads, 0, stream>>>(p);
+  } else if (O <= 16) {
+    if (cpt == 2) isla_fwd_kernel<16, 2><<<grid, threads, 0, stream>>>(p); else isla_fwd_kernel<16, 1><<<grid, threads, 0, stream>>>(p);
+  } else {
+    isla_fwd_kernel<32, 1><<<grid, threads, 0, stream>>>(p);
+  }
   return check_launch("isla_fwd_kernel");
 }
 
-// ------------------------------------------------------------------------------------------
-// backward.  Three passes:
-//   A  pixel-major   : g = relu'(out) * (sum of the 2x2 up-sampled dout)  -> gbuf ; dmask (reduce over c)
-//   B  channel-major : dgamma, dbeta (reduce over pixels of one image), sum dxh, sum dxh*xh (per channel)
-//   C  elementwise   : dx = (G*g - mean(dxh) - xh*mean(dxh*xh)) * invstd      [train]
-//                      dx = G*g*invstd                                         [eval]
-// ------------------------------------------------------------------------------------------
-struct IslaBwdParams {
-  const float* x; const float* mean_invstd; const float* mask; const float* gamma; const float* beta;
-  const float* aff_w; const float* aff_b;
-  const float* dout;        // [B,H<<up,W<<up,C]
-  float* gbuf;              // [B,H,W,C]
-  float* dmask;             // [B,H,W,O]
-  float* dgamma;            // [B,O,C]  (zero-initialised, atomics)
-  float* dbeta;
-  double* csum;             // [2C] sum dxh, sum dxh*xh  (zero-initialised);  O == 0: dbias, dweight sums
-  float* dx;                // [B,H,W,C]
-  double count;
-  int B, H, W, C, O, relu, up, train;
-};
-
-// pass A: LPP lanes per pixel (32, or 16 when C <= 64), lanes stride the channels (float4 per lane per step)
-template <int OM, int LPP>
-__global__ void __launch_bounds__(256, OM <= 8 ? 3 : 2) isla_bwd_a_kernel(const IslaBwdParams p) {
-  const int lane = threadIdx.x & 31;
-  const int sub = lane / LPP, l = lane % LPP;
-  constexpr int PPW = 32 / LPP;
-  const int wpb = blockDim.x >> 5;
-  const int warp = threadIdx.x >> 5;
-  const long long pixels = 1LL * p.B * p.H * p.W;
-  const int hw = p.H * p.W;
-  const int Ho = p.H << p.up, Wo = p.W << p.up;
-  const long long pixel_groups = (pixels + PPW - 1) / PPW;
-  for (long long pg = 1LL * blockIdx.x * wpb + warp; pg < pixel_groups; pg += 1LL * gridDim.x * wpb) {
-    const long long gp = pg * PPW + sub;
-    const bool pok = gp < pixels;
-    const long long gpc = pok ? gp : pixels - 1;
-    const int b = static_cast<int>(gpc / hw);
-    const int pix = static_cast<int>(gpc - 1LL * b * hw);
-    const int h = pix / p.W, w = pix - h * p.W;
-    float S = kMaskEps;
-    const float* mp = p.mask ? p.mask + gpc * p.O : nullptr;
-    for (int o = 0; o < p.O; ++o) S += __ldg(mp + o);
-    const float invS = 1.0f / S;
-    float dm[OM];
-    float common = 0.f;
+// ---- backward, pass 1: every reduction ---------------------------------------------------------------------------
+// sum of v[i] over the 32 lanes for all 32 indices at once: afterwards lane L holds the total of index L
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 #pragma unroll
-    for (int o = 0; o < OM; ++o) dm[o] = 0.f;
-    for (int c = l * 4; c < p.C; c += LPP * 4) {
-      const float4 xv4 = __ldg(reinterpret_cast<const float4*>(p.x + gpc * p.C + c));
-      const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
-      float dsum[4] = {0, 0, 0, 0};
-      const int rep = 1 << p.up;
-      for (int dy = 0; dy < rep; ++dy)
-        for (int dx = 0; dx < rep; ++dx) {
-          const size_t op = ((static_cast<size_t>(b) * Ho + (h << p.up) + dy) * Wo + (w << p.up) + dx) * p.C + c;
-          const float4 d4 = __ldg(reinterpret_cast<const float4*>(p.dout + op));
-          dsum[0] += d4.x; dsum[1] += d4.y; dsum[2] += d4.z; dsum[3] += d4.w;
-        }
-      float G[4] = {0, 0, 0, 0}, Bt[4] = {0, 0, 0, 0};
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
 #pragma unroll
-      for (int o = 0; o < OM; ++o) {
-        if (o < p.O) {
-          const float m = __ldg(mp + o);
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + (static_cast<size_t>(b) * p.O + o) * p.C + c));
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + (static_cast<size_t>(b) * p.O + o) * p.C + c));
-          G[0] = fmaf(m, g4.x, G[0]); G[1] = fmaf(m, g4.y, G[1]); G[2] = fmaf(m, g4.z, G[2]); G[3] = fmaf(m, g4.w, G[3]);
-          Bt[0] = fmaf(m, b4.x, Bt[0]); Bt[1] = fmaf(m, b4.y, Bt[1]); Bt[2] = fmaf(m, b4.z, Bt[2]); Bt[3] = fmaf(m, b4.w, Bt[3]);
-        }
-      }
-      // d m_o * S = sum_c g xh gamma_oc + sum_c g beta_oc - sum_c g (xh (Gamma - 1) + B), and
-      // xh (Gamma - 1) + B = out - xh: the subtracted term is the same for every object (`common`)
-      float gv[4], gx[4], dxh[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float xh = (xv[j] - __ldg(p.mean_invstd + c + j)) * __ldg(p.mean_invstd + p.C + c + j);
-        float outv;
-        if (p.O > 0) {
-          outv = (G[j] * invS + 1.0f) * xh + Bt[j] * invS;
-        } else {
-          outv = xh;
-          if (p.aff_w) outv = outv * __ldg(p.aff_w + c + j) + __ldg(p.aff_b + c + j);
-        }
-        gv[j] = (p.relu && !(outv > 0.f)) ? 0.f : dsum[j];
-        gx[j] = gv[j] * xh;
-        common = fmaf(gv[j], outv - xh, common);
-        // d xh = Gamma * g (ISLA) or aff_w * g (affine BN): parked in dx for passes B and C
-        dxh[j] = gv[j] * ((p.O > 0) ? (G[j] * invS + 1.0f) : (p.aff_w ? __ldg(p.aff_w + c + j) : 1.0f));
-      }
-      if (pok) {
-        *reinterpret_cast<float4*>(p.gbuf + gp * p.C + c) = make_float4(gv[0], gv[1], gv[2], gv[3]);
-        *reinterpret_cast<float4*>(p.dx + gp * p.C + c) = make_float4(dxh[0], dxh[1], dxh[2], dxh[3]);
-      }
-#pragma unroll
-      for (int o = 0; o < OM; ++o) {
-        if (o < p.O) {
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + (static_cast<size_t>(b) * p.O + o) * p.C + c));
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + (static_cast<size_t>(b) * p.O + o) * p.C + c));
-          const float go[4] = {g4.x, g4.y, g4.z, g4.w}, bo[4] = {b4.x, b4.y, b4.z, b4.w};
-          float acc = 0.f;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc = fmaf(gx[j], go[j], fmaf(gv[j], bo[j], acc));
-          dm[o] += acc;
-        }
-      }
-    }
-    if (p.O > 0) {
-#pragma unroll
-      for (int o = 0; o < OM; ++o) {
-        if (o < p.O) {
-          float v = dm[o] - common;
-#pragma unroll
-          for (int off = LPP / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-          if (l == 0 && pok) p.dmask[gp * p.O + o] = v * invS;
-        }
-      }
+    for (int i = 0; i < half; ++i) {
+      const float keep = upper ? v[i + half] : v[i];
+      const float send = upper ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
     }
   }
+  return v[0];
 }
 
-// pass B: block = (pixel segment, channel chunk, image); thread <-> channel, loops over pixels
-template <int OM>
-__global__ void __launch_bounds__(128) isla_bwd_b_kernel(const IslaBwdParams p) {
+template <int OM, int CPT>
+__global__ void __launch_bounds__(256) isla_bwd_reduce_kernel(const IslaBwdParams p) {
+  using Lane = IslaLane<OM, CPT>;
+  constexpr int OMX = Lane::OMX;
+  constexpr int PIXG = OM > 0 ? 32 / OM : 1;        // pixels per butterfly
+  extern __shared__ float sh[];                     // s_dm [seg * O]  then (reused) the block reductions
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wc = warp % p.warps_c, wp = warp / p.warps_c;
   const int b = blockIdx.z;
-  const int c = blockIdx.y * blockDim.x + threadIdx.x;
-  if (c >= p.C) return;
+  const int cl = (wc * 32 + lane) * CPT;            // channel inside the block's chunk
+  const int cb = 32 * CPT * p.warps_c;              // channels per block
+  const int c = blockIdx.y * cb + cl;
+  const bool c_ok = c < p.C;
+  Lane L;
+  L.load(p.mean_invstd, p.gamma, p.beta, p.aff_w, p.aff_b, b, c, p.C, p.O);
   const int hw = p.H * p.W;
-  const int seg = (hw + gridDim.x - 1) / gridDim.x;
-  const int p0 = blockIdx.x * seg, p1 = min(hw, p0 + seg);
-  float accg[OM], accb[OM];
-#pragma unroll
-  for (int o = 0; o < OM; ++o) { accg[o] = 0.f; accb[o] = 0.f; }
-  const float mean = __ldg(p.mean_invstd + c), invstd = __ldg(p.mean_invstd + p.C + c);
-  const float aw = (p.O == 0 && p.aff_w) ? __ldg(p.aff_w + c) : 1.0f;
-  float s1 = 0.f, s2 = 0.f;
-  double d1 = 0, d2 = 0;
-#pragma unroll 4
-  for (int pix = p0; pix < p1; ++pix) {
-    const size_t gp = static_cast<size_t>(b) * hw + pix;
-    const float g = __ldg(p.gbuf + gp * p.C + c);
-    const float xh = (__ldg(p.x + gp * p.C + c) - mean) * invstd;
-    if (p.O > 0) {
-      float m[OM];
-      float S = kMaskEps;
-#pragma unroll
-      for (int o = 0; o < OM; ++o) {
-        m[o] = (o < p.O) ? __ldg(p.mask + gp * p.O + o) : 0.f;   // warp-uniform address: one broadcast load
-        S += m[o];
-      }
-      const float invS = 1.0f / S;
-      const float gx = g * xh * invS, gs = g * invS;
-#pragma unroll
-      for (int o = 0; o < OM; ++o) { accg[o] = fmaf(gx, m[o], accg[o]); accb[o] = fmaf(gs, m[o], accb[o]); }
-      const float dxh = __ldg(p.dx + gp * p.C + c);            // Gamma * g, written by pass A
-      s1 += dxh; s2 += dxh * xh;
-    } else {
-      s1 += g; s2 += g * xh;           // dbias, dweight of the affine form
-    }
-    if (((pix - p0) & 63) == 63) { d1 += s1; d2 += s2; s1 = 0.f; s2 = 0.f; }
+  const int Wo = p.W << p.up;
+  const int rep = 1 << p.up;
+  const int p0 = blockIdx.x * p.seg, p1 = min(hw, p0 + p.seg);
+  if constexpr (OM > 0) {
+    for (int i = threadIdx.x; i < (p1 - p0) * p.O; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
   }
-  d1 += s1; d2 += s2;
+  const float* __restrict__ xb = p.x + static_cast<size_t>(b) * hw * p.C + c;
+  const float* __restrict__ db = p.dout + static_cast<size_t>(b) * hw * rep * rep * p.C + c;
+  const float* __restrict__ mb = p.mask ? p.mask + static_cast<size_t>(b) * hw * p.O : nullptr;
+  float accg[OMX][CPT], accb[OMX][CPT], s1[CPT], s2[CPT];
+  double d1[CPT], d2[CPT];
 #pragma unroll
-  for (int o = 0; o < OM; ++o)
-    if (o < p.O) {
-      atomicAdd(p.dgamma + (static_cast<size_t>(b) * p.O + o) * p.C + c, accg[o]);
-      atomicAdd(p.dbeta + (static_cast<size_t>(b) * p.O + o) * p.C + c, accb[o]);
+  for (int j = 0; j < CPT; ++j) {
+    s1[j] = s2[j] = 0.f; d1[j] = d2[j] = 0.0;
+#pragma unroll
+    for (int o = 0; o < OMX; ++o) accg[o][j] = accb[o][j] = 0.f;
+  }
+  int since_flush = 0;
+  for (int base = p0 + wp * PIXG; base < p1; base += p.warps_p * PIXG) {
+    float part[32];
+    float invS_q[PIXG];
+#pragma unroll
+    for (int q = 0; q < PIXG; ++q) {
+      const int pix = base + q;
+      const bool ok = pix < p1 && c_ok;
+      const int pc = pix < p1 ? pix : p1 - 1;       // clamped: loads stay in bounds, contributions are zeroed
+      float xv[CPT], dv[CPT];
+      load_cpt<CPT>(xb + static_cast<size_t>(pc) * p.C, c_ok, xv);
+      if (rep == 1) {
+        load_cpt<CPT>(db + static_cast<size_t>(pc) * p.C, c_ok, dv);
+      } else {
+        const int hh = pc / p.W, ww = pc - hh * p.W;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) dv[j] = 0.f;
+        for (int dy = 0; dy < 2; ++dy)
+          for (int dx = 0; dx < 2; ++dx) {
+            float t[CPT];
+            load_cpt<CPT>(db + ((static_cast<size_t>(hh) * 2 + dy) * Wo + ww * 2 + dx) * p.C, c_ok, t);
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) dv[j] += t[j];
+          }
+      }
+      float m[OMX];
+      float invS = 1.0f;
+      if constexpr (OM > 0) invS = isla_masks<OM>(mb + static_cast<size_t>(pc) * p.O, p.O, m);
+      invS_q[q] = invS;
+      float g[CPT], gx[CPT], common = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const float xh = (xv[j] - L.mean[j]) * L.invstd[j];
+        float y, fac;
+        if constexpr (OM > 0) {
+          float G = 0.f, Bt = 0.f;
+#pragma unroll
+          for (int o = 0; o < OM; ++o) { G = fmaf(m[o], L.gam[o][j], G); Bt = fmaf(m[o], L.bet[o][j], Bt); }
+          y = isla_y(G, Bt, invS, xh);
+          fac = fmaf(G, invS, 1.0f);
+        } else {
+          y = fmaf(xh, L.aw[j], L.ab[j]);
+          fac = 1.0f;                                // csum of the affine form = (sum g, sum g*xh) = (d bias, d weight)
+        }
+        g[j] = (!ok || (p.relu && !(y > 0.f))) ? 0.f : dv[j];
+        gx[j] = g[j] * xh;
+        const float dxh = g[j] * fac;
+        s1[j] += dxh;
+        s2[j] = fmaf(dxh, xh, s2[j]);
+        // d m_o * S = sum_c (g xh gamma_oc + g beta_oc) - sum_c g (y - xh): the last term is the same for every object
+        common = fmaf(g[j], y - xh, common);
+      }
+      if constexpr (OM > 0) {
+#pragma unroll
+        for (int o = 0; o < OM; ++o) {
+          const float mo = m[o] * invS;
+          float acc = -common;
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) {
+            accg[o][j] = fmaf(gx[j], mo, accg[o][j]);
+            accb[o][j] = fmaf(g[j], mo, accb[o][j]);
+            acc = fmaf(gx[j], L.gam[o][j], fmaf(g[j], L.bet[o][j], acc));
+          }
+          part[q * OM + o] = acc;
+        }
+      }
     }
-  atomicAdd(p.csum + 2 * c, d1);
-  atomicAdd(p.csum + 2 * c + 1, d2);
-  (void)aw;
+    if constexpr (OM > 0) {
+      const float tot = warp_transpose_sum(part, lane);
+      const int q = lane / OM, o = lane - q * OM;
+      float invS = invS_q[0];
+#pragma unroll
+      for (int qq = 1; qq < PIXG; ++qq) if (q == qq) invS = invS_q[qq];
+      const int pix = base + q;
+      if (pix < p1 && o < p.O) atomicAdd(&sh[(pix - p0) * p.O + o], tot * invS);
+    }
+    if (++since_flush == 16) {                      // fold the fp32 running sums into fp64 every 16 * PIXG pixels
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; s1[j] = s2[j] = 0.f; }
+      since_flush = 0;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; }
+  __syncthreads();
+  // ---- dmask of this block's pixels
+  if constexpr (OM > 0) {
+    float* dm = p.dmask + (static_cast<size_t>(b) * hw + p0) * p.O;
+    if (gridDim.y == 1) {
+      for (int i = threadIdx.x; i < (p1 - p0) * p.O; i += blockDim.x) dm[i] = sh[i];
+    } else {
+      for (int i = threadIdx.x; i < (p1 - p0) * p.O; i += blockDim.x) atomicAdd(dm + i, sh[i]);
+    }
+    __syncthreads();
+  }
+  // ---- per-channel results: combine the block's pixel-lane warps in shared memory, one global atomic per value
+  double* s_cs = reinterpret_cast<double*>(sh);                       // [2][cb]
+  float* s_gb = reinterpret_cast<float*>(s_cs + 2 * cb);              // [2 * O][cb]
+  for (int i = threadIdx.x; i < 2 * cb; i += blockDim.x) s_cs[i] = 0.0;
+  if constexpr (OM > 0)
+    for (int i = threadIdx.x; i < 2 * p.O * cb; i += blockDim.x) s_gb[i] = 0.f;
+  __syncthreads();
+  if (c_ok) {
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      atomicAdd(&s_cs[cl + j], d1[j]);
+      atomicAdd(&s_cs[cb + cl + j], d2[j]);
+      if constexpr (OM > 0) {
+#pragma unroll
+        for (int o = 0; o < OM; ++o)
+          if (o < p.O) {
+            atomicAdd(&s_gb[(2 * o) * cb + cl + j], accg[o][j]);
+            atomicAdd(&s_gb[(2 * o + 1) * cb + cl + j], accb[o][j]);
+          }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cb; i += blockDim.x) {
+    const int ch = blockIdx.y * cb + i;
+    if (ch >= p.C) continue;
+    atomicAdd(p.csum + 2 * ch, s_cs[i]);
+    atomicAdd(p.csum + 2 * ch + 1, s_cs[cb + i]);
+    if constexpr (OM > 0) {
+      for (int o = 0; o < p.O; ++o) {
+        atomicAdd(p.dgamma + (static_cast<size_t>(b) * p.O + o) * p.C + ch, s_gb[(2 * o) * cb + i]);
+        atomicAdd(p.dbeta + (static_cast<size_t>(b) * p.O + o) * p.C + ch, s_gb[(2 * o + 1) * cb + i]);
+      }
+    }
+  }
 }
 
-// pass C: dx = (dxh - mean(dxh) - xh * mean(dxh * xh)) * invstd in place (dx holds dxh from pass A).
-// thread <-> (pixel, 4 channels); a pure streaming pass.
-__global__ void __launch_bounds__(256) isla_bwd_c_kernel(const IslaBwdParams p) {
-  const int cg = p.C >> 2;
-  const long long items = 1LL * p.B * p.H * p.W * cg;
-  for (long long it = 1LL * blockIdx.x * blockDim.x + threadIdx.x; it < items; it += 1LL * gridDim.x * blockDim.x) {
-    const int g4 = static_cast<int>(it % cg);
-    const long long gp = it / cg;
-    const int c = g4 * 4;
-    const float4 xv4 = __ldg(reinterpret_cast<const float4*>(p.x + gp * p.C + c));
-    const float4 dv4 = *reinterpret_cast<const float4*>(p.dx + gp * p.C + c);
-    const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w}, dv[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
-    float r[4];
+// ---- backward, pass 2: dx (x and dout are read a second time; g and dxh are recomputed, never stored)
+template <int OM, int CPT>
+__global__ void __launch_bounds__(256) isla_bwd_dx_kernel(const IslaBwdParams p) {
+  using Lane = IslaLane<OM, CPT>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wc = warp % p.warps_c, wp = warp / p.warps_c;
+  const int b = blockIdx.z;
+  const int c = ((blockIdx.y * p.warps_c + wc) * 32 + lane) * CPT;
+  if (c >= p.C) return;
+  Lane L;
+  L.load(p.mean_invstd, p.gamma, p.beta, p.aff_w, p.aff_b, b, c, p.C, p.O);
+  float m1[CPT], m2[CPT];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float mean = __ldg(p.mean_invstd + c + j), invstd = __ldg(p.mean_invstd + p.C + c + j);
-      const float xh = (xv[j] - mean) * invstd;
-      float dxh = dv[j];
-      if (p.train) {
-        double m1 = p.csum[2 * (c + j)], m2 = p.csum[2 * (c + j) + 1];
-        if (p.O == 0) {                  // csum holds (sum g, sum g*xh) = (d bias, d weight) of the affine form
-          const float scale = p.aff_w ? __ldg(p.aff_w + c + j) : 1.0f;
-          m1 *= scale; m2 *= scale;
-        }
-        dxh = dxh - static_cast<float>(m1 / p.count) - xh * static_cast<float>(m2 / p.count);
-      }
-      r[j] = dxh * invstd;
+  for (int j = 0; j < CPT; ++j) {
+    m1[j] = m2[j] = 0.f;
+    if (p.train) {
+      double a = p.csum[2 * (c + j)], q = p.csum[2 * (c + j) + 1];
+      if (OM == 0) { a *= L.aw[j]; q *= L.aw[j]; }     // csum holds (d bias, d weight); d xh = aff_w * g
+      m1[j] = static_cast<float>(a / p.count);
+      m2[j] = static_cast<float>(q / p.count);
     }
-    *reinterpret_cast<float4*>(p.dx + gp * p.C + c) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+  const int hw = p.H * p.W;
+  const int Wo = p.W << p.up;
+  const int rep = 1 << p.up;
+  const float* __restrict__ xb = p.x + static_cast<size_t>(b) * hw * p.C + c;
+  const float* __restrict__ db = p.dout + static_cast<size_t>(b) * hw * rep * rep * p.C + c;
+  const float* __restrict__ mb = p.mask ? p.mask + static_cast<size_t>(b) * hw * p.O : nullptr;
+  float* __restrict__ ob = p.dx + static_cast<size_t>(b) * hw * p.C + c;
+#pragma unroll 2
+  for (int pix = blockIdx.x * p.warps_p + wp; pix < hw; pix += gridDim.x * p.warps_p) {
+    float xv[CPT], dv[CPT];
+    load_cpt<CPT>(xb + static_cast<size_t>(pix) * p.C, true, xv);
+    if (rep == 1) {
+      load_cpt<CPT>(db + static_cast<size_t>(pix) * p.C, true, dv);
+    } else {
+      const int hh = pix / p.W, ww = pix - hh * p.W;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) dv[j] = 0.f;
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+          float t[CPT];
+          load_cpt<CPT>(db + ((static_cast<size_t>(hh) * 2 + dy) * Wo + ww * 2 + dx) * p.C, true, t);
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) dv[j] += t[j];
+        }
+    }
+    float m[Lane::OMX];
+    float invS = 1.0f;
+    if constexpr (OM > 0) invS = isla_masks<OM>(mb + static_cast<size_t>(pix) * p.O, p.O, m);
+    float r[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const float xh = (xv[j] - L.mean[j]) * L.invstd[j];
+      float y, fac;
+      if constexpr (OM > 0) {
+        float G = 0.f, Bt = 0.f;
+#pragma unroll
+        for (int o = 0; o < OM; ++o) { G = fmaf(m[o], L.gam[o][j], G); Bt = fmaf(m[o], L.bet[o][j], Bt); }
+        y = isla_y(G, Bt, invS, xh);
+        fac = fmaf(G, invS, 1.0f);
+      } else {
+        y = fmaf(xh, L.aw[j], L.ab[j]);
+        fac = L.aw[j];
+      }
+      const float g = (p.relu && !(y > 0.f)) ? 0.f : dv[j];
+      float dxh = g * fac;
+      if (p.train) dxh = dxh - m1[j] - xh * m2[j];
+      r[j] = dxh * L.invstd[j];
+    }
+    float* op = ob + static_cast<size_t>(pix) * p.C;
+    if constexpr (CPT == 2) *reinterpret_cast<float2*>(op) = make_float2(r[0], r[1]); else op[0] = r[0];
   }
 }
 
@@ -491,73 +601,84 @@ int isla_bwd(const float* x, const float* mean_invstd, const float* mask, const 
              const float* aff_w, const float* aff_b, const float* dout, int B, int H, int W, int C, int O, int relu,
              int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum, float* dx,
              int phase, double count, cudaStream_t stream) {
-  if (!x || !mean_invstd || !dout || !gbuf || !csum || !dx || B <= 0 || C <= 0 || (C & 3)) { set_error("isla_bwd: bad arguments (C must be a multiple of 4)"); return L2I_ERR_BAD_ARG; }
+  (void)gbuf;                  // no intermediate tensor is written any more; the argument is kept for ABI stability
+  if (!x || !mean_invstd || !dout || !csum || !dx || B <= 0 || C <= 0) { set_error("isla_bwd: bad arguments"); return L2I_ERR_BAD_ARG; }
   if (O > 0 && (!mask || !gamma || !beta || !dmask || !dgamma || !dbeta)) { set_error("isla_bwd: null ISLA operand"); return L2I_ERR_BAD_ARG; }
-  if (O > 48) { set_error("isla_bwd: at most 48 objects per image supported"); return L2I_ERR_UNSUPPORTED; }
+  if (O > 32) { set_error("isla_bwd: at most 32 objects per image supported"); return L2I_ERR_UNSUPPORTED; }
+  if (phase < 0 || phase > 2) { set_error("isla_bwd: phase must be 0 (all), 1 (reductions) or 2 (dx)"); return L2I_ERR_BAD_ARG; }
   IslaBwdParams p;
   p.x = x; p.mean_invstd = mean_invstd; p.mask = mask; p.gamma = gamma; p.beta = beta; p.aff_w = aff_w; p.aff_b = aff_b;
-  p.dout = dout; p.gbuf = gbuf; p.dmask = dmask; p.dgamma = dgamma; p.dbeta = dbeta; p.csum = csum; p.dx = dx;
+  p.dout = dout; p.dmask = dmask; p.dgamma = dgamma; p.dbeta = dbeta; p.csum = csum; p.dx = dx;
   p.count = count > 0 ? count : static_cast<double>(B) * H * W;   // > 0: global count of a cross-rank batch norm
-  if (phase < 0 || phase > 2) { set_error("isla_bwd: phase must be 0 (all), 1 (reductions) or 2 (dx)"); return L2I_ERR_BAD_ARG; }
-  p.B = B; p.H = H; p.W = W; p.C = C; p.O = O; p.relu = relu; p.up = up2 ? 1 : 0; p.train = train;
-  const long long pixels = 1LL * B * H * W;
-  if (phase == 2) {            // csum has been reduced across ranks by the caller; dx holds Gamma * g from phase 1
-    const long long items = pixels * (C >> 2);
-    long long blocks = (items + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    isla_bwd_c_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p);
-    return check_launch("isla_bwd_c_kernel");
-  }
-  cudaError_t e = cudaMemsetAsync(csum, 0, sizeof(double) * 2 * C, stream);
-  if (e == cudaSuccess && O > 0) e = cudaMemsetAsync(dgamma, 0, sizeof(float) * B * O * C, stream);
-  if (e == cudaSuccess && O > 0) e = cudaMemsetAsync(dbeta, 0, sizeof(float) * B * O * C, stream);
-  if (e != cudaSuccess) { set_error("isla_bwd: memset: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
-  {
-    long long blocks = (pixels + 7) / 8;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    // lanes per pixel: each lane should own >= 4 float4 channel groups, so that the per-pixel shuffle reduction
-    // of the O mask gradients is amortised (C = 64 -> 4 lanes, 8 pixels per warp; C >= 512 -> a whole warp)
-    int lpp = C / 16;
-    lpp = lpp < 4 ? 4 : (lpp > 32 ? 32 : lpp);
-    while (lpp & (lpp - 1)) lpp &= lpp - 1;              // power of two
-    blocks = (pixels * lpp / 32 + 7) / 8;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    if (blocks < 1) blocks = 1;
-    const int nb = static_cast<int>(blocks);
-#define L2I_ISLA_A(OM)                                                                   \
-    switch (lpp) {                                                                       \
-      case 4: isla_bwd_a_kernel<OM, 4><<<nb, 256, 0, stream>>>(p); break;                \
-      case 8: isla_bwd_a_kernel<OM, 8><<<nb, 256, 0, stream>>>(p); break;                \
-      case 16: isla_bwd_a_kernel<OM, 16><<<nb, 256, 0, stream>>>(p); break;              \
-      default: isla_bwd_a_kernel<OM, 32><<<nb, 256, 0, stream>>>(p); break;              \
+  p.B = B; p.H = H; p.W = W; p.C = C; p.O = O; p.relu = relu; p.up = up2 ? 1 : 0; p.train = train; p.seg = 0;
+  const int hw = H * W;
+  if (phase != 2) {
+    // ---- pass 1
+    const int cpt = ((C & 1) == 0 && O <= 8) ? 2 : 1;
+    int chunks;
+    isla_shape(C, cpt, &p.warps_c, &p.warps_p, &chunks);
+    const int cb = 32 * cpt * p.warps_c;
+    cudaError_t e = cudaMemsetAsync(csum, 0, sizeof(double) * 2 * C, stream);
+    if (e == cudaSuccess && O > 0) e = cudaMemsetAsync(dgamma, 0, sizeof(float) * B * O * C, stream);
+    if (e == cudaSuccess && O > 0) e = cudaMemsetAsync(dbeta, 0, sizeof(float) * B * O * C, stream);
+    if (e == cudaSuccess && O > 0 && chunks > 1) e = cudaMemsetAsync(dmask, 0, sizeof(float) * B * hw * O, stream);
+    if (e != cudaSuccess) { set_error("isla_bwd: memset: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
+    // pixels per block: ~4 blocks per SM over the launch, at least 8 butterflies per pixel-lane warp, bounded by the
+    // shared-memory dmask accumulator (seg * O floats <= 32 KB)
+    const int pixg = O > 0 ? 32 / (O <= 8 ? 8 : (O <= 16 ? 16 : 32)) : 1;
+    long long want_blocks = (148LL * 4 + 1LL * B * chunks - 1) / (1LL * B * chunks);
+    int seg = static_cast<int>((hw + want_blocks - 1) / want_blocks);
+    const int min_seg = p.warps_p * pixg * 8;
+    if (seg < min_seg) seg = min_seg;
+    const int max_seg = O > 0 ? 8192 / O : 1 << 20;
+    if (seg > max_seg) seg = max_seg;
+    if (seg > hw) seg = hw;
+    p.seg = seg;
+    const size_t smem_dm = sizeof(float) * seg * (O > 0 ? O : 0);
+    const size_t smem_red = sizeof(double) * 2 * cb + sizeof(float) * 2 * O * cb;
+    const size_t smem = smem_dm > smem_red ? smem_dm : smem_red;
+    dim3 grid((hw + seg - 1) / seg, chunks, B);
+    const int threads = 32 * p.warps_c * p.warps_p;
+    static DeviceOnce configured;
+    if (configured.need()) {
+      cudaFuncSetAttribute(isla_bwd_reduce_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(isla_bwd_reduce_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      configured.done();
     }
-    if (O <= 8) { L2I_ISLA_A(8) } else if (O <= 16) { L2I_ISLA_A(16) } else { L2I_ISLA_A(48) }
-#undef L2I_ISLA_A
-    int rc = check_launch("isla_bwd_a_kernel");
+    if (O == 0) {
+      if (cpt == 2) isla_bwd_reduce_kernel<0, 2><<<grid, threads, smem, stream>>>(p); else isla_bwd_reduce_kernel<0, 1><<<grid, threads, smem, stream>>>(p);
+    } else if (O <= 8) {
+      if (cpt == 2) isla_bwd_reduce_kernel<8, 2><<<grid, threads, smem, stream>>>(p); else isla_bwd_reduce_kernel<8, 1><<<grid, threads, smem, stream>>>(p);
+    } else if (O <= 16) {
+      isla_bwd_reduce_kernel<16, 1><<<grid, threads, smem, stream>>>(p);
+    } else {
+      isla_bwd_reduce_kernel<32, 1><<<grid, threads, smem, stream>>>(p);
+    }
+    int rc = check_launch("isla_bwd_reduce_kernel");
     if (rc) return rc;
+    if (phase == 1) return L2I_OK;
   }
   {
-    const int threads = C <= 64 ? 64 : 128;
-    const int chunks = (C + threads - 1) / threads;
-    const long long base = 1LL * B * chunks * threads;
-    int segs = static_cast<int>((148LL * 1024 + base - 1) / base);
-    const int hw = H * W;
-    if (segs > (hw + 15) / 16) segs = (hw + 15) / 16;
-    if (segs < 1) segs = 1;
-    dim3 grid(segs, chunks, B);
-    if (O <= 8) isla_bwd_b_kernel<8><<<grid, threads, 0, stream>>>(p);
-    else if (O <= 16) isla_bwd_b_kernel<16><<<grid, threads, 0, stream>>>(p);
-    else isla_bwd_b_kernel<48><<<grid, threads, 0, stream>>>(p);
-    int rc = check_launch("isla_bwd_b_kernel");
-    if (rc) return rc;
-  }
-  if (phase == 1) return L2I_OK;
-  {
-    const long long items = pixels * (C >> 2);
-    long long blocks = (items + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    isla_bwd_c_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(p);
-    return check_launch("isla_bwd_c_kernel");
+    // ---- pass 2 (phase 2: csum has been reduced across ranks by the caller)
+    const int cpt = ((C & 1) == 0 && O <= 16) ? 2 : 1;
+    int chunks;
+    isla_shape(C, cpt, &p.warps_c, &p.warps_p, &chunks);
+    long long bx = (hw + p.warps_p * 4 - 1) / (p.warps_p * 4);
+    const long long cap = (148LL * 12 + 1LL * B * chunks - 1) / (1LL * B * chunks);
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid(static_cast<int>(bx), chunks, B);
+    const int threads = 32 * p.warps_c * p.warps_p;
+    if (O == 0) {
+      if (cpt == 2) isla_bwd_dx_kernel<0, 2><<<grid, threads, 0, stream>>>(p); else isla_bwd_dx_kernel<0, 1><<<grid, threads, 0, stream>>>(p);
+    } else if (O <= 8) {
+      if (cpt == 2) isla_bwd_dx_kernel<8, 2><<<grid, threads, 0, stream>>>(p); else isla_bwd_dx_kernel<8, 1><<<grid, threads, 0, stream>>>(p);
+    } else if (O <= 16) {
+      if (cpt == 2) isla_bwd_dx_kernel<16, 2><<<grid, threads, 0, stream>>>(p); else isla_bwd_dx_kernel<16, 1><<<grid, threads, 0, stream>>>(p);
+    } else {
+      isla_bwd_dx_kernel<32, 1><<<grid, threads, 0, stream>>>(p);
+    }
+    return check_launch("isla_bwd_dx_kernel");
   }
 }
 

@@ -80,6 +80,29 @@ int sn_sigma(const float* W, int R, int Cc, float* u, float* v, int training, fl
 int sn_weight_grad(const float* G, const float* W, const float* u, const float* v, const float* sigma, int R, int cin,
                    int taps, float* dW, float* scratch, cudaStream_t stream);
 
+// Grouped spectral norm + weight preparation: one table entry per module of a network (72 bytes; include/l2i.h).
+struct SnEntry {
+  const float* W;        // weight_orig (or the plain weight when has_sn = 0), [R, Cc] / torch layout [cout][cin][kh][kw]
+  float* u;              // [R]  (updated in place when training)
+  float* v;              // [Cc]
+  long long f32_off;     // this module's slice of the per-call fp32 buffer (floats): sigma, u_used, v_used, t, s
+  long long bf_off;      // this module's slice of the per-call bf16 buffer (elements), < 0: no operand pairs wanted
+  int R, Cc;
+  float eps;
+  int training, has_sn;
+  int cin, taps;         // conv geometry for the operand pairs (cout = R)
+  int pad_;
+};
+__host__ __device__ inline long long sn_pad4(long long x) { return (x + 3) & ~3LL; }
+__host__ __device__ inline long long sn_off_u() { return 4; }                                    // sigma at 0
+__host__ __device__ inline long long sn_off_v(int R, int Cc) { return 4 + sn_pad4(R); }
+__host__ __device__ inline long long sn_off_t(int R, int Cc) { return 4 + sn_pad4(R) + sn_pad4(Cc); }
+__host__ __device__ inline long long sn_off_s(int R, int Cc) { return 4 + sn_pad4(R) + 2 * sn_pad4(Cc); }
+int sn_group_sigma(const void* table, int n_modules, const int* wt_items, int n_wt, int wt_smem_floats, const int* wv_items,
+                   int n_wv, int max_cc, float* f32, long long f32_floats, cudaStream_t stream);
+int weight_prep_group(const void* table, const int* items9, int n9, const int* items1, int n1, const float* f32, void* bf16,
+                      int want_dgrad, cudaStream_t stream);
+
 // optim.cu
 struct AdamTensor {       // one entry of the device-resident tensor table (48 bytes, see include/l2i.h)
   float* p;

@@ -15,13 +15,12 @@ namespace l2i {
 // in 64-byte runs (32 consecutive bf16 along Cin for the forward operand, along Cout for the dgrad operand).
 static constexpr int kWpTile = 32;
 template <int taps>
-__global__ void __launch_bounds__(256)
-weight_prep_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int cout, int cin,
-                   __nv_bfloat16* __restrict__ f_hi, __nv_bfloat16* __restrict__ f_lo, int cin_pad,
-                   __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo, int cout_pad) {
-  extern __shared__ float tile[];                         // [32][32 * taps + 1]
+__device__ __forceinline__ void weight_prep_body(const float* __restrict__ w, const float* __restrict__ sigma, int cout, int cin,
+                                                 __nv_bfloat16* __restrict__ f_hi, __nv_bfloat16* __restrict__ f_lo, int cin_pad,
+                                                 __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo, int cout_pad,
+                                                 int tile_x, int tile_y, float* tile) {
   const int pitch = kWpTile * taps + 1;
-  const int ci0 = blockIdx.x * kWpTile, co0 = blockIdx.y * kWpTile;
+  const int ci0 = tile_x * kWpTile, co0 = tile_y * kWpTile;
   const float inv = sigma ? 1.0f / __ldg(sigma) : 1.0f;
   const int nci = max(0, min(kWpTile, cin - ci0));        // valid input channels in this tile
   for (int i = threadIdx.x; i < kWpTile * kWpTile * taps; i += blockDim.x) {
@@ -61,6 +60,65 @@ weight_prep_kernel(const float* __restrict__ w, const float* __restrict__ sigma,
       *reinterpret_cast<uint32_t*>(d_lo + o) = pack_bf16x2(al, bl);
     }
   }
+}
+template <int taps>
+__global__ void __launch_bounds__(256)
+weight_prep_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int cout, int cin,
+                   __nv_bfloat16* __restrict__ f_hi, __nv_bfloat16* __restrict__ f_lo, int cin_pad,
+                   __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo, int cout_pad) {
+  extern __shared__ float tile[];                         // [32][32 * taps + 1]
+  weight_prep_body<taps>(w, sigma, cout, cin, f_hi, f_lo, cin_pad, d_hi, d_lo, cout_pad, blockIdx.x, blockIdx.y, tile);
+}
+
+// Channel padding of an operand pair (must match layout2img_b200/ops.py pad8): a multiple of 8; counts <= 8 are padded
+// to a full 64-wide K chunk and tails <= 40 of a 64-chunk are rounded up (TMA boxes that are mostly out of bounds in the
+// channel dimension are slow).
+__host__ __device__ inline int wp_pad8(int c) {
+  if (c <= 8) return 64;
+  const int c8 = (c + 7) / 8 * 8, tail = c8 % 64;
+  return (tail > 0 && tail <= 40) ? c8 + (64 - tail) : c8;
+}
+// Elements of one half (hi or lo) of the forward / data-gradient operand, rounded to 64 elements (128 B) so that every
+// slice of the per-call bf16 buffer satisfies TMA's global-address alignment.
+__host__ __device__ inline long long wp_fwd_elems(int cout, int cin, int taps) { return ((1LL * cout * taps * wp_pad8(cin)) + 63) & ~63LL; }
+__host__ __device__ inline long long wp_dg_elems(int cout, int cin, int taps) { return ((1LL * cin * taps * wp_pad8(cout)) + 63) & ~63LL; }
+
+// Grouped form: the operand pairs of EVERY convolution weight of a network call in one launch per tap count.  items:
+// (module, tile_x, tile_y).  The module's slice of the bf16 buffer holds f_hi, f_lo, then (want_dgrad) d_hi, d_lo.
+template <int taps>
+__global__ void __launch_bounds__(256)
+weight_prep_group_kernel(const SnEntry* __restrict__ tab, const int4* __restrict__ items, const float* __restrict__ f32,
+                         __nv_bfloat16* __restrict__ bf, int want_dgrad) {
+  extern __shared__ float tile[];
+  const int4 it = items[blockIdx.x];
+  const SnEntry e = tab[it.x];
+  const int cout = e.R, cin = e.cin;
+  const long long nf = wp_fwd_elems(cout, cin, taps), nd = wp_dg_elems(cout, cin, taps);
+  __nv_bfloat16* f_hi = bf + e.bf_off;
+  __nv_bfloat16* f_lo = f_hi + nf;
+  __nv_bfloat16* d_hi = want_dgrad ? f_lo + nf : nullptr;
+  __nv_bfloat16* d_lo = want_dgrad ? d_hi + nd : nullptr;
+  weight_prep_body<taps>(e.W, e.has_sn ? f32 + e.f32_off : nullptr, cout, cin, f_hi, f_lo, wp_pad8(cin), d_hi, d_lo,
+                         wp_pad8(cout), it.y, it.z, tile);
+}
+
+int weight_prep_group(const void* table, const int* items9, int n9, const int* items1, int n1, const float* f32, void* bf16,
+                      int want_dgrad, cudaStream_t stream) {
+  if (!table || !bf16 || (n9 > 0 && !items9) || (n1 > 0 && !items1)) { set_error("weight_prep_group: bad arguments"); return L2I_ERR_BAD_ARG; }
+  const SnEntry* tab = reinterpret_cast<const SnEntry*>(table);
+  __nv_bfloat16* bf = reinterpret_cast<__nv_bfloat16*>(bf16);
+  int rc;
+  if (n9 > 0) {
+    weight_prep_group_kernel<9><<<n9, 256, sizeof(float) * kWpTile * (kWpTile * 9 + 1), stream>>>(
+        tab, reinterpret_cast<const int4*>(items9), f32, bf, want_dgrad);
+    if ((rc = check_launch("weight_prep_group_kernel<9>"))) return rc;
+  }
+  if (n1 > 0) {
+    weight_prep_group_kernel<1><<<n1, 256, sizeof(float) * kWpTile * (kWpTile * 1 + 1), stream>>>(
+        tab, reinterpret_cast<const int4*>(items1), f32, bf, want_dgrad);
+    if ((rc = check_launch("weight_prep_group_kernel<1>"))) return rc;
+  }
+  return L2I_OK;
 }
 
 int weight_prep(const float* w, const float* sigma, int cout, int cin, int taps, void* f_hi, void* f_lo, int cin_pad,

@@ -29,14 +29,12 @@ __device__ __forceinline__ float block_sum(float v, float* red) {   // blockDim.
   return red[0];
 }
 
-// t[c] (+)= sum_{r in split} W[r,c] * u[r]
-__global__ void __launch_bounds__(256) sn_wt_u_kernel(const float* __restrict__ W, const float* __restrict__ u, int R, int Cc,
-                                                      int rows_per_split, float* __restrict__ t) {
-  extern __shared__ float s_u[];
-  const int r0 = blockIdx.y * rows_per_split, r1 = min(R, r0 + rows_per_split);
+// t[c] (+)= sum_{r in [r0, r1)} W[r,c] * u[r] for the 256 columns of column block `cb`
+__device__ __forceinline__ void sn_wt_u_body(const float* __restrict__ W, const float* __restrict__ u, int Cc, int r0, int r1,
+                                             int cb, float* __restrict__ t, float* s_u) {
   for (int i = threadIdx.x; i < r1 - r0; i += blockDim.x) s_u[i] = __ldg(u + r0 + i);
   __syncthreads();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = cb * blockDim.x + threadIdx.x;
   if (c >= Cc) return;
   float acc = 0.f;
   const float* wp = W + static_cast<size_t>(r0) * Cc + c;
@@ -44,12 +42,17 @@ __global__ void __launch_bounds__(256) sn_wt_u_kernel(const float* __restrict__ 
   for (int r = r0; r < r1; ++r, wp += Cc) acc = fmaf(__ldg(wp), s_u[r - r0], acc);
   atomicAdd(t + c, acc);
 }
+__global__ void __launch_bounds__(256) sn_wt_u_kernel(const float* __restrict__ W, const float* __restrict__ u, int R, int Cc,
+                                                      int rows_per_split, float* __restrict__ t) {
+  extern __shared__ float s_u[];
+  const int r0 = blockIdx.y * rows_per_split, r1 = min(R, r0 + rows_per_split);
+  sn_wt_u_body(W, u, Cc, r0, r1, blockIdx.x, t, s_u);
+}
 
 // v = normalize_v ? t / max(|t|, eps) : t;  s[r] = W[r,:] . v  (one warp per row);  block 0 also stores v
-__global__ void __launch_bounds__(256) sn_w_v_kernel(const float* __restrict__ W, const float* __restrict__ t, int R, int Cc,
-                                                     int normalize_v, float eps, float* __restrict__ v_out,
-                                                     float* __restrict__ v_out2, float* __restrict__ s) {
-  extern __shared__ float s_v[];          // [Cc] + 32
+__device__ __forceinline__ void sn_w_v_body(const float* __restrict__ W, const float* __restrict__ t, int R, int Cc,
+                                            int normalize_v, float eps, float* __restrict__ v_out,
+                                            float* __restrict__ v_out2, float* __restrict__ s, int row_block, float* s_v) {
   float* red = s_v + Cc;
   float inv = 1.f;
   if (normalize_v) {
@@ -61,14 +64,14 @@ __global__ void __launch_bounds__(256) sn_w_v_kernel(const float* __restrict__ W
   for (int i = threadIdx.x; i < Cc; i += blockDim.x) {
     const float x = __ldg(t + i) * inv;
     s_v[i] = x;
-    if (blockIdx.x == 0) {
+    if (row_block == 0) {
       if (v_out) v_out[i] = x;
       if (v_out2) v_out2[i] = x;
     }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int r = row_block * (blockDim.x >> 5) + warp;
   if (r >= R) return;
   const float* wp = W + static_cast<size_t>(r) * Cc;
   float acc = 0.f;
@@ -76,12 +79,17 @@ __global__ void __launch_bounds__(256) sn_w_v_kernel(const float* __restrict__ W
   acc = warp_sum(acc);
   if (lane == 0) s[r] = acc;
 }
+__global__ void __launch_bounds__(256) sn_w_v_kernel(const float* __restrict__ W, const float* __restrict__ t, int R, int Cc,
+                                                     int normalize_v, float eps, float* __restrict__ v_out,
+                                                     float* __restrict__ v_out2, float* __restrict__ s) {
+  extern __shared__ float s_v[];          // [Cc] + 32
+  sn_w_v_body(W, t, R, Cc, normalize_v, eps, v_out, v_out2, s, blockIdx.x, s_v);
+}
 
 // update_u: u = s / max(|s|, eps) (stored to u_out and u_out2);  sigma = u . s
-__global__ void __launch_bounds__(1024) sn_finish_kernel(const float* __restrict__ s, const float* __restrict__ u_in, int R,
-                                                         int update_u, float eps, float* __restrict__ u_out,
-                                                         float* __restrict__ u_out2, float* __restrict__ sigma) {
-  __shared__ float red[32];
+__device__ __forceinline__ void sn_finish_body(const float* __restrict__ s, const float* __restrict__ u_in, int R,
+                                               int update_u, float eps, float* __restrict__ u_out,
+                                               float* __restrict__ u_out2, float* __restrict__ sigma, float* red) {
   float inv = 1.f;
   if (update_u) {
     float q = 0.f;
@@ -98,6 +106,66 @@ __global__ void __launch_bounds__(1024) sn_finish_kernel(const float* __restrict
   }
   d = block_sum(d, red);
   if (threadIdx.x == 0) *sigma = d;
+}
+__global__ void __launch_bounds__(1024) sn_finish_kernel(const float* __restrict__ s, const float* __restrict__ u_in, int R,
+                                                         int update_u, float eps, float* __restrict__ u_out,
+                                                         float* __restrict__ u_out2, float* __restrict__ sigma) {
+  __shared__ float red[32];
+  sn_finish_body(s, u_in, R, update_u, eps, u_out, u_out2, sigma, red);
+}
+
+// ---- grouped forms: one launch per phase for ALL spectrally normalised modules of a network call.  `tab` is the
+// device table of SnEntry (kernels.h), `items` the static work list of the phase, `f32` the per-call fp32 buffer that
+// receives every module's (sigma, u_used, v_used) and holds its scratch (t, s) at the entry's offsets.
+__global__ void __launch_bounds__(256) sn_wt_u_group_kernel(const SnEntry* __restrict__ tab, const int4* __restrict__ items,
+                                                            float* __restrict__ f32) {
+  extern __shared__ float s_u[];
+  const int4 it = items[blockIdx.x];                  // (module, column block, r0, r1)
+  const SnEntry e = tab[it.x];
+  if (!e.has_sn || !e.training) return;
+  sn_wt_u_body(e.W, e.u, e.Cc, it.z, it.w, it.y, f32 + e.f32_off + sn_off_t(e.R, e.Cc), s_u);
+}
+__global__ void __launch_bounds__(256) sn_w_v_group_kernel(const SnEntry* __restrict__ tab, const int2* __restrict__ items,
+                                                           float* __restrict__ f32) {
+  extern __shared__ float s_v[];
+  const int2 it = items[blockIdx.x];                  // (module, row block)
+  const SnEntry e = tab[it.x];
+  if (!e.has_sn) return;
+  float* base = f32 + e.f32_off;
+  sn_w_v_body(e.W, e.training ? base + sn_off_t(e.R, e.Cc) : e.v, e.R, e.Cc, e.training, e.eps, e.training ? e.v : nullptr,
+              base + sn_off_v(e.R, e.Cc), base + sn_off_s(e.R, e.Cc), it.y, s_v);
+}
+__global__ void __launch_bounds__(1024) sn_finish_group_kernel(const SnEntry* __restrict__ tab, float* __restrict__ f32) {
+  __shared__ float red[32];
+  const SnEntry e = tab[blockIdx.x];
+  if (!e.has_sn) return;
+  float* base = f32 + e.f32_off;
+  sn_finish_body(base + sn_off_s(e.R, e.Cc), e.u, e.R, e.training, e.eps, e.u, base + sn_off_u(), base, red);
+}
+
+int sn_group_sigma(const void* table, int n_modules, const int* wt_items, int n_wt, int wt_smem_floats, const int* wv_items,
+                   int n_wv, int max_cc, float* f32, long long f32_floats, cudaStream_t stream) {
+  if (!table || n_modules <= 0 || !f32 || f32_floats <= 0 || max_cc > 40000) { set_error("sn_group_sigma: bad arguments"); return L2I_ERR_BAD_ARG; }
+  cudaError_t e = cudaMemsetAsync(f32, 0, sizeof(float) * f32_floats, stream);      // zeroes every module's t accumulator
+  if (e != cudaSuccess) { set_error("sn_group_sigma: memset: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
+  static DeviceOnce configured;
+  if (configured.need()) {
+    cudaFuncSetAttribute(sn_w_v_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40032 * 4);
+    configured.done();
+  }
+  const SnEntry* tab = reinterpret_cast<const SnEntry*>(table);
+  int rc;
+  if (n_wt > 0) {
+    sn_wt_u_group_kernel<<<n_wt, 256, sizeof(float) * wt_smem_floats, stream>>>(tab, reinterpret_cast<const int4*>(wt_items), f32);
+    if ((rc = check_launch("sn_wt_u_group_kernel"))) return rc;
+  }
+  if (n_wv > 0) {
+    sn_w_v_group_kernel<<<n_wv, 256, sizeof(float) * (max_cc + 32), stream>>>(tab, reinterpret_cast<const int2*>(wv_items), f32);
+    if ((rc = check_launch("sn_w_v_group_kernel"))) return rc;
+    sn_finish_group_kernel<<<n_modules, 1024, 0, stream>>>(tab, f32);
+    if ((rc = check_launch("sn_finish_group_kernel"))) return rc;
+  }
+  return L2I_OK;
 }
 
 int sn_sigma(const float* W, int R, int Cc, float* u, float* v, int training, float eps, float* u_used, float* v_used,
@@ -192,3 +260,5 @@ int sn_weight_grad(const float* G, const float* W, const float* u, const float* 
 }
 
 }  // namespace l2i
+
+static_assert(sizeof(l2i::SnEntry) == 72, "SnEntry layout is part of the C ABI (include/l2i.h)");

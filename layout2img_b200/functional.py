@@ -8,10 +8,34 @@ from __future__ import annotations
 import torch
 
 from . import ops
+from .sn_group import take_prepared
 
 
 def _c(t):
     return t if t is None or t.is_contiguous() else t.contiguous()
+
+
+def _sigma(weight, sn):
+    """SNState of a spectrally normalised weight (sn = (u, v, eps, training)) or None: taken from the network-level
+    grouped launch (sn_group.SNGroup.prepare) when this forward prepared it, else computed by the per-module kernels."""
+    pre = take_prepared(weight)
+    if pre is not None and (pre[0] is not None) == (sn is not None):
+        return pre[0]
+    return ops.sn_sigma(_c(weight), sn[0], sn[1], training=sn[3], eps=sn[2]) if sn else None
+
+
+def _sigma_and_prep(weight, sn, need_dgrad):
+    """(SNState | None, WeightPair) of a convolution weight, from the grouped launch when available.  The power
+    iteration must run exactly once per module call: a prepared state is always used; only missing operand pairs
+    (e.g. the data-gradient pair after a no-grad preparation) are produced here."""
+    pre = take_prepared(weight)
+    if pre is not None and (pre[0] is not None) == (sn is not None):
+        st, wp = pre
+        if wp is None or (need_dgrad and wp.d_hi is None):
+            wp = ops.conv_weight_prep(_c(weight), st.sigma if st else None, need_dgrad=need_dgrad)
+        return st, wp
+    st = ops.sn_sigma(_c(weight), sn[0], sn[1], training=sn[3], eps=sn[2]) if sn else None
+    return st, ops.conv_weight_prep(_c(weight), st.sigma if st else None, need_dgrad=need_dgrad)
 
 
 def _dw_to_torch(dw, cout, cin, taps):
@@ -36,8 +60,7 @@ class ConvFn(torch.autograd.Function):
         cout, cin, kh, kw = weight.shape
         taps = kh * kw
         xp = ops.act_split(x, relu=relu_in, up2=up2_in)
-        st = ops.sn_sigma(_c(weight), sn[0], sn[1], training=sn[3], eps=sn[2]) if sn else None
-        wp = ops.conv_weight_prep(_c(weight), st.sigma if st else None, need_dgrad=ctx.needs_input_grad[0])
+        st, wp = _sigma_and_prep(weight, sn, ctx.needs_input_grad[0])
         out, _ = ops.conv2d_fwd(xp, wp.f_hi, wp.f_lo, cout, taps, bias=_c(bias), residual=_c(residual), res_up2=res_up2)
         ctx.save_for_backward(xp.hi, xp.lo, wp.d_hi, wp.d_lo, weight, *(st or (None, None, None)))
         ctx.meta = (cout, cin, taps, relu_in, up2_in, res_up2, bias is not None, residual is not None)
@@ -92,17 +115,14 @@ class DBlockFn(torch.autograd.Function):
         a0, s0 = ops.act_split2(x, relu_a=not optimized, b_mode=(2 if down else 1) if has_sc else 0)
         c1, cin = w1.shape[0], w1.shape[1]
         c2 = w2.shape[0]
-        st1 = ops.sn_sigma(_c(w1), *sn1[:2], training=sn1[3], eps=sn1[2]) if sn1 else None
-        st2 = ops.sn_sigma(_c(w2), *sn2[:2], training=sn2[3], eps=sn2[2]) if sn2 else None
-        stsc = ops.sn_sigma(_c(wsc), *snsc[:2], training=snsc[3], eps=snsc[2]) if (snsc and has_sc) else None
-        wp1 = ops.conv_weight_prep(_c(w1), st1.sigma if st1 else None, need_dgrad=need_dx)
-        wp2 = ops.conv_weight_prep(_c(w2), st2.sigma if st2 else None, need_dgrad=True)
+        st1, wp1 = _sigma_and_prep(w1, sn1, need_dx)
+        st2, wp2 = _sigma_and_prep(w2, sn2, True)
         _, a1 = ops.conv2d_fwd(a0, wp1.f_hi, wp1.f_lo, c1, 9, bias=_c(b1), want_f32=False, want_pair=True, relu_pair=True)
         if has_sc:
-            wps = ops.conv_weight_prep(_c(wsc), stsc.sigma if stsc else None, need_dgrad=need_dx)
+            stsc, wps = _sigma_and_prep(wsc, snsc, need_dx)
             sc, _ = ops.conv2d_fwd(s0, wps.f_hi, wps.f_lo, c2, 1, bias=_c(bsc))
         else:
-            wps, sc = None, x
+            stsc, wps, sc = None, None, x
         out, _ = ops.conv2d_fwd(a1, wp2.f_hi, wp2.f_lo, c2, 9, bias=_c(b2), residual=sc, pool=1 if down else 0)
         none3 = (None, None, None)
         ctx.save_for_backward(a0.hi, a0.lo, s0.hi if has_sc else None, s0.lo if has_sc else None, a1.hi, a1.lo,
@@ -174,7 +194,7 @@ class SNLinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w_orig, bias, u, v, eps, training):
-        st = ops.sn_sigma(_c(w_orig), u, v, training, eps)
+        st = _sigma(w_orig, (u, v, eps, training))
         x2 = x.reshape(-1, x.shape[-1])
         y = (x2 @ w_orig.t()) / st.sigma
         if bias is not None:
@@ -206,7 +226,7 @@ class SNWeightFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, w_orig, u, v, eps, training):
-        st = ops.sn_sigma(_c(w_orig), u, v, training, eps)
+        st = _sigma(w_orig, (u, v, eps, training))
         ctx.save_for_backward(w_orig, st.sigma, st.u, st.v)
         return w_orig / st.sigma
 
@@ -269,12 +289,9 @@ class GBlockFn(torch.autograd.Function):
             rm, rv, training, momentum, eps = bn
             return ops.bn_batch_stats(t, rm, rv, eps, momentum) if training else ops.bn_eval_stats(rm, rv, eps)
 
-        st1 = ops.sn_sigma(_c(w1), *sn1[:2], training=sn1[3], eps=sn1[2]) if sn1 else None
-        st2 = ops.sn_sigma(_c(w2), *sn2[:2], training=sn2[3], eps=sn2[2]) if sn2 else None
-        stsc = ops.sn_sigma(_c(wsc), *snsc[:2], training=snsc[3], eps=snsc[2]) if snsc else None
-        wp1 = ops.conv_weight_prep(_c(w1), st1.sigma if st1 else None, need_dgrad=True)
-        wp2 = ops.conv_weight_prep(_c(w2), st2.sigma if st2 else None, need_dgrad=True)
-        wps = ops.conv_weight_prep(_c(wsc), stsc.sigma if stsc else None, need_dgrad=True)
+        st1, wp1 = _sigma_and_prep(w1, sn1, True)
+        st2, wp2 = _sigma_and_prep(w2, sn2, True)
+        stsc, wps = _sigma_and_prep(wsc, snsc, True)
         mi1 = stats(x, bn1)
         _, a0 = ops.isla_fwd(x, mi1, mask1, gamma1, beta1, None, None, relu=True, up2=True)
         h1, _ = ops.conv2d_fwd(a0, wp1.f_hi, wp1.f_lo, ch, 9, bias=_c(b1))
@@ -334,11 +351,12 @@ def g_block(x, mask1, gamma1, beta1, mask2, gamma2, beta2, conv1, conv2, c_sc, b
 class NormConvFn(torch.autograd.Function):
     """y = conv(up2?(relu(norm(x))), W) + bias + residual with norm = ISLA (mask_pm given) or affine/plain
     batch norm (mask_pm None).  reference: ResBlock.residual resnet_generator_app_v2.py:653-663,
-    SpatialAdaptiveSynBatchNorm2d norm_module.py:163-186, `final` :416-419, mask heads :645-651."""
+    SpatialAdaptiveSynBatchNorm2d norm_module.py:163-186, `final` :416-419, mask heads :645-651.
+    sn = None (weight is the weight itself) or (u, v, eps, training): weight is weight_orig (spectral norm in-kernel)."""
 
     @staticmethod
     def forward(ctx, x, mask_pm, gamma, beta, aff_w, aff_b, weight, bias, residual, running_mean, running_var,
-                training, momentum, eps, up2, res_up2):
+                training, momentum, eps, up2, res_up2, sn):
         x = _c(x)
         cout, cin, kh, kw = weight.shape
         taps = kh * kw
@@ -348,20 +366,22 @@ class NormConvFn(torch.autograd.Function):
             mi = ops.bn_eval_stats(running_mean, running_var, eps)
         mask_pm, gamma, beta = _c(mask_pm), _c(gamma), _c(beta)
         _, ap = ops.isla_fwd(x, mi, mask_pm, gamma, beta, _c(aff_w), _c(aff_b), relu=True, up2=up2)
-        wp = ops.conv_weight_prep(_c(weight), need_dgrad=True)
+        st, wp = _sigma_and_prep(weight, sn, True)
         out, _ = ops.conv2d_fwd(ap, wp.f_hi, wp.f_lo, cout, taps, bias=_c(bias), residual=_c(residual), res_up2=res_up2)
-        ctx.save_for_backward(x, mi, mask_pm, gamma, beta, aff_w, aff_b, ap.hi, ap.lo, wp.d_hi, wp.d_lo)
+        ctx.save_for_backward(x, mi, mask_pm, gamma, beta, aff_w, aff_b, ap.hi, ap.lo, wp.d_hi, wp.d_lo, weight,
+                              *(st or (None, None, None)))
         ctx.meta = (cout, cin, taps, training, up2, res_up2, bias is not None, residual is not None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, mi, mask_pm, gamma, beta, aff_w, aff_b, ahi, alo, dhi, dlo = ctx.saved_tensors
+        x, mi, mask_pm, gamma, beta, aff_w, aff_b, ahi, alo, dhi, dlo, weight, sg, u, v = ctx.saved_tensors
         cout, cin, taps, training, up2, res_up2, has_bias, has_res = ctx.meta
         dout = _c(dout)
         dyp, _, colsum = ops.grad_split(dout, want_lo=True, up=False)
         da, _ = ops.conv2d_fwd(dyp, dhi, dlo, cin, taps)
-        dw = _dw_to_torch(ops.conv2d_wgrad(dyp, ops.Pair(ahi, alo, cin), taps), cout, cin, taps)
+        g = ops.conv2d_wgrad(dyp, ops.Pair(ahi, alo, cin), taps)
+        dw = ops.sn_weight_grad(g, weight, ops.SNState(sg, u, v)) if sg is not None else _dw_to_torch(g, cout, cin, taps)
         dx, dmask, dgamma, dbeta, csum = ops.isla_bwd(x, mi, mask_pm, gamma, beta, _c(aff_w), _c(aff_b), da,
                                                       relu=True, up2=up2, train=training)
         daw = dab = None
@@ -372,13 +392,13 @@ class NormConvFn(torch.autograd.Function):
         dres = None
         if has_res:
             dres = _sum2x2(dout) if res_up2 else dout
-        return dx, dmask, dgamma, dbeta, daw, dab, dw, db, dres, None, None, None, None, None, None, None
+        return dx, dmask, dgamma, dbeta, daw, dab, dw, db, dres, None, None, None, None, None, None, None, None
 
 
 def norm_conv(x, weight, bias, running_mean, running_var, training, mask_pm=None, gamma=None, beta=None,
-              aff_w=None, aff_b=None, residual=None, up2=False, res_up2=False, momentum=0.1, eps=1e-5):
+              aff_w=None, aff_b=None, residual=None, up2=False, res_up2=False, momentum=0.1, eps=1e-5, sn=None):
     return NormConvFn.apply(x, mask_pm, gamma, beta, aff_w, aff_b, weight, bias, residual, running_mean, running_var,
-                            training, momentum, eps, up2, res_up2)
+                            training, momentum, eps, up2, res_up2, sn)
 
 
 class MaskTrunkFn(torch.autograd.Function):
@@ -394,8 +414,8 @@ class MaskTrunkFn(torch.autograd.Function):
     def forward(ctx, x, w1, b1, w2, b2, w3, b3, w4, b4, sn1, sn2, sn3, sn4):
         x = _c(x)
         ws, bs, sns = (w1, w2, w3, w4), (b1, b2, b3, b4), (sn1, sn2, sn3, sn4)
-        sts = [ops.sn_sigma(_c(w), sn[0], sn[1], training=sn[3], eps=sn[2]) if sn else None for w, sn in zip(ws, sns)]
-        wps = [ops.conv_weight_prep(_c(w), st.sigma if st else None, need_dgrad=True) for w, st in zip(ws, sts)]
+        both = [_sigma_and_prep(w, sn, True) for w, sn in zip(ws, sns)]
+        sts, wps = [b[0] for b in both], [b[1] for b in both]
         pair = ops.act_split(x)
         saved_pairs, hs, stats = [pair], [], []
         for i in range(3):
@@ -483,7 +503,7 @@ class PspBottleneckFn(torch.autograd.Function):
         feats, priors = _c(feats), _c(priors)
         cout = weight.shape[0]
         pair = ops.psp_concat_fwd(feats, priors)
-        wp = ops.conv_weight_prep(_c(weight), need_dgrad=True)
+        _, wp = _sigma_and_prep(weight, None, True)
         out, _ = ops.conv2d_fwd(pair, wp.f_hi, wp.f_lo, cout, 9)
         ctx.save_for_backward(pair.hi, pair.lo, wp.d_hi, wp.d_lo)
         ctx.meta = (cout, pair.C, priors.shape[2])

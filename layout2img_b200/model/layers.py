@@ -34,10 +34,11 @@ class Conv2d(nn.Conv2d):
         if norm is None:
             return L.conv2d(x, self.weight, self.bias, residual, relu_in, up2_in, res_up2)   # plain (non-SN) use
         bn, mask_pm, gamma, beta = norm
-        return L.norm_conv(x, L.sn_weight(self), self.bias, bn.running_mean, bn.running_var, bn.training,
+        w, b, sn = L._sn_of(self)             # weight_orig + (u, v, eps, training) when spectrally normalised
+        return L.norm_conv(x, w, b, bn.running_mean, bn.running_var, bn.training,
                            mask_pm=mask_pm, gamma=gamma, beta=beta, aff_w=bn.weight if bn.affine else None,
                            aff_b=bn.bias if bn.affine else None, residual=residual, up2=up2_in, res_up2=res_up2,
-                           momentum=bn.momentum, eps=bn.eps)
+                           momentum=bn.momentum, eps=bn.eps, sn=sn)
 
 
 class SynchronizedBatchNorm2d(nn.BatchNorm2d):

@@ -8,6 +8,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import functional as L
+from ..sn_group import prepare_network
 from .layers import conv2d, to_nhwc
 
 __all__ = ["CombineDiscriminator128_app", "ResnetDiscriminator128_app", "OptimizedBlock", "ResBlock", "conv2d"]
@@ -73,6 +74,7 @@ class ResnetDiscriminator128_app(nn.Module):
         self.app = nn.utils.spectral_norm(nn.Linear(ch * 16, 1))
 
     def forward(self, x, y=None, bbox=None):         # x NHWC; bbox (K,5) rois in pixels
+        prepare_network(self)          # spectral norm of all 33 modules + every conv's operand pairs: one grouped call
         x = self.block1(x)
         x1 = self.block2(x)
         x2 = self.block3(x1)

@@ -13,6 +13,7 @@ import torch.nn.functional as F
 
 from .. import functional as L
 from .. import ops
+from ..sn_group import prepare_network
 from .layers import BatchNorm, Conv2d, SynchronizedBatchNorm2d, conv2d, to_nchw_view, to_nhwc
 from .mask_regression import MaskRegressNetv2
 from .norm_module import SpatialAdaptiveSynBatchNorm2d
@@ -216,6 +217,7 @@ class _GeneratorBase(nn.Module):
             raise RuntimeError("layout2img_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         bbox = bbox.to(dev).float().contiguous()
         y = y.to(dev).to(torch.int64).contiguous()
+        prepare_network(self)          # spectral norm of all 42 modules + every conv's operand pairs: one grouped call
         label_embedding = self.label_embedding(y)
         latent_vector = torch.cat((z.reshape(b * o, -1), label_embedding.view(b * o, -1)), dim=1).view(b, o, -1)
         w = self.mapping(latent_vector.view(b * o, -1)).view(b, o, -1)

@@ -153,7 +153,8 @@ def conv2d_fwd(x: Pair, w_hi: torch.Tensor, w_lo: torch.Tensor, cout: int, taps:
     """pool((conv(x, w) + bias) * out_scale * [mask_hi > 0]) + res_scale * residual
     -> (fp32 NHWC or None, Pair or None); see include/l2i.h."""
     n, h, w_, cin_pad = x.hi.shape
-    if w_hi.shape != (cout, taps, cin_pad):
+    # (cout, taps, cin_pad) tensors from conv_weight_prep, or flat slices of the grouped preparation's buffer
+    if w_hi.shape != (cout, taps, cin_pad) and not (w_hi.dim() == 1 and w_hi.numel() >= cout * taps * cin_pad):
         raise ValueError(f"weight operand {tuple(w_hi.shape)} does not match ({cout},{taps},{cin_pad})")
     ho, wo = (h // 2, w_ // 2) if pool else (h, w_)
     out = torch.empty((n, ho, wo, cout), dtype=torch.float32, device=x.hi.device) if want_f32 else None
@@ -257,14 +258,13 @@ def isla_bwd(x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, dout, relu: boo
     _chk(x); _chk(dout)
     b, h, w, c = x.shape
     o = 0 if mask_pm is None else mask_pm.shape[-1]
-    gbuf = torch.empty_like(x)
     dx = torch.empty_like(x)
     csum = torch.empty((c, 2), dtype=torch.float64, device=x.device)
     dmask = torch.empty_like(mask_pm) if o else None
     dgamma = torch.empty_like(gamma) if o else None
     dbeta = torch.empty_like(beta) if o else None
     args = (x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, dout, b, h, w, c, o, int(relu), int(up2), int(train),
-            gbuf, dmask, dgamma, dbeta, csum, dx)
+            None, dmask, dgamma, dbeta, csum, dx)
     if train and _SYNC_BN["world"] > 1:
         # global-batch norm: reduce (sum d xhat, sum d xhat * xhat) over the ranks between the two phases.  For the
         # affine form (O == 0) csum also carries the LOCAL (d bias, d weight); keep a copy for the caller.

@@ -101,9 +101,13 @@ def tensor_class(name: str) -> str:
 def parity_report(path, title, got, r32, r64, keys):
     """Per-tensor table: ours vs fp64 oracle next to fp32 oracle vs fp64 oracle (max-norm and relative L2), plus a
     per-class summary.  Returns the text."""
-    rows, classes = [], {}
+    rows, classes, zero = [], {}, []
     for k in keys:
         w = r64[k].detach().double().cpu()
+        if w.abs().max().item() < 1e-12:
+            # biases in front of a normalisation layer: the true gradient is exactly 0, every arm returns rounding residue
+            zero.append((got[k].detach().double().abs().max().item(), r32[k].detach().double().abs().max().item(), k))
+            continue
         m = max(w.abs().max().item(), 1e-30)
         n2 = max(w.norm().item(), 1e-30)
         eo = (got[k].detach().double().cpu() - w)
@@ -122,6 +126,9 @@ def parity_report(path, title, got, r32, r64, keys):
     lines += ["", f"{'ours max':>10s} {'fp32 max':>10s} {'ours L2':>10s} {'fp32 L2':>10s} {'max|ref|':>10s}  tensor"]
     for r in sorted(rows, reverse=True):
         lines.append(f"{r[0]:10.2e} {r[1]:10.2e} {r[2]:10.2e} {r[3]:10.2e} {r[4]:10.2e}  {r[5]}")
+    if zero:
+        lines += ["", "tensors whose true gradient is exactly zero (conv biases in front of a normalisation layer): max|value| ours | fp32 oracle"]
+        lines += [f"{a:10.2e} {b:10.2e}  {k}" for a, b, k in zero]
     text = "\n".join(lines) + "\n"
     if path:
         os.makedirs(os.path.dirname(path), exist_ok=True)

@@ -253,3 +253,37 @@ def test_pinned_feeder_delivers_loader_batches():
         assert torch.equal(real.cpu(), want[0]) and torch.equal(label.cpu(), want[1]) and torch.equal(bbox.cpu(), want[2])
         seen += 1
     assert seen == 5 and feeder.bytes_per_batch == sum(t.numel() * t.element_size() for t in batches[0])
+
+
+def test_grouped_spectral_norm_equals_per_module_path():
+    """sn_group.SNGroup (one grouped launch for all power iterations + operand pairs) against the per-module kernels:
+    same outputs, same u / v buffers (block_obj4, called twice, must still iterate twice), same gradients."""
+    import copy
+    from layout2img_b200 import sn_group
+    from layout2img_b200.model import rcnn_discriminator_app as dmod
+    dev = torch.device("cuda:0")
+    z, meta = load_case("C")
+    data = _data(meta)
+    _, D, _, _ = _build(meta, dev)
+    D2 = copy.deepcopy(D)
+    D.train(); D2.train()
+    args = (data["real"].to(dev), data["bbox"].to(dev), data["label"].to(dev).unsqueeze(-1))
+    out1 = D(*args)
+    sum(o.sum() for o in out1).backward()
+    orig = dmod.prepare_network
+    dmod.prepare_network = lambda net: None          # per-module kernels only
+    try:
+        out2 = D2(*args)
+        sum(o.sum() for o in out2).backward()
+    finally:
+        dmod.prepare_network = orig
+    assert not sn_group.PREPARED or all(k not in sn_group.PREPARED for k in [id(p) for p in D2.parameters()])
+    for a, b in zip(out1, out2):
+        close(a, b, 1e-5, 1e-6, "D output grouped vs per-module")
+    sd1, sd2 = D.state_dict(), D2.state_dict()
+    for k in sd1:
+        if k.endswith(("_u", "_v")):
+            close(sd1[k], sd2[k], 1e-5, 1e-7, k)
+    for (n, p1), (_, p2) in zip(D.named_parameters(), D2.named_parameters()):
+        m = p2.grad.abs().max().item()
+        close(p1.grad, p2.grad, 1e-4, 1e-5 * max(m, 1e-30), "grad " + n)

@@ -87,7 +87,8 @@ def _worker(rank, world, port, backend, q):
                 return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-20)).item()
 
             for k, v in res.items():
-                e = rel(v, ref[k][sl])
+                want = ref[k][sl.start * 3:sl.stop * 3] if k == "dw_vec" else ref[k][sl]      # the latents are (b * O, num_w)
+                e = rel(v, want)
                 if e > 2e-4:
                     msgs.append(f"psp={psp} {k}: {e:.2e}")
             for k, v in pg.items():
