@@ -203,6 +203,29 @@ int l2i_sn_prepare_group(const void* table, int n_modules, const int* wt_items, 
                          const int* wv_items, int n_wv, int max_cc, const int* prep9_items, int n9, const int* prep1_items,
                          int n1, float* f32, long long f32_floats, void* bf16, int want_dgrad, void* stream);
 
+/* ---- discriminator output heads (reference model/rcnn_discriminator_app.py:125-127 image head, :160-166 object head,
+ *      :148-157 appearance head).  feat / x: [N, P, C] fp32 (NHWC feature maps, P pixels).  w, emb are the ORIGINAL
+ *      (un-normalised) spectrally normalised weights; sigma_w / sigma_e device scalars from l2i_sn_sigma. ----------- */
+/* s[n,:] = sum_p relu(feat[n,p,:]) (kept for the backward);  out[n] = s[n,:] . w/sigma_w + bias[0]
+ *          (+ s[n,:] . emb[y[n],:]/sigma_e when emb != NULL: the class projection of the object head). */
+int l2i_head_fwd(const float* feat, int N, int P, int C, const float* w, const float* sigma_w, const float* bias,
+                 const float* emb, const float* sigma_e, const int64_t* y, float* s, float* out, void* stream);
+/* dfeat [N,P,C] (nullable); gw [C] = dL/d(w/sigma_w), gemb [num_emb,C] = dL/d(emb/sigma_e) (both zeroed by the call,
+ * nullable; feed them to l2i_sn_weight_grad with taps = 1); dbias [1]. */
+int l2i_head_bwd(const float* feat, const float* s, const float* dout, int N, int P, int C, const float* w,
+                 const float* sigma_w, const float* emb, const float* sigma_e, const int64_t* y, int num_emb, float* dfeat,
+                 float* gw, float* gemb, float* dbias, void* stream);
+/* Appearance head without the (K,C,C) Gram matrix or the (K,C,2C) concatenation: F = relu(x);
+ *   out[k] = (1/C^2) sum_p (sum_c F[k,p,c]) (sum_c F[k,p,c] w1[c]) + e[y[k],:] . w2 + bias[0],
+ * w = [w1 | w2] (2C, divided by sigma_w), e = emb / sigma_e.  colsum, proj [K,P] are kept for the backward. */
+int l2i_gram_proj_fwd(const float* x, int K, int P, int C, const float* w, const float* sigma_w, const float* bias,
+                      const float* emb, const float* sigma_e, const int64_t* y, float* colsum, float* proj, float* out,
+                      void* stream);
+/* dx [K,P,C]; gw [2C] = dL/d(w/sigma_w); gemb [num_emb,C] = dL/d(emb/sigma_e); dbias [1] (all zeroed by the call). */
+int l2i_gram_proj_bwd(const float* x, const float* colsum, const float* proj, const float* dout, int K, int P, int C,
+                      const float* w, const float* sigma_w, const float* emb, const float* sigma_e, const int64_t* y,
+                      int num_emb, float* dx, float* gw, float* gemb, float* dbias, void* stream);
+
 /* ---- optimizer (reference train_context_app_v2.py:113-127,174,189: torch.optim.Adam(betas=(0, 0.999)),
  *      one parameter group per tensor).  One launch updates every tensor of a network.
  *      tensors: device array of { float* p; const float* g; float* m; float* v; int64 n; float step_size;

@@ -194,6 +194,28 @@ int l2i_sn_prepare_group(const void* table, int n_modules, const int* wt_items, 
   if (n9 + n1 > 0) rc = weight_prep_group(table, prep9_items, n9, prep1_items, n1, f32, bf16, want_dgrad, ST(stream));
   return rc;
 }
+int l2i_head_fwd(const float* feat, int N, int P, int C, const float* w, const float* sigma_w, const float* bias,
+                 const float* emb, const float* sigma_e, const int64_t* y, float* s, float* out, void* stream) {
+  return head_fwd(feat, N, P, C, w, sigma_w, bias, emb, sigma_e, reinterpret_cast<const long long*>(y), s, out, ST(stream));
+}
+int l2i_head_bwd(const float* feat, const float* s, const float* dout, int N, int P, int C, const float* w,
+                 const float* sigma_w, const float* emb, const float* sigma_e, const int64_t* y, int num_emb, float* dfeat,
+                 float* gw, float* gemb, float* dbias, void* stream) {
+  return head_bwd(feat, s, dout, N, P, C, w, sigma_w, emb, sigma_e, reinterpret_cast<const long long*>(y), num_emb, dfeat, gw,
+                  gemb, dbias, ST(stream));
+}
+int l2i_gram_proj_fwd(const float* x, int K, int P, int C, const float* w, const float* sigma_w, const float* bias,
+                      const float* emb, const float* sigma_e, const int64_t* y, float* colsum, float* proj, float* out,
+                      void* stream) {
+  return gram_proj_fwd(x, K, P, C, w, sigma_w, bias, emb, sigma_e, reinterpret_cast<const long long*>(y), colsum, proj, out,
+                       ST(stream));
+}
+int l2i_gram_proj_bwd(const float* x, const float* colsum, const float* proj, const float* dout, int K, int P, int C,
+                      const float* w, const float* sigma_w, const float* emb, const float* sigma_e, const int64_t* y,
+                      int num_emb, float* dx, float* gw, float* gemb, float* dbias, void* stream) {
+  return gram_proj_bwd(x, colsum, proj, dout, K, P, C, w, sigma_w, emb, sigma_e, reinterpret_cast<const long long*>(y), num_emb,
+                       dx, gw, gemb, dbias, ST(stream));
+}
 int l2i_adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, double beta1, double beta2,
                   double eps, void* stream) {
   return adam_step(tensors, chunks, n_chunks, chunk_elems, beta1, beta2, eps, ST(stream));

@@ -202,6 +202,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(128, 2 * BN, 0, 0);
       int ring = 0, ring_b = 0, pass_i = 0;       // smem stage counters / accumulator pass counter (run across tiles)
       (void)ring_b;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -257,16 +258,31 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             const uint32_t a_lo = a_hi + kTileBytes;
             const uint32_t b_hi = a_hi + 2 * kTileBytes;
             const uint32_t b_lo = b_hi + Cfg::kBBytes;
+            if (p.ncat) {
+              // [main | cross] (+)= a_hi x [b_hi ; b_lo]: the lo tile follows the hi tile in shared memory and the cross
+              // accumulator follows the main one in TMEM, so ONE N = 2 BN instruction forms both products and a_hi is
+              // read from shared memory once instead of twice; then cross += a_lo x b_hi.
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t dah = umma_desc_sw128(a_hi + k * 32, 16, 1024);
-              const uint64_t dal = umma_desc_sw128(a_lo + k * 32, 16, 1024);
-              const uint64_t dbh = umma_desc_sw128(b_hi + k * 32, 16, 1024);
-              const uint64_t dbl = umma_desc_sw128(b_lo + k * 32, 16, 1024);
-              umma_bf16(d_cross, dal, dbh, idesc, fresh);
-              umma_bf16(d_cross, dah, dbl, idesc, 1u);
-              umma_bf16(d_main, dah, dbh, idesc, fresh);
-              fresh = 1u;
+              for (int k = 0; k < kBK / 16; ++k) {
+                const uint64_t dah = umma_desc_sw128(a_hi + k * 32, 16, 1024);
+                const uint64_t dal = umma_desc_sw128(a_lo + k * 32, 16, 1024);
+                const uint64_t dbh = umma_desc_sw128(b_hi + k * 32, 16, 1024);
+                umma_bf16(d_main, dah, dbh, idesc2, fresh);
+                umma_bf16(d_cross, dal, dbh, idesc, 1u);
+                fresh = 1u;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k) {
+                const uint64_t dah = umma_desc_sw128(a_hi + k * 32, 16, 1024);
+                const uint64_t dal = umma_desc_sw128(a_lo + k * 32, 16, 1024);
+                const uint64_t dbh = umma_desc_sw128(b_hi + k * 32, 16, 1024);
+                const uint64_t dbl = umma_desc_sw128(b_lo + k * 32, 16, 1024);
+                umma_bf16(d_cross, dal, dbh, idesc, fresh);
+                umma_bf16(d_cross, dah, dbl, idesc, 1u);
+                umma_bf16(d_main, dah, dbh, idesc, fresh);
+                fresh = 1u;
+              }
             }
             umma_commit(&empty_bar[s]);             // frees the smem stage once these MMAs have read it
           }
@@ -551,6 +567,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_con
     } else if (warp == 1) {
       if (lane == 0) {
         constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+        constexpr uint32_t idesc2 = umma_idesc_bf16(128, 2 * BN, 1, 1);
         int it = 0;
         for (int ps = 0; ps < n_pass; ++ps) {
           const int buf = ps & 1;
@@ -569,16 +586,28 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy_hi, const __grid_con
             const uint32_t a_lo = a_hi + Cfg::kABytes;
             const uint32_t b_hi = a_hi + 2 * Cfg::kABytes;
             const uint32_t b_lo = b_hi + Cfg::kBBytes;
+            if (p.ncat) {       // as in the forward kernel: [main | cross] (+)= a_hi x [b_hi ; b_lo], cross += a_lo x b_hi
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {   // 16 pixels per MMA
-              const uint64_t dah = umma_desc_sw128(a_hi + k * 2048, 8192, 1024);
-              const uint64_t dal = umma_desc_sw128(a_lo + k * 2048, 8192, 1024);
-              const uint64_t dbh = umma_desc_sw128(b_hi + k * 2048, 8192, 1024);
-              const uint64_t dbl = umma_desc_sw128(b_lo + k * 2048, 8192, 1024);
-              umma_bf16(d_cross, dal, dbh, idesc, fresh);
-              umma_bf16(d_cross, dah, dbl, idesc, 1u);
-              umma_bf16(d_main, dah, dbh, idesc, fresh);
-              fresh = 1u;
+              for (int k = 0; k < 4; ++k) {   // 16 pixels per MMA
+                const uint64_t dah = umma_desc_sw128(a_hi + k * 2048, 8192, 1024);
+                const uint64_t dal = umma_desc_sw128(a_lo + k * 2048, 8192, 1024);
+                const uint64_t dbh = umma_desc_sw128(b_hi + k * 2048, 8192, 1024);
+                umma_bf16(d_main, dah, dbh, idesc2, fresh);
+                umma_bf16(d_cross, dal, dbh, idesc, 1u);
+                fresh = 1u;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {   // 16 pixels per MMA
+                const uint64_t dah = umma_desc_sw128(a_hi + k * 2048, 8192, 1024);
+                const uint64_t dal = umma_desc_sw128(a_lo + k * 2048, 8192, 1024);
+                const uint64_t dbh = umma_desc_sw128(b_hi + k * 2048, 8192, 1024);
+                const uint64_t dbl = umma_desc_sw128(b_lo + k * 2048, 8192, 1024);
+                umma_bf16(d_cross, dal, dbh, idesc, fresh);
+                umma_bf16(d_cross, dah, dbl, idesc, 1u);
+                umma_bf16(d_main, dah, dbh, idesc, fresh);
+                fresh = 1u;
+              }
             }
             umma_commit(&empty_bar[s]);
           }
@@ -808,6 +837,8 @@ int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream) {
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(a.out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(a.out_lo);
   p.cout_pad = a.cout_pad; p.relu_split = a.relu_split; p.out_scale = a.out_scale;
   p.mask_hi = reinterpret_cast<const __nv_bfloat16*>(a.mask_hi); p.mask_cpad = a.mask_cpad; p.pool = a.pool;
+  static const int ncat_enabled = env_int("L2I_CONV_NCAT", 1);
+  p.ncat = ncat_enabled;
   const int BN = (a.cout > 64) ? 128 : 64;
   p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
   p.n_tiles = (a.cout + BN - 1) / BN;
@@ -892,6 +923,8 @@ int conv_wgrad_tc(const ConvWgradArgs& a, cudaStream_t stream) {
   splits = (p.pix_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
   p.atomic = splits > 1;
   p.dw = a.dw;
+  static const int ncat_enabled = env_int("L2I_CONV_NCAT", 1);
+  p.ncat = ncat_enabled;
   if (p.atomic) {
     cudaError_t e = cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.cout * a.taps * a.cin, stream);
     if (e != cudaSuccess) { set_error("wgrad: memset failed: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }

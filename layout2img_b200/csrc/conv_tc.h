@@ -15,6 +15,7 @@ struct ConvFwdParams {          // device-side view
   int pool;                     // 0 none, 1 = 2x2 average, 2 = 2x2 sum of the conv output (stored at H/2 x W/2)
   float res_scale;
   int pair_maps;                // 1: tm_a_hi / tm_b_hi are (hi, lo) pair maps (one TMA instruction per operand tile)
+  int ncat;                     // 1: a_hi x [b_hi ; b_lo] as one N = 2 BN instruction (2 MMAs per k16 step instead of 3)
   const float* bias;            // [cout] or null
   const float* residual;        // [N,H,W,cout] (res_shift=0) or [N,H/2,W/2,cout] nearest-x2 (res_shift=1), or null
   int res_shift;
@@ -43,7 +44,7 @@ struct ConvFwdArgs {            // host-side call
 
 struct ConvWgradParams {
   int N, H, W, cin, cout, taps;
-  int TW, TH, TN, tiles_w, tiles_h, pix_blocks, blocks_per_split, cin_tiles, atomic, tap_pairs;
+  int TW, TH, TN, tiles_w, tiles_h, pix_blocks, blocks_per_split, cin_tiles, atomic, tap_pairs, ncat;
   float* dw;                    // [cout][taps][cin] fp32
 };
 

@@ -103,6 +103,18 @@ int sn_group_sigma(const void* table, int n_modules, const int* wt_items, int n_
 int weight_prep_group(const void* table, const int* items9, int n9, const int* items1, int n1, const float* f32, void* bf16,
                       int want_dgrad, cudaStream_t stream);
 
+// heads.cu
+int head_fwd(const float* feat, int N, int P, int C, const float* w, const float* sigma_w, const float* bias, const float* emb,
+             const float* sigma_e, const long long* y, float* s, float* out, cudaStream_t stream);
+int head_bwd(const float* feat, const float* s, const float* dout, int N, int P, int C, const float* w, const float* sigma_w,
+             const float* emb, const float* sigma_e, const long long* y, int num_emb, float* dfeat, float* gw, float* gemb,
+             float* dbias, cudaStream_t stream);
+int gram_proj_fwd(const float* x, int K, int P, int C, const float* w, const float* sigma_w, const float* bias, const float* emb,
+                  const float* sigma_e, const long long* y, float* colsum, float* proj, float* out, cudaStream_t stream);
+int gram_proj_bwd(const float* x, const float* colsum, const float* proj, const float* dout, int K, int P, int C, const float* w,
+                  const float* sigma_w, const float* emb, const float* sigma_e, const long long* y, int num_emb, float* dx,
+                  float* gw, float* gemb, float* dbias, cudaStream_t stream);
+
 // optim.cu
 struct AdamTensor {       // one entry of the device-resident tensor table (48 bytes, see include/l2i.h)
   float* p;

@@ -644,3 +644,88 @@ class BoxAttentionFn(torch.autograd.Function):
 
 def box_attention(q, k, v, bbox, y, wg_w, wg_b):
     return BoxAttentionFn.apply(q, k, v, bbox, y, wg_w, wg_b)
+
+
+class ProjHeadFn(torch.autograd.Function):
+    """The discriminator's projection heads (rcnn_discriminator_app.py:125-127,160-166):
+        out = Linear_sn(sum_hw relu(feat)) [+ <Embedding_sn[y], sum_hw relu(feat)>]
+    feat (N,h,w,C) NHWC.  One kernel forward (csrc/heads.cu), one backward + the spectral-norm gradient maps."""
+
+    @staticmethod
+    def forward(ctx, feat, w_orig, bias, sn_w, emb_orig, sn_e, y):
+        feat = _c(feat)
+        n, h, w_, c = feat.shape
+        st_w = _sigma(w_orig, sn_w)
+        st_e = _sigma(emb_orig, sn_e) if emb_orig is not None else None
+        f3 = feat.view(n, h * w_, c)
+        s, out = ops.head_fwd(f3, _c(w_orig), st_w.sigma, _c(bias), _c(emb_orig), st_e.sigma if st_e else None, y)
+        ctx.save_for_backward(feat, s, w_orig, emb_orig, y, *st_w, *(st_e or (None, None, None)))
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        feat, s, w_orig, emb_orig, y, sg, u, v, sge, ue, ve = ctx.saved_tensors
+        n, h, w_, c = feat.shape
+        need = ctx.needs_input_grad
+        dfeat, gw, gemb, dbias = ops.head_bwd(feat.view(n, h * w_, c), s, _c(dout).view(-1), _c(w_orig), sg, _c(emb_orig), sge, y,
+                                              need_dfeat=need[0], need_gw=need[1] or need[4], need_db=ctx.has_bias and need[2])
+        dw = demb = None
+        if need[1]:
+            dw = ops.sn_weight_grad(gw.view(1, 1, c), _c(w_orig), ops.SNState(sg, u, v)).view_as(w_orig)
+        if emb_orig is not None and need[4]:
+            demb = ops.sn_weight_grad(gemb.view(-1, 1, c), _c(emb_orig), ops.SNState(sge, ue, ve)).view_as(emb_orig)
+        return (dfeat.view_as(feat) if dfeat is not None else None, dw, dbias if (ctx.has_bias and need[2]) else None, None,
+                demb, None, None)
+
+
+def proj_head(feat, linear, embedding=None, y=None):
+    """feat (N,h,w,C) through a spectrally normalised nn.Linear(C, 1) (+ the class projection with a spectrally normalised
+    nn.Embedding(num_classes, C))."""
+    w, b, sn = _sn_of(linear)
+    if sn is None:
+        raise ValueError("proj_head expects a spectrally normalised linear layer")
+    if embedding is None:
+        return ProjHeadFn.apply(feat, w, b, sn, None, None, None)
+    we, _, sne = _sn_of(embedding)
+    return ProjHeadFn.apply(feat, w, b, sn, we, sne, y.contiguous())
+
+
+class GramProjFn(torch.autograd.Function):
+    """The appearance head (rcnn_discriminator_app.py:148-157) on x = app_conv(obj_feat) (K,h,w,C): ReLU, Gram matrix,
+    concatenation with the class embedding, Linear(2C, 1), mean over rows -- as one kernel that never forms the Gram
+    matrix (csrc/heads.cu gram_proj_*)."""
+
+    @staticmethod
+    def forward(ctx, x, w_orig, bias, sn_w, emb_orig, sn_e, y):
+        x = _c(x)
+        k, h, w_, c = x.shape
+        if w_orig.shape != (1, 2 * c):
+            raise ValueError(f"appearance projection must be (1, {2 * c}), got {tuple(w_orig.shape)}")
+        st_w, st_e = _sigma(w_orig, sn_w), _sigma(emb_orig, sn_e)
+        colsum, proj, out = ops.gram_proj_fwd(x.view(k, h * w_, c), _c(w_orig), st_w.sigma, _c(bias), _c(emb_orig), st_e.sigma, y)
+        ctx.save_for_backward(x, colsum, proj, w_orig, emb_orig, y, *st_w, *st_e)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, colsum, proj, w_orig, emb_orig, y, sg, u, v, sge, ue, ve = ctx.saved_tensors
+        k, h, w_, c = x.shape
+        dx, gw, gemb, dbias = ops.gram_proj_bwd(x.view(k, h * w_, c), colsum, proj, _c(dout).view(-1), _c(w_orig), sg,
+                                                _c(emb_orig), sge, y)
+        dw = demb = None
+        if ctx.needs_input_grad[1]:
+            dw = ops.sn_weight_grad(gw.view(1, 1, 2 * c), _c(w_orig), ops.SNState(sg, u, v)).view_as(w_orig)
+        if ctx.needs_input_grad[4]:
+            demb = ops.sn_weight_grad(gemb.view(-1, 1, c), _c(emb_orig), ops.SNState(sge, ue, ve)).view_as(emb_orig)
+        return (dx.view_as(x) if ctx.needs_input_grad[0] else None, dw, dbias if (ctx.has_bias and ctx.needs_input_grad[2]) else None,
+                None, demb, None, None)
+
+
+def gram_proj(x, linear, embedding, y):
+    w, b, sn = _sn_of(linear)
+    we, _, sne = _sn_of(embedding)
+    if sn is None or sne is None:
+        raise ValueError("gram_proj expects spectrally normalised app / l_y_app modules")
+    return GramProjFn.apply(x, w, b, sn, we, sne, y.contiguous())

@@ -5,7 +5,6 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import functional as L
 from ..sn_group import prepare_network
@@ -81,8 +80,7 @@ class ResnetDiscriminator128_app(nn.Module):
         x = self.block4(x2)
         x = self.block5(x)
         x = self.block6(x)
-        x = F.relu(x).sum(dim=(1, 2))
-        out_im = L.sn_linear(self.l7, x)
+        out_im = L.proj_head(x, self.l7)                               # sum_hw relu -> SN linear (:125-127), one kernel
 
         # small / large object paths (:131-146); order = all large then all small
         s_idx = ((bbox[:, 3] - bbox[:, 1]) < 64) * ((bbox[:, 4] - bbox[:, 2]) < 64)
@@ -96,25 +94,12 @@ class ResnetDiscriminator128_app(nn.Module):
         obj_feat = torch.cat([obj_feat_l, obj_feat_s], dim=0)          # (K,8,8,512) NHWC
         y = torch.cat([y_l, y_s], dim=0)
 
-        # appearance head (:148-157).  mean_i Linear([Gram_i, e_y]) is evaluated without forming the
-        # (K,512,512) Gram matrix or the (K,512,1024) concat:
-        #   sum_i Gram[i,:] . w1 = (1/C) sum_p (sum_i F[i,p]) (sum_j F[j,p] w1[j])
-        app_feat = F.relu(self.app_conv(obj_feat))
-        k_, hh, ww_, c = app_feat.shape
-        feat = app_feat.view(k_, hh * ww_, c)
-        w_app = L.sn_weight(self.app)                                   # (1, 2c), spectrally normalised
-        w1, w2 = w_app[0, :c], w_app[0, c:]
-        colsum = feat.sum(dim=2)                                        # (K, P)
-        proj = feat @ w1                                                # (K, P)
-        app_y = F.embedding(y, L.sn_weight(self.l_y_app))               # (K, C)
-        out_app = ((colsum * proj).sum(dim=1, keepdim=True) / (c * c)
-                   + (app_y @ w2).unsqueeze(1) + self.app.bias)
+        # appearance head (:148-157): mean_i Linear([Gram_i, e_y]) without forming the (K,512,512) Gram matrix or the
+        # (K,512,1024) concat (csrc/heads.cu):  sum_i Gram[i,:] . w1 = (1/C) sum_p (sum_i F[i,p]) (sum_j F[j,p] w1[j])
+        out_app = L.gram_proj(self.app_conv(obj_feat), self.app, self.l_y_app, y)
 
-        # object head (:160-166)
-        obj_feat = self.block_obj5(obj_feat)
-        obj_feat = F.relu(obj_feat).sum(dim=(1, 2))                     # (K,1024)
-        out_obj = L.sn_linear(self.l_obj, obj_feat)
-        out_obj = out_obj + torch.sum(F.embedding(y, L.sn_weight(self.l_y)) * obj_feat, dim=1, keepdim=True)
+        # object head (:160-166): sum_hw relu -> SN linear + <SN embedding[y], .>
+        out_obj = L.proj_head(self.block_obj5(obj_feat), self.l_obj, self.l_y, y)
         return out_im, out_obj, out_app
 
 

@@ -446,6 +446,53 @@ def avgpool2_bwd(dout):
 
 
 # --------------------------------------------------------------------------------------------
+# discriminator heads
+# --------------------------------------------------------------------------------------------
+def head_fwd(feat, w, sigma_w, bias, emb, sigma_e, y):
+    """feat (N,P,C) -> (s (N,C), out (N,1)); see include/l2i.h."""
+    _chk(feat); _chk(w)
+    n, p, c = feat.shape
+    s = torch.empty((n, c), dtype=torch.float32, device=feat.device)
+    out = torch.empty((n, 1), dtype=torch.float32, device=feat.device)
+    call("l2i_head_fwd", feat, n, p, c, w, sigma_w, bias, emb, sigma_e, y, s, out)
+    return s, out
+
+
+def head_bwd(feat, s, dout, w, sigma_w, emb, sigma_e, y, need_dfeat=True, need_gw=True, need_db=True):
+    n, p, c = feat.shape
+    dev = feat.device
+    dfeat = torch.empty_like(feat) if need_dfeat else None
+    gw = torch.empty((c,), dtype=torch.float32, device=dev) if need_gw else None
+    gemb = torch.empty((emb.shape[0], c), dtype=torch.float32, device=dev) if (emb is not None and need_gw) else None
+    dbias = torch.empty((1,), dtype=torch.float32, device=dev) if need_db else None
+    call("l2i_head_bwd", feat, s, _chk(dout), n, p, c, w, sigma_w, emb, sigma_e, y, emb.shape[0] if emb is not None else 0,
+         dfeat, gw, gemb, dbias)
+    return dfeat, gw, gemb, dbias
+
+
+def gram_proj_fwd(x, w, sigma_w, bias, emb, sigma_e, y):
+    """x (K,P,C) -> (colsum (K,P), proj (K,P), out (K,1))."""
+    _chk(x); _chk(w); _chk(emb)
+    k, p, c = x.shape
+    colsum = torch.empty((k, p), dtype=torch.float32, device=x.device)
+    proj = torch.empty((k, p), dtype=torch.float32, device=x.device)
+    out = torch.empty((k, 1), dtype=torch.float32, device=x.device)
+    call("l2i_gram_proj_fwd", x, k, p, c, w, sigma_w, bias, emb, sigma_e, y, colsum, proj, out)
+    return colsum, proj, out
+
+
+def gram_proj_bwd(x, colsum, proj, dout, w, sigma_w, emb, sigma_e, y):
+    k, p, c = x.shape
+    dev = x.device
+    dx = torch.empty_like(x)
+    gw = torch.empty((2 * c,), dtype=torch.float32, device=dev)
+    gemb = torch.empty((emb.shape[0], c), dtype=torch.float32, device=dev)
+    dbias = torch.empty((1,), dtype=torch.float32, device=dev)
+    call("l2i_gram_proj_bwd", x, colsum, proj, _chk(dout), k, p, c, w, sigma_w, emb, sigma_e, y, emb.shape[0], dx, gw, gemb, dbias)
+    return dx, gw, gemb, dbias
+
+
+# --------------------------------------------------------------------------------------------
 # object-context attention
 # --------------------------------------------------------------------------------------------
 def box_attention_fwd(q, k, v, bbox, y, wg, bg):

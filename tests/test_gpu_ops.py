@@ -547,3 +547,79 @@ def test_inorm_relu_upsample_matches_torch(dev, H, up2):
     close(got, y, 1e-3, 1e-4, "inorm fwd pair")
     dx = ops.inorm_relu_bwd(xg, stats, nhwc(da).to(dev), up2)
     close(dx.permute(0, 3, 1, 2), xr.grad, 1e-3, 1e-4 * max(1.0, xr.grad.abs().max().item()), "inorm bwd")
+
+
+def _sn_mod(mod, dev, seed):
+    """Spectrally normalised module with deterministic weights and converged-ish u / v on `dev` (eval: no iteration)."""
+    m = torch.nn.utils.spectral_norm(mod)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        m.weight_orig.copy_(torch.randn(m.weight_orig.shape, generator=g) * 0.2)
+        if getattr(m, "bias", None) is not None:
+            m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+    return m.to(dev)
+
+
+@pytest.mark.parametrize("with_emb,training", [(False, True), (True, True), (True, False)])
+def test_projection_head_matches_composition(dev, with_emb, training):
+    """functional.proj_head (csrc/heads.cu) vs rcnn_discriminator_app.py:125-127 / :160-166 composed from torch ops in fp64
+    (sum_hw relu -> spectral-norm linear [+ <spectral-norm embedding[y], .>]), forward, every gradient, u / v buffers."""
+    import copy
+    from layout2img_b200 import functional as L
+    N, H, C, NC = 37, 4, 1024, 184
+    g = torch.Generator().manual_seed(17)
+    feat = torch.randn(N, H, H, C, generator=g)
+    y = torch.randint(1, NC, (N,), generator=g)
+    lin, emb = _sn_mod(torch.nn.Linear(C, 1), dev, 1), _sn_mod(torch.nn.Embedding(NC, C), dev, 2)
+    lin_r, emb_r = copy.deepcopy(lin).cpu().double(), copy.deepcopy(emb).cpu().double()
+    for m in (lin, emb, lin_r, emb_r):
+        m.train(training)
+    fr = feat.double().requires_grad_()
+    s = F.relu(fr).sum(dim=(1, 2))
+    ref = lin_r(s)
+    if with_emb:
+        ref = ref + (emb_r(y) * s).sum(dim=1, keepdim=True)
+    dy = torch.randn(N, 1, generator=g)
+    ref.backward(dy.double())
+    fg = feat.to(dev).requires_grad_()
+    out = L.proj_head(fg, lin, emb if with_emb else None, y.to(dev) if with_emb else None)
+    out.backward(dy.to(dev))
+    close(out, ref, what="head fwd")
+    close(fg.grad, fr.grad, 1e-3, 1e-5, "head dfeat")
+    close(lin.weight_orig.grad, lin_r.weight_orig.grad, 1e-3, 1e-4 * lin_r.weight_orig.grad.abs().max().item(), "head dw")
+    close(lin.bias.grad, lin_r.bias.grad, 1e-3, 1e-4, "head dbias")
+    close(lin.weight_u, lin_r.weight_u, 1e-4, 1e-5, "u")
+    if with_emb:
+        close(emb.weight_orig.grad, emb_r.weight_orig.grad, 1e-3, 1e-4 * emb_r.weight_orig.grad.abs().max().item(), "head demb")
+        close(emb.weight_v, emb_r.weight_v, 1e-4, 1e-5, "emb v")
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_gram_projection_head_matches_reference_formula(dev, training):
+    """functional.gram_proj (csrc/heads.cu) vs the reference's appearance head evaluated literally in fp64
+    (rcnn_discriminator_app.py:148-157: Gram matrix, concat with the class embedding, linear, row mean)."""
+    import copy
+    from layout2img_b200 import functional as L
+    K, H, C, NC = 9, 8, 64, 20
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(K, H, H, C, generator=g)
+    y = torch.randint(1, NC, (K,), generator=g)
+    app, emb = _sn_mod(torch.nn.Linear(2 * C, 1), dev, 3), _sn_mod(torch.nn.Embedding(NC, C), dev, 4)
+    app_r, emb_r = copy.deepcopy(app).cpu().double(), copy.deepcopy(emb).cpu().double()
+    for m in (app, emb, app_r, emb_r):
+        m.train(training)
+    xr = x.double().requires_grad_()
+    f = F.relu(xr.permute(0, 3, 1, 2)).reshape(K, C, -1)               # (K, C, P) as the reference's NCHW view
+    gram = torch.bmm(f, f.transpose(1, 2)) / C
+    ey = emb_r(y)
+    ref = app_r(torch.cat([gram, ey[:, None, :].expand(K, C, C)], dim=-1)).sum(1) / C
+    dy = torch.randn(K, 1, generator=g)
+    ref.backward(dy.double())
+    xg = x.to(dev).requires_grad_()
+    out = L.gram_proj(xg, app, emb, y.to(dev))
+    out.backward(dy.to(dev))
+    close(out, ref, what="gram fwd")
+    close(xg.grad, xr.grad, 1e-3, 1e-4 * xr.grad.abs().max().item(), "gram dx")
+    close(app.weight_orig.grad, app_r.weight_orig.grad, 1e-3, 1e-4 * app_r.weight_orig.grad.abs().max().item(), "gram dw")
+    close(app.bias.grad, app_r.bias.grad, 1e-3, 1e-4, "gram dbias")
+    close(emb.weight_orig.grad, emb_r.weight_orig.grad, 1e-3, 1e-4 * emb_r.weight_orig.grad.abs().max().item(), "gram demb")
