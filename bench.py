@@ -349,7 +349,8 @@ def run_ours(args, rank, local_rank, world):
     G.load_state_dict(make_state(schema_of(G), 1))      # same weights on every rank (replicated DP)
     D.load_state_dict(make_state(schema_of(D), 2))
     G.to(dev).train(); D.to(dev).train()
-    g_opt, d_opt = make_optimizers(G, D)
+    use_graph = bool(args.graph) and world == 1
+    g_opt, d_opt = make_optimizers(G, D, capturable=use_graph)
     # zero-copy gradient buckets, all-reduced on a side stream while the backward pass is still running
     sync_g = GradBuckets(G) if world > 1 else None
     sync_d = GradBuckets(D) if world > 1 else None
@@ -360,16 +361,28 @@ def run_ours(args, rank, local_rank, world):
     keys = ("real", "label", "bbox", "z", "z_im")
     h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in keys)
 
+    graphed = None
+    if use_graph:
+        # the whole iteration as ONE CUDA graph replayed from static buffers (fixed-shape discriminator, device-side ROI
+        # compaction, capturable Adam): no host synchronisation and one launch per step
+        from layout2img_b200.train import GraphedTrainStep
+        graphed = GraphedTrainStep(G, D, g_opt, d_opt, devd["real"], devd["label"], devd["bbox"], devd["z"], devd["z_im"], warmup=3)
+
     def step_resident():
+        if graphed is not None:
+            return graphed(devd["real"], devd["label"], devd["bbox"], devd["z"], devd["z_im"])
         return train_step(G, D, g_opt, d_opt, devd["real"], devd["label"], devd["bbox"], devd["z"], devd["z_im"],
                           sync_g=sync_g, sync_d=sync_d)
 
     loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
 
     def step_e2e():
-        d = {k: host[k].to(dev, non_blocking=True) for k in keys}
-        dl, gl, _ = train_step(G, D, g_opt, d_opt, d["real"], d["label"], d["bbox"], d["z"], d["z_im"],
-                               sync_g=sync_g, sync_d=sync_d)
+        if graphed is not None:
+            dl, gl, _ = graphed(host["real"], host["label"], host["bbox"], host["z"], host["z_im"])   # pinned host -> static buffers
+        else:
+            d = {k: host[k].to(dev, non_blocking=True) for k in keys}
+            dl, gl, _ = train_step(G, D, g_opt, d_opt, d["real"], d["label"], d["bbox"], d["z"], d["z_im"],
+                                   sync_g=sync_g, sync_d=sync_d)
         loss_host.copy_(torch.stack([dl, gl]), non_blocking=True)
         torch.cuda.current_stream().synchronize()       # the user reads the losses every step
         return loss_host
@@ -413,7 +426,11 @@ def run_ours(args, rank, local_rank, world):
 
     line = None
     # every rank runs the instrumented step (it contains the gradient all-reduces); rank 0 reports it
-    agg, step_ms = kernel_breakdown(step_resident)
+    def step_eager():         # graph mode: the same fixed-shape iteration issued call by call, for the per-kernel breakdown
+        return train_step(G, D, g_opt, d_opt, devd["real"], devd["label"], devd["bbox"], devd["z"], devd["z_im"],
+                          sync_g=graphed.sync_g, sync_d=graphed.sync_d)
+
+    agg, step_ms = kernel_breakdown(step_eager if graphed is not None else step_resident)
     conv_shapes = agg.pop("_conv_shapes")
     if rank == 0 and args.shapes_file:
         with open(args.shapes_file, "w") as f:
@@ -476,7 +493,7 @@ def run_ours(args, rank, local_rank, world):
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "host_enqueue_ms_per_step": host_ms.get("step_resident"),
+            "host_enqueue_ms_per_step": host_ms.get("step_resident"), "cuda_graph": bool(use_graph),
             "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "library_baseline": lib,
             "kernel_ms_per_step": breakdown,
@@ -498,6 +515,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--ref-batch", type=int, default=0, help="--impl reference: images per CPU step (default 8, 16 for short runs)")
+    ap.add_argument("--graph", type=int, default=0, help="1: replay the whole step as one CUDA graph (single GPU)")
     ap.add_argument("--no-library", action="store_true", help="skip the library_baseline leg (reference modules, PyTorch eager, same GPU)")
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (the metric is quoted at 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

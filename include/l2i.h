@@ -143,6 +143,19 @@ int l2i_roi_align_fwd(const float* feat, const float* rois, int K, int N, int H,
                       float* out, void* stream);
 int l2i_roi_align_bwd(const float* dout, const float* rois, int K, int N, int H, int W, int C, int P, float scale,
                       float* dfeat, void* stream);
+/* Device-side ROI preparation (reference rcnn_discriminator_app.py:402-417,131-146), no host round trip: bbox [B,O,4]
+ * xywh in [0,1], label [B*O].  Writes ALL B*O rows of rois [B*O,5] = (image, x0, y0, x1, y1) px, y_sorted, level and
+ * perm (source row): first the large ROIs (level 0), then the small ones (level 1: width < small_thresh and height <
+ * small_thresh), each in (b, o) order -- the reference's order -- then the dropped rows (label == 0, level 2).
+ * counts [2] = (n_large, n_small).  Bit-exact with the reference's float arithmetic. */
+int l2i_roi_prepare(const float* bbox, const int64_t* label, int B, int O, float img_size, float small_thresh, float* rois,
+                    int64_t* y_sorted, int32_t* level, int32_t* perm, int32_t* counts, void* stream);
+/* ROIAlign of the two-level object path in one launch: row k samples feat_l [N,Hl,Wl,C] at scale_l (level 0), feat_s
+ * [N,Hs,Ws,C] at scale_s (level 1), or is zero (level 2).  out [K,P,P,C].  bwd zero-fills both feature gradients. */
+int l2i_roi_align2_fwd(const float* feat_l, int Hl, int Wl, float scale_l, const float* feat_s, int Hs, int Ws, float scale_s,
+                       const float* rois, const int32_t* level, int K, int N, int C, int P, float* out, void* stream);
+int l2i_roi_align2_bwd(const float* dout, const float* rois, const int32_t* level, int K, int N, int C, int P, int Hl, int Wl,
+                       float scale_l, float* dfeat_l, int Hs, int Ws, float scale_s, float* dfeat_s, void* stream);
 /* 2x2 average pooling, NHWC (F.avg_pool2d(x, 2) in the discriminator blocks). */
 int l2i_avgpool2_fwd(const float* x, int N, int H, int W, int C, float* out, void* stream);
 int l2i_avgpool2_bwd(const float* dout, int N, int H, int W, int C, float* dx, void* stream);
@@ -232,9 +245,11 @@ int l2i_gram_proj_bwd(const float* x, const float* colsum, const float* proj, co
  *      float bc2_sqrt; } (48 bytes each) with step_size = lr / (1 - beta1^step), bc2_sqrt = sqrt(1 - beta2^step) for
  *      the tensor's OWN step count (torch keeps one per parameter) and n = 0 for a tensor without a gradient
  *      (skipped); chunks: device array of n_chunks (tensor index, chunk index) int pairs, each covering
- *      chunk_elems (multiple of 4) consecutive elements.  Arithmetic = torch's Adam step. ---- */
+ *      chunk_elems (multiple of 4) consecutive elements.  Arithmetic = torch's Adam step.
+ *      step_dev != NULL (CUDA-graph capturable form): *step_dev is the common step count on the device, the entries'
+ *      step_size holds the plain lr and both bias corrections are formed in the kernel. ---- */
 int l2i_adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, double beta1, double beta2,
-                  double eps, void* stream);
+                  double eps, const int64_t* step_dev, void* stream);
 
 #ifdef __cplusplus
 }

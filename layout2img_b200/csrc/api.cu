@@ -194,6 +194,19 @@ int l2i_sn_prepare_group(const void* table, int n_modules, const int* wt_items, 
   if (n9 + n1 > 0) rc = weight_prep_group(table, prep9_items, n9, prep1_items, n1, f32, bf16, want_dgrad, ST(stream));
   return rc;
 }
+int l2i_roi_prepare(const float* bbox, const int64_t* label, int B, int O, float img_size, float small_thresh, float* rois,
+                    int64_t* y_sorted, int32_t* level, int32_t* perm, int32_t* counts, void* stream) {
+  return roi_prepare(bbox, reinterpret_cast<const long long*>(label), B, O, img_size, small_thresh, rois,
+                     reinterpret_cast<long long*>(y_sorted), level, perm, counts, ST(stream));
+}
+int l2i_roi_align2_fwd(const float* feat_l, int Hl, int Wl, float scale_l, const float* feat_s, int Hs, int Ws, float scale_s,
+                       const float* rois, const int32_t* level, int K, int N, int C, int P, float* out, void* stream) {
+  return roi_align2_fwd(feat_l, Hl, Wl, scale_l, feat_s, Hs, Ws, scale_s, rois, level, K, N, C, P, out, ST(stream));
+}
+int l2i_roi_align2_bwd(const float* dout, const float* rois, const int32_t* level, int K, int N, int C, int P, int Hl, int Wl,
+                       float scale_l, float* dfeat_l, int Hs, int Ws, float scale_s, float* dfeat_s, void* stream) {
+  return roi_align2_bwd(dout, rois, level, K, N, C, P, Hl, Wl, scale_l, dfeat_l, Hs, Ws, scale_s, dfeat_s, ST(stream));
+}
 int l2i_head_fwd(const float* feat, int N, int P, int C, const float* w, const float* sigma_w, const float* bias,
                  const float* emb, const float* sigma_e, const int64_t* y, float* s, float* out, void* stream) {
   return head_fwd(feat, N, P, C, w, sigma_w, bias, emb, sigma_e, reinterpret_cast<const long long*>(y), s, out, ST(stream));
@@ -217,8 +230,9 @@ int l2i_gram_proj_bwd(const float* x, const float* colsum, const float* proj, co
                        dx, gw, gemb, dbias, ST(stream));
 }
 int l2i_adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, double beta1, double beta2,
-                  double eps, void* stream) {
-  return adam_step(tensors, chunks, n_chunks, chunk_elems, beta1, beta2, eps, ST(stream));
+                  double eps, const int64_t* step_dev, void* stream) {
+  return adam_step(tensors, chunks, n_chunks, chunk_elems, beta1, beta2, eps, reinterpret_cast<const long long*>(step_dev),
+                   ST(stream));
 }
 
 }  // extern "C"

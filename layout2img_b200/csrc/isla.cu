@@ -235,8 +235,28 @@ __device__ __forceinline__ void load_cpt(const float* __restrict__ p, bool ok, f
   }
 }
 
+// G = sum_o m_o gamma_o, Bt = sum_o m_o beta_o for the lane's channels; objects whose mask is exactly 0 at this pixel are
+// skipped (their terms are exactly 0; the masks are box-shaped, so most are) -- the test is warp-uniform.
 template <int OM, int CPT>
-__global__ void __launch_bounds__(256) isla_fwd_kernel(const IslaFwdParams p) {
+__device__ __forceinline__ void isla_modulation(const IslaLane<OM, CPT>& L, const float (&m)[OM > 0 ? OM : 1], float (&G)[CPT],
+                                                float (&Bt)[CPT]) {
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) { G[j] = 0.f; Bt[j] = 0.f; }
+  if constexpr (OM > 0) {
+#pragma unroll
+    for (int o = 0; o < OM; ++o) {
+      if (m[o] != 0.f) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) { G[j] = fmaf(m[o], L.gam[o][j], G[j]); Bt[j] = fmaf(m[o], L.bet[o][j], Bt[j]); }
+      }
+    }
+  }
+}
+
+static constexpr int kIslaU = 4;        // pixels whose loads are in flight together per warp (forward / dx kernels)
+
+template <int OM, int CPT>
+__global__ void __launch_bounds__(256, 2) isla_fwd_kernel(const IslaFwdParams p) {
   using Lane = IslaLane<OM, CPT>;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wc = warp % p.warps_c, wp = warp / p.warps_c;
@@ -251,47 +271,53 @@ __global__ void __launch_bounds__(256) isla_fwd_kernel(const IslaFwdParams p) {
   const int rep = 1 << p.up;
   const float* __restrict__ xb = p.x + static_cast<size_t>(b) * hw * p.C + c;
   const float* __restrict__ mb = p.mask ? p.mask + static_cast<size_t>(b) * hw * p.O : nullptr;
-#pragma unroll 2
-  for (int pix = blockIdx.x * p.warps_p + wp; pix < hw; pix += gridDim.x * p.warps_p) {
-    float xv[CPT];
-    load_cpt<CPT>(xb + static_cast<size_t>(pix) * p.C, c_ok, xv);
-    float m[Lane::OMX];
-    float invS = 1.0f;
-    if constexpr (OM > 0) invS = isla_masks<OM>(mb + static_cast<size_t>(pix) * p.O, p.O, m);
-    float y[CPT];
+  float* __restrict__ outb = p.out ? p.out + static_cast<size_t>(b) * hw * p.C + c : nullptr;
+  __nv_bfloat16* __restrict__ hib = p.hi;
+  __nv_bfloat16* __restrict__ lob = p.lo;
+  const int stride = gridDim.x * p.warps_p;
+  for (int base = blockIdx.x * p.warps_p + wp; base < hw; base += stride * kIslaU) {
+    // ---- all loads of kIslaU pixels first (the stores below may alias them as far as the compiler knows)
+    float xv[kIslaU][CPT], m[kIslaU][Lane::OMX], invS[kIslaU];
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      const float xh = (xv[j] - L.mean[j]) * L.invstd[j];
-      if constexpr (OM > 0) {
-        float G = 0.f, Bt = 0.f;
+    for (int u = 0; u < kIslaU; ++u) {
+      const int pix = min(base + u * stride, hw - 1);
+      load_cpt<CPT>(xb + static_cast<size_t>(pix) * p.C, c_ok, xv[u]);
+      invS[u] = 1.0f;
+      if constexpr (OM > 0) invS[u] = isla_masks<OM>(mb + static_cast<size_t>(pix) * p.O, p.O, m[u]);
+    }
 #pragma unroll
-        for (int o = 0; o < OM; ++o) { G = fmaf(m[o], L.gam[o][j], G); Bt = fmaf(m[o], L.bet[o][j], Bt); }
-        y[j] = isla_y(G, Bt, invS, xh);
-      } else {
-        y[j] = fmaf(xh, L.aw[j], L.ab[j]);
+    for (int u = 0; u < kIslaU; ++u) {
+      const int pix = base + u * stride;
+      if (pix >= hw) break;
+      float G[CPT], Bt[CPT], y[CPT];
+      isla_modulation<OM, CPT>(L, m[u], G, Bt);
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const float xh = (xv[u][j] - L.mean[j]) * L.invstd[j];
+        if constexpr (OM > 0) y[j] = isla_y(G[j], Bt[j], invS[u], xh); else y[j] = fmaf(xh, L.aw[j], L.ab[j]);
+        if (!c_ok) y[j] = 0.f;
       }
-      if (!c_ok) y[j] = 0.f;
-    }
-    if (p.out && c_ok) {
-      float* op = p.out + (static_cast<size_t>(b) * hw + pix) * p.C + c;
-      if constexpr (CPT == 2) *reinterpret_cast<float2*>(op) = make_float2(y[0], y[1]); else op[0] = y[0];
-    }
-    if (c_pad) {
-      __nv_bfloat16 h[CPT], l[CPT];
+      if (outb && c_ok) {
+        float* op = outb + static_cast<size_t>(pix) * p.C;
+        if constexpr (CPT == 2) *reinterpret_cast<float2*>(op) = make_float2(y[0], y[1]); else op[0] = y[0];
+      }
+      if (c_pad) {
+        __nv_bfloat16 h[CPT], l[CPT];
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) split_bf16(p.relu ? fmaxf(y[j], 0.f) : y[j], h[j], l[j]);
-      const int hh = pix / p.W, ww = pix - hh * p.W;
-      for (int dy = 0; dy < rep; ++dy)
-        for (int dx = 0; dx < rep; ++dx) {
-          const size_t op = ((static_cast<size_t>(b) * Ho + (hh << p.up) + dy) * Wo + (ww << p.up) + dx) * p.cpad + c;
-          if constexpr (CPT == 2) {
-            *reinterpret_cast<uint32_t*>(p.hi + op) = pack_bf16x2(h[0], h[1]);
-            *reinterpret_cast<uint32_t*>(p.lo + op) = pack_bf16x2(l[0], l[1]);
-          } else {
-            p.hi[op] = h[0];
-            p.lo[op] = l[0];
+        for (int j = 0; j < CPT; ++j) split_bf16(p.relu ? fmaxf(y[j], 0.f) : y[j], h[j], l[j]);
+        const int hh = pix / p.W, ww = pix - hh * p.W;
+        for (int dy = 0; dy < rep; ++dy)
+          for (int dx = 0; dx < rep; ++dx) {
+            const size_t op = ((static_cast<size_t>(b) * Ho + (hh << p.up) + dy) * Wo + (ww << p.up) + dx) * p.cpad + c;
+            if constexpr (CPT == 2) {
+              *reinterpret_cast<uint32_t*>(hib + op) = pack_bf16x2(h[0], h[1]);
+              *reinterpret_cast<uint32_t*>(lob + op) = pack_bf16x2(l[0], l[1]);
+            } else {
+              hib[op] = h[0];
+              lob[op] = l[0];
+            }
           }
-        }
+      }
     }
   }
 }
@@ -318,7 +344,7 @@ int isla_fwd(const float* x, const float* mean_invstd, const float* mask, const 
   p.x = x; p.mean_invstd = mean_invstd; p.mask = mask; p.gamma = gamma; p.beta = beta; p.aff_w = aff_w; p.aff_b = aff_b;
   p.out = out; p.hi = reinterpret_cast<__nv_bfloat16*>(hi); p.lo = reinterpret_cast<__nv_bfloat16*>(lo);
   p.B = B; p.H = H; p.W = W; p.C = C; p.O = O; p.cpad = cpad; p.relu = relu; p.up = up2 ? 1 : 0;
-  const int cpt = ((C & 1) == 0 && O <= 16) ? 2 : 1;
+  const int cpt = ((C & 1) == 0 && O <= 8) ? 2 : 1;      // O > 8: the per-lane gamma / beta registers allow one channel
   int chunks;
   isla_shape(hi ? (cpad > C ? cpad : C) : C, cpt, &p.warps_c, &p.warps_p, &chunks);
   const int hw = H * W;
@@ -333,7 +359,7 @@ int isla_fwd(const float* x, const float* mean_invstd, const float* mask, const 
   } else if (O <= 8) {
     if (cpt == 2) isla_fwd_kernel<8, 2><<<grid, threads, 0, stream>>>(p); else isla_fwd_kernel<8, 1><<<grid, threads, 0, stream>>>(p);
   } else if (O <= 16) {
-    if (cpt == 2) isla_fwd_kernel<16, 2><<<grid, threads, 0, stream>>>(p); else isla_fwd_kernel<16, 1><<<grid, threads, 0, stream>>>(p);
+    isla_fwd_kernel<16, 1><<<grid, threads, 0, stream>>>(p);
   } else {
     isla_fwd_kernel<32, 1><<<grid, threads, 0, stream>>>(p);
   }
@@ -341,26 +367,79 @@ int isla_fwd(const float* x, const float* mean_invstd, const float* mask, const 
 }
 
 // ---- backward, pass 1: every reduction ---------------------------------------------------------------------------
-// sum of v[i] over the 32 lanes for all 32 indices at once: afterwards lane L holds the total of index L
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+// Sum over the 32 lanes of N per-lane values at once (N = 8, 16 or 32): afterwards the total of value i sits in the lanes
+// whose (lane / (32 / N)) == i.  N - 1 + log2(32 / N) shuffles instead of 5 N.
+template <int N>
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[N], int lane) {
 #pragma unroll
-  for (int half = 16; half >= 1; half >>= 1) {
-    const bool upper = (lane & half) != 0;
+  for (int half = N / 2; half >= 1; half >>= 1) {
+    const int bit = half * (32 / N);                 // lane bit that selects the kept half
+    const bool upper = (lane & bit) != 0;
 #pragma unroll
     for (int i = 0; i < half; ++i) {
       const float keep = upper ? v[i + half] : v[i];
       const float send = upper ? v[i] : v[i + half];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
     }
   }
-  return v[0];
+  float t = v[0];
+#pragma unroll
+  for (int off = 32 / N / 2; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+  return t;
 }
 
 template <int OM, int CPT>
-__global__ void __launch_bounds__(256) isla_bwd_reduce_kernel(const IslaBwdParams p) {
+struct IslaPix {            // one pixel's operands for a lane: x, dout (2x2 sum when up-sampled) and the O masks
+  float xv[CPT], dv[CPT], m[OM > 0 ? OM : 1];
+};
+
+template <int OM, int CPT>
+__device__ __forceinline__ void isla_load_pix(IslaPix<OM, CPT>& q, const float* __restrict__ xb, const float* __restrict__ db,
+                                              const float* __restrict__ mb, int pix, int C, int O, int W, int rep, bool c_ok) {
+  load_cpt<CPT>(xb + static_cast<size_t>(pix) * C, c_ok, q.xv);
+  if (rep == 1) {
+    load_cpt<CPT>(db + static_cast<size_t>(pix) * C, c_ok, q.dv);
+  } else {
+    const int hh = pix / W, ww = pix - hh * W;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) q.dv[j] = 0.f;
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) {
+        float t[CPT];
+        load_cpt<CPT>(db + ((static_cast<size_t>(hh) * 2 + dy) * (2 * W) + ww * 2 + dx) * C, c_ok, t);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) q.dv[j] += t[j];
+      }
+  }
+  if constexpr (OM > 0) {
+    if ((O & 3) == 0) {
+#pragma unroll
+      for (int o = 0; o < OM; o += 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o < O) v = __ldg(reinterpret_cast<const float4*>(mb + static_cast<size_t>(pix) * O + o));
+        q.m[o] = v.x; q.m[o + 1] = v.y; q.m[o + 2] = v.z; q.m[o + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int o = 0; o < OM; ++o) q.m[o] = (o < O) ? __ldg(mb + static_cast<size_t>(pix) * O + o) : 0.f;
+    }
+  }
+}
+
+template <int OM>
+__device__ __forceinline__ float isla_inv_s(const float (&m)[OM > 0 ? OM : 1]) {
+  float S = kMaskEps;
+  if constexpr (OM > 0) {
+#pragma unroll
+    for (int o = 0; o < OM; ++o) S += m[o];
+  }
+  return 1.0f / S;
+}
+
+template <int OM, int CPT>
+__global__ void __launch_bounds__(256, 2) isla_bwd_reduce_kernel(const IslaBwdParams p) {
   using Lane = IslaLane<OM, CPT>;
   constexpr int OMX = Lane::OMX;
-  constexpr int PIXG = OM > 0 ? 32 / OM : 1;        // pixels per butterfly
   extern __shared__ float sh[];                     // s_dm [seg * O]  then (reused) the block reductions
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wc = warp % p.warps_c, wp = warp / p.warps_c;
@@ -372,7 +451,6 @@ __global__ void __launch_bounds__(256) isla_bwd_reduce_kernel(const IslaBwdParam
   Lane L;
   L.load(p.mean_invstd, p.gamma, p.beta, p.aff_w, p.aff_b, b, c, p.C, p.O);
   const int hw = p.H * p.W;
-  const int Wo = p.W << p.up;
   const int rep = 1 << p.up;
   const int p0 = blockIdx.x * p.seg, p1 = min(hw, p0 + p.seg);
   if constexpr (OM > 0) {
@@ -391,82 +469,59 @@ __global__ void __launch_bounds__(256) isla_bwd_reduce_kernel(const IslaBwdParam
     for (int o = 0; o < OMX; ++o) accg[o][j] = accb[o][j] = 0.f;
   }
   int since_flush = 0;
-  for (int base = p0 + wp * PIXG; base < p1; base += p.warps_p * PIXG) {
-    float part[32];
-    float invS_q[PIXG];
+  // the warp walks pixels p0 + wp, p0 + wp + warps_p, ...; the next pixel's operands are loaded before the current
+  // one is processed (rolling prefetch)
+  IslaPix<OM, CPT> nxt;
+  int pix = p0 + wp;
+  if (pix < p1) isla_load_pix<OM, CPT>(nxt, xb, db, mb, pix, p.C, p.O, p.W, rep, c_ok);
+  for (; pix < p1; pix += p.warps_p) {
+    const IslaPix<OM, CPT> cur = nxt;
+    if (pix + p.warps_p < p1) isla_load_pix<OM, CPT>(nxt, xb, db, mb, pix + p.warps_p, p.C, p.O, p.W, rep, c_ok);
+    const float invS = isla_inv_s<OM>(cur.m);
+    float G[CPT], Bt[CPT];
+    isla_modulation<OM, CPT>(L, cur.m, G, Bt);
+    float g[CPT], gx[CPT], common = 0.f;
 #pragma unroll
-    for (int q = 0; q < PIXG; ++q) {
-      const int pix = base + q;
-      const bool ok = pix < p1 && c_ok;
-      const int pc = pix < p1 ? pix : p1 - 1;       // clamped: loads stay in bounds, contributions are zeroed
-      float xv[CPT], dv[CPT];
-      load_cpt<CPT>(xb + static_cast<size_t>(pc) * p.C, c_ok, xv);
-      if (rep == 1) {
-        load_cpt<CPT>(db + static_cast<size_t>(pc) * p.C, c_ok, dv);
-      } else {
-        const int hh = pc / p.W, ww = pc - hh * p.W;
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) dv[j] = 0.f;
-        for (int dy = 0; dy < 2; ++dy)
-          for (int dx = 0; dx < 2; ++dx) {
-            float t[CPT];
-            load_cpt<CPT>(db + ((static_cast<size_t>(hh) * 2 + dy) * Wo + ww * 2 + dx) * p.C, c_ok, t);
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) dv[j] += t[j];
-          }
-      }
-      float m[OMX];
-      float invS = 1.0f;
-      if constexpr (OM > 0) invS = isla_masks<OM>(mb + static_cast<size_t>(pc) * p.O, p.O, m);
-      invS_q[q] = invS;
-      float g[CPT], gx[CPT], common = 0.f;
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const float xh = (xv[j] - L.mean[j]) * L.invstd[j];
-        float y, fac;
-        if constexpr (OM > 0) {
-          float G = 0.f, Bt = 0.f;
-#pragma unroll
-          for (int o = 0; o < OM; ++o) { G = fmaf(m[o], L.gam[o][j], G); Bt = fmaf(m[o], L.bet[o][j], Bt); }
-          y = isla_y(G, Bt, invS, xh);
-          fac = fmaf(G, invS, 1.0f);
-        } else {
-          y = fmaf(xh, L.aw[j], L.ab[j]);
-          fac = 1.0f;                                // csum of the affine form = (sum g, sum g*xh) = (d bias, d weight)
-        }
-        g[j] = (!ok || (p.relu && !(y > 0.f))) ? 0.f : dv[j];
-        gx[j] = g[j] * xh;
-        const float dxh = g[j] * fac;
-        s1[j] += dxh;
-        s2[j] = fmaf(dxh, xh, s2[j]);
-        // d m_o * S = sum_c (g xh gamma_oc + g beta_oc) - sum_c g (y - xh): the last term is the same for every object
-        common = fmaf(g[j], y - xh, common);
-      }
+    for (int j = 0; j < CPT; ++j) {
+      const float xh = (cur.xv[j] - L.mean[j]) * L.invstd[j];
+      float y, fac;
       if constexpr (OM > 0) {
+        y = isla_y(G[j], Bt[j], invS, xh);
+        fac = fmaf(G[j], invS, 1.0f);
+      } else {
+        y = fmaf(xh, L.aw[j], L.ab[j]);
+        fac = 1.0f;                                  // csum of the affine form = (sum g, sum g*xh) = (d bias, d weight)
+      }
+      g[j] = (!c_ok || (p.relu && !(y > 0.f))) ? 0.f : cur.dv[j];
+      gx[j] = g[j] * xh;
+      const float dxh = g[j] * fac;
+      s1[j] += dxh;
+      s2[j] = fmaf(dxh, xh, s2[j]);
+      // d m_o * S = sum_c (g xh gamma_oc + g beta_oc) - sum_c g (y - xh): the last term is the same for every object
+      common = fmaf(g[j], y - xh, common);
+    }
+    if constexpr (OM > 0) {
+      float part[OM];
 #pragma unroll
-        for (int o = 0; o < OM; ++o) {
-          const float mo = m[o] * invS;
-          float acc = -common;
+      for (int o = 0; o < OM; ++o) {
+        float acc = -common;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) acc = fmaf(gx[j], L.gam[o][j], fmaf(g[j], L.bet[o][j], acc));
+        part[o] = acc;
+        if (cur.m[o] != 0.f) {                       // warp-uniform: objects that do not touch this pixel contribute 0
+          const float mo = cur.m[o] * invS;
 #pragma unroll
           for (int j = 0; j < CPT; ++j) {
             accg[o][j] = fmaf(gx[j], mo, accg[o][j]);
             accb[o][j] = fmaf(g[j], mo, accb[o][j]);
-            acc = fmaf(gx[j], L.gam[o][j], fmaf(g[j], L.bet[o][j], acc));
           }
-          part[q * OM + o] = acc;
         }
       }
+      const float tot = warp_transpose_sum<OM>(part, lane);
+      const int o = lane / (32 / OM);
+      if ((lane & (32 / OM - 1)) == 0 && o < p.O) atomicAdd(&sh[(pix - p0) * p.O + o], tot * invS);
     }
-    if constexpr (OM > 0) {
-      const float tot = warp_transpose_sum(part, lane);
-      const int q = lane / OM, o = lane - q * OM;
-      float invS = invS_q[0];
-#pragma unroll
-      for (int qq = 1; qq < PIXG; ++qq) if (q == qq) invS = invS_q[qq];
-      const int pix = base + q;
-      if (pix < p1 && o < p.O) atomicAdd(&sh[(pix - p0) * p.O + o], tot * invS);
-    }
-    if (++since_flush == 16) {                      // fold the fp32 running sums into fp64 every 16 * PIXG pixels
+    if (++since_flush == 64) {                      // fold the fp32 running sums into fp64 every 64 pixels
 #pragma unroll
       for (int j = 0; j < CPT; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; s1[j] = s2[j] = 0.f; }
       since_flush = 0;
@@ -524,7 +579,7 @@ __global__ void __launch_bounds__(256) isla_bwd_reduce_kernel(const IslaBwdParam
 
 // ---- backward, pass 2: dx (x and dout are read a second time; g and dxh are recomputed, never stored)
 template <int OM, int CPT>
-__global__ void __launch_bounds__(256) isla_bwd_dx_kernel(const IslaBwdParams p) {
+__global__ void __launch_bounds__(256, 2) isla_bwd_dx_kernel(const IslaBwdParams p) {
   using Lane = IslaLane<OM, CPT>;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wc = warp % p.warps_c, wp = warp / p.warps_c;
@@ -545,55 +600,43 @@ __global__ void __launch_bounds__(256) isla_bwd_dx_kernel(const IslaBwdParams p)
     }
   }
   const int hw = p.H * p.W;
-  const int Wo = p.W << p.up;
   const int rep = 1 << p.up;
   const float* __restrict__ xb = p.x + static_cast<size_t>(b) * hw * p.C + c;
   const float* __restrict__ db = p.dout + static_cast<size_t>(b) * hw * rep * rep * p.C + c;
   const float* __restrict__ mb = p.mask ? p.mask + static_cast<size_t>(b) * hw * p.O : nullptr;
   float* __restrict__ ob = p.dx + static_cast<size_t>(b) * hw * p.C + c;
-#pragma unroll 2
-  for (int pix = blockIdx.x * p.warps_p + wp; pix < hw; pix += gridDim.x * p.warps_p) {
-    float xv[CPT], dv[CPT];
-    load_cpt<CPT>(xb + static_cast<size_t>(pix) * p.C, true, xv);
-    if (rep == 1) {
-      load_cpt<CPT>(db + static_cast<size_t>(pix) * p.C, true, dv);
-    } else {
-      const int hh = pix / p.W, ww = pix - hh * p.W;
+  const int stride = gridDim.x * p.warps_p;
+  for (int base = blockIdx.x * p.warps_p + wp; base < hw; base += stride * kIslaU) {
+    IslaPix<OM, CPT> q[kIslaU];
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) dv[j] = 0.f;
-      for (int dy = 0; dy < 2; ++dy)
-        for (int dx = 0; dx < 2; ++dx) {
-          float t[CPT];
-          load_cpt<CPT>(db + ((static_cast<size_t>(hh) * 2 + dy) * Wo + ww * 2 + dx) * p.C, true, t);
+    for (int u = 0; u < kIslaU; ++u)
+      isla_load_pix<OM, CPT>(q[u], xb, db, mb, min(base + u * stride, hw - 1), p.C, p.O, p.W, rep, true);
 #pragma unroll
-          for (int j = 0; j < CPT; ++j) dv[j] += t[j];
+    for (int u = 0; u < kIslaU; ++u) {
+      const int pix = base + u * stride;
+      if (pix >= hw) break;
+      const float invS = isla_inv_s<OM>(q[u].m);
+      float G[CPT], Bt[CPT], r[CPT];
+      isla_modulation<OM, CPT>(L, q[u].m, G, Bt);
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const float xh = (q[u].xv[j] - L.mean[j]) * L.invstd[j];
+        float y, fac;
+        if constexpr (OM > 0) {
+          y = isla_y(G[j], Bt[j], invS, xh);
+          fac = fmaf(G[j], invS, 1.0f);
+        } else {
+          y = fmaf(xh, L.aw[j], L.ab[j]);
+          fac = L.aw[j];
         }
-    }
-    float m[Lane::OMX];
-    float invS = 1.0f;
-    if constexpr (OM > 0) invS = isla_masks<OM>(mb + static_cast<size_t>(pix) * p.O, p.O, m);
-    float r[CPT];
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      const float xh = (xv[j] - L.mean[j]) * L.invstd[j];
-      float y, fac;
-      if constexpr (OM > 0) {
-        float G = 0.f, Bt = 0.f;
-#pragma unroll
-        for (int o = 0; o < OM; ++o) { G = fmaf(m[o], L.gam[o][j], G); Bt = fmaf(m[o], L.bet[o][j], Bt); }
-        y = isla_y(G, Bt, invS, xh);
-        fac = fmaf(G, invS, 1.0f);
-      } else {
-        y = fmaf(xh, L.aw[j], L.ab[j]);
-        fac = L.aw[j];
+        const float g = (p.relu && !(y > 0.f)) ? 0.f : q[u].dv[j];
+        float dxh = g * fac;
+        if (p.train) dxh = dxh - m1[j] - xh * m2[j];
+        r[j] = dxh * L.invstd[j];
       }
-      const float g = (p.relu && !(y > 0.f)) ? 0.f : dv[j];
-      float dxh = g * fac;
-      if (p.train) dxh = dxh - m1[j] - xh * m2[j];
-      r[j] = dxh * L.invstd[j];
+      float* op = ob + static_cast<size_t>(pix) * p.C;
+      if constexpr (CPT == 2) *reinterpret_cast<float2*>(op) = make_float2(r[0], r[1]); else op[0] = r[0];
     }
-    float* op = ob + static_cast<size_t>(pix) * p.C;
-    if constexpr (CPT == 2) *reinterpret_cast<float2*>(op) = make_float2(r[0], r[1]); else op[0] = r[0];
   }
 }
 
@@ -660,7 +703,7 @@ int isla_bwd(const float* x, const float* mean_invstd, const float* mask, const 
   }
   {
     // ---- pass 2 (phase 2: csum has been reduced across ranks by the caller)
-    const int cpt = ((C & 1) == 0 && O <= 16) ? 2 : 1;
+    const int cpt = ((C & 1) == 0 && O <= 8) ? 2 : 1;      // O > 8: the per-lane gamma / beta registers allow one channel
     int chunks;
     isla_shape(C, cpt, &p.warps_c, &p.warps_p, &chunks);
     long long bx = (hw + p.warps_p * 4 - 1) / (p.warps_p * 4);
@@ -674,7 +717,7 @@ int isla_bwd(const float* x, const float* mean_invstd, const float* mask, const 
     } else if (O <= 8) {
       if (cpt == 2) isla_bwd_dx_kernel<8, 2><<<grid, threads, 0, stream>>>(p); else isla_bwd_dx_kernel<8, 1><<<grid, threads, 0, stream>>>(p);
     } else if (O <= 16) {
-      if (cpt == 2) isla_bwd_dx_kernel<16, 2><<<grid, threads, 0, stream>>>(p); else isla_bwd_dx_kernel<16, 1><<<grid, threads, 0, stream>>>(p);
+      isla_bwd_dx_kernel<16, 1><<<grid, threads, 0, stream>>>(p);
     } else {
       isla_bwd_dx_kernel<32, 1><<<grid, threads, 0, stream>>>(p);
     }

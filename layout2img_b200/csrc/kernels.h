@@ -56,6 +56,12 @@ int roi_align_fwd(const float* feat, const float* rois, int K, int N, int H, int
                   cudaStream_t stream);
 int roi_align_bwd(const float* dout, const float* rois, int K, int N, int H, int W, int C, int P, float scale, float* dfeat,
                   cudaStream_t stream);
+int roi_prepare(const float* bbox, const long long* label, int B, int O, float img, float thresh, float* rois,
+                long long* y_sorted, int* level, int* perm, int* counts, cudaStream_t stream);
+int roi_align2_fwd(const float* feat_l, int Hl, int Wl, float scale_l, const float* feat_s, int Hs, int Ws, float scale_s,
+                   const float* rois, const int* level, int K, int N, int C, int P, float* out, cudaStream_t stream);
+int roi_align2_bwd(const float* dout, const float* rois, const int* level, int K, int N, int C, int P, int Hl, int Wl,
+                   float scale_l, float* dfeat_l, int Hs, int Ws, float scale_s, float* dfeat_s, cudaStream_t stream);
 int avgpool2_fwd(const float* x, int N, int H, int W, int C, float* out, cudaStream_t stream);
 int avgpool2_bwd(const float* dout, int N, int H, int W, int C, float* dx, cudaStream_t stream);
 // attention.cu
@@ -126,6 +132,6 @@ struct AdamTensor {       // one entry of the device-resident tensor table (48 b
   float bc2_sqrt;         // sqrt(1 - beta2^step)
 };
 int adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, double beta1, double beta2, double eps,
-              cudaStream_t stream);
+              const long long* step_dev, cudaStream_t stream);
 
 }  // namespace l2i

@@ -29,9 +29,18 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 }
 
 __global__ void __launch_bounds__(256)
-adam_kernel(const AdamTensor* __restrict__ tensors, const int2* __restrict__ chunks, int chunk_elems, AdamConsts c) {
+adam_kernel(const AdamTensor* __restrict__ tensors, const int2* __restrict__ chunks, int chunk_elems, AdamConsts c,
+            const long long* __restrict__ step_dev, double beta1, double beta2) {
   const int2 ck = chunks[blockIdx.x];
-  const AdamTensor t = tensors[ck.x];
+  AdamTensor t = tensors[ck.x];
+  if (step_dev) {
+    // graph-capturable form: the step count lives on the device (advanced by the caller before this launch), the
+    // table's step_size field holds the plain learning rate and the bias corrections are formed here, in double like
+    // torch's host code
+    const double st = static_cast<double>(*step_dev);
+    t.step_size = static_cast<float>(static_cast<double>(t.step_size) / (1.0 - pow(beta1, st)));
+    t.bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(beta2, st)));
+  }
   const long long begin = 1LL * ck.y * chunk_elems;
   long long end = begin + chunk_elems;
   if (end > t.n) end = t.n;
@@ -66,7 +75,7 @@ adam_kernel(const AdamTensor* __restrict__ tensors, const int2* __restrict__ chu
 }
 
 int adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_elems, double beta1, double beta2, double eps,
-              cudaStream_t stream) {
+              const long long* step_dev, cudaStream_t stream) {
   if (!tensors || !chunks || n_chunks <= 0 || chunk_elems <= 0 || (chunk_elems & 3)) {
     set_error("adam_step: bad arguments (n_chunks=%d chunk_elems=%d)", n_chunks, chunk_elems);
     return L2I_ERR_BAD_ARG;
@@ -74,7 +83,8 @@ int adam_step(const void* tensors, const int* chunks, int n_chunks, int chunk_el
   adam_kernel<<<n_chunks, 256, 0, stream>>>(reinterpret_cast<const AdamTensor*>(tensors),
                                             reinterpret_cast<const int2*>(chunks), chunk_elems,
                                             AdamConsts{static_cast<float>(beta2), static_cast<float>(1.0 - beta1),
-                                                       static_cast<float>(1.0 - beta2), static_cast<float>(eps)});
+                                                       static_cast<float>(1.0 - beta2), static_cast<float>(eps)},
+                                            step_dev, beta1, beta2);
   return check_launch("adam_kernel");
 }
 

@@ -560,6 +560,30 @@ def roi_align(feat, rois, scale):
     return RoiAlignFn.apply(feat, rois, scale)
 
 
+class RoiAlign2Fn(torch.autograd.Function):
+    """The object path's two RoIAligns + concatenation (rcnn_discriminator_app.py:137-146) as one launch: row k of the
+    (K,8,8,C) stack samples the large-object map (level 0, scale 1/8), the small-object map (level 1, scale 1/4), or is
+    zero (level 2: a dropped object in the fixed-shape form)."""
+
+    @staticmethod
+    def forward(ctx, feat_l, feat_s, rois, level, scale_l, scale_s):
+        feat_l, feat_s = _c(feat_l), _c(feat_s)
+        ctx.save_for_backward(rois, level)
+        ctx.meta = (tuple(feat_l.shape), tuple(feat_s.shape), scale_l, scale_s)
+        return ops.roi_align2_fwd(feat_l, scale_l, feat_s, scale_s, rois, level)
+
+    @staticmethod
+    def backward(ctx, dout):
+        rois, level = ctx.saved_tensors
+        shape_l, shape_s, scale_l, scale_s = ctx.meta
+        dl, ds = ops.roi_align2_bwd(_c(dout), rois, level, shape_l, scale_l, shape_s, scale_s)
+        return dl, ds, None, None, None, None
+
+
+def roi_align2(feat_l, feat_s, rois, level, scale_l=1.0 / 8.0, scale_s=1.0 / 4.0):
+    return RoiAlign2Fn.apply(feat_l, feat_s, rois, level, scale_l, scale_s)
+
+
 class MasksToLayoutFn(torch.autograd.Function):
     """utils/bilinear.py:137-158 (grid_sample paste of per-object masks into the layout map)."""
 

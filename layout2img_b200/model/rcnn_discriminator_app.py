@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as L
+from .. import ops
 from ..sn_group import prepare_network
 from .layers import conv2d, to_nhwc
 
@@ -72,7 +73,7 @@ class ResnetDiscriminator128_app(nn.Module):
         self.l_y_app = nn.utils.spectral_norm(nn.Embedding(num_classes, ch * 8))
         self.app = nn.utils.spectral_norm(nn.Linear(ch * 16, 1))
 
-    def forward(self, x, y=None, bbox=None):         # x NHWC; bbox (K,5) rois in pixels
+    def forward(self, x, y=None, bbox=None, level=None):   # x NHWC; bbox (K,5) rois in pixels, level (K,) 0 large / 1 small / 2 dropped
         prepare_network(self)          # spectral norm of all 33 modules + every conv's operand pairs: one grouped call
         x = self.block1(x)
         x1 = self.block2(x)
@@ -82,17 +83,11 @@ class ResnetDiscriminator128_app(nn.Module):
         x = self.block6(x)
         out_im = L.proj_head(x, self.l7)                               # sum_hw relu -> SN linear (:125-127), one kernel
 
-        # small / large object paths (:131-146); order = all large then all small
-        s_idx = ((bbox[:, 3] - bbox[:, 1]) < 64) * ((bbox[:, 4] - bbox[:, 2]) < 64)
-        bbox_l, bbox_s = bbox[~s_idx], bbox[s_idx]
-        y_l, y_s = y[~s_idx], y[s_idx]
-        obj_feat_s = self.block_obj3(x1)
-        obj_feat_s = self.block_obj4(obj_feat_s)
-        obj_feat_s = L.roi_align(obj_feat_s, bbox_s, 1.0 / 4.0)
+        # small / large object paths (:131-146): rois arrive ordered [all large, all small] with their level; one launch
+        # samples both feature maps into the (K,8,8,512) stack the reference builds with two RoIAligns and a cat
+        obj_feat_s = self.block_obj4(self.block_obj3(x1))
         obj_feat_l = self.block_obj4(x2)
-        obj_feat_l = L.roi_align(obj_feat_l, bbox_l, 1.0 / 8.0)
-        obj_feat = torch.cat([obj_feat_l, obj_feat_s], dim=0)          # (K,8,8,512) NHWC
-        y = torch.cat([y_l, y_s], dim=0)
+        obj_feat = L.roi_align2(obj_feat_l, obj_feat_s, bbox, level)
 
         # appearance head (:148-157): mean_i Linear([Gram_i, e_y]) without forming the (K,512,512) Gram matrix or the
         # (K,512,1024) concat (csrc/heads.cu):  sum_i Gram[i,:] . w1 = (1/C) sum_p (sum_i F[i,p]) (sum_j F[j,p] w1[j])
@@ -109,20 +104,28 @@ class CombineDiscriminator128_app(nn.Module):
     def __init__(self, num_classes=81):
         super().__init__()
         self.obD = ResnetDiscriminator128_app(num_classes=num_classes, input_dim=3)
+        # False (default): outputs have one row per valid object, as the reference returns them (one host sync per call).
+        # True: fixed b*o rows, dropped objects as zero-feature rows flagged in `valid_mask` -- no host sync, CUDA-graph safe.
+        self.static_shapes = False
+        self.valid_mask = None
+        self.valid_count = None
 
     def forward(self, images, bbox, label, mask=None):
         if not images.is_cuda:
             raise RuntimeError("layout2img_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         dev = images.device
         b, o = bbox.size(0), bbox.size(1)
-        idx = torch.arange(start=0, end=b, device=dev).view(b, 1, 1).expand(-1, o, -1).float()
-        bbox = bbox.to(dev).float().clone()          # the reference edits a GPU-resident bbox in place (:408-409)
-        bbox[:, :, 2] = bbox[:, :, 2] + bbox[:, :, 0]
-        bbox[:, :, 3] = bbox[:, :, 3] + bbox[:, :, 1]
-        bbox = bbox * images.size(2)
-        bbox = torch.cat((idx, bbox), dim=2).view(-1, 5)
-        label = label.to(dev).view(-1)
-        keep = (label != 0).nonzero().view(-1)
-        bbox = bbox[keep]
-        label = label[keep]
-        return self.obD(to_nhwc(images), label, bbox)
+        # :402-417 and the small / large partition of :131-134 on the device (csrc/roi_align.cu roi_prepare): bit-exact
+        # rois in the reference's order [large ..., small ...], dropped (label 0) rows last, counts on the device
+        rois, y, level, _, counts = ops.roi_prepare(bbox.to(dev).float().contiguous(),
+                                                    label.to(dev).to(torch.int64).reshape(-1).contiguous(), float(images.size(2)))
+        if self.static_shapes:
+            # graph-capturable form: all b*o rows are processed (dropped rows as zero features), no host round trip;
+            # `valid_mask` (b*o,) marks the rows the losses may use, `valid_count` their number (device scalars)
+            self.valid_mask = level < 2
+            self.valid_count = counts.sum()
+        else:
+            k = int(counts.sum())                     # the one host synchronisation of the call: output rows = valid objects
+            rois, y, level = rois[:k], y[:k], level[:k]
+            self.valid_mask = self.valid_count = None
+        return self.obD(to_nhwc(images), y, rois, level)

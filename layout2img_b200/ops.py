@@ -429,6 +429,42 @@ def roi_align_bwd(dout, rois, scale: float, shape, P: int = 8):
     return dfeat
 
 
+def roi_prepare(bbox: torch.Tensor, label: torch.Tensor, img_size: float, small_thresh: float = 64.0):
+    """bbox (B,O,4) xywh fp32, label (B*O,) int64 on the device -> (rois (B*O,5), y_sorted (B*O,), level (B*O,) int32,
+    perm (B*O,) int32, counts (2,) int32 = (n_large, n_small)); rows ordered [large, small, dropped].  No host sync."""
+    _chk(bbox); _chk(label, torch.int64)
+    b, o, _ = bbox.shape
+    k = b * o
+    dev = bbox.device
+    rois = torch.empty((k, 5), dtype=torch.float32, device=dev)
+    y_sorted = torch.empty((k,), dtype=torch.int64, device=dev)
+    meta = torch.empty((2 * k + 2,), dtype=torch.int32, device=dev)
+    level, perm, counts = meta[:k], meta[k:2 * k], meta[2 * k:]
+    call("l2i_roi_prepare", bbox, label, b, o, float(img_size), float(small_thresh), rois, y_sorted, level, perm, counts)
+    return rois, y_sorted, level, perm, counts
+
+
+def roi_align2_fwd(feat_l, scale_l: float, feat_s, scale_s: float, rois, level, P: int = 8):
+    _chk(feat_l); _chk(feat_s)
+    n, hl, wl, c = feat_l.shape
+    _, hs, ws, _ = feat_s.shape
+    k = rois.shape[0]
+    out = torch.empty((k, P, P, c), dtype=torch.float32, device=feat_l.device)
+    call("l2i_roi_align2_fwd", feat_l, hl, wl, float(scale_l), feat_s, hs, ws, float(scale_s), rois, level, k, n, c, P, out)
+    return out
+
+
+def roi_align2_bwd(dout, rois, level, shape_l, scale_l: float, shape_s, scale_s: float, P: int = 8):
+    n, hl, wl, c = shape_l
+    _, hs, ws, _ = shape_s
+    k = rois.shape[0]
+    dl = torch.empty(shape_l, dtype=torch.float32, device=dout.device)
+    ds = torch.empty(shape_s, dtype=torch.float32, device=dout.device)
+    call("l2i_roi_align2_bwd", _chk(dout) if k else None, rois if k else None, level if k else None, k, n, c, P, hl, wl,
+         float(scale_l), dl, hs, ws, float(scale_s), ds)
+    return dl, ds
+
+
 def avgpool2_fwd(x):
     _chk(x)
     n, h, w, c = x.shape

@@ -26,9 +26,14 @@ CHUNK = 16384            # elements per CTA
 
 class FusedAdam:
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 amsgrad: bool = False):
+                 amsgrad: bool = False, capturable: bool = False):
         if weight_decay != 0.0 or amsgrad:
             raise ValueError("FusedAdam implements the reference's configuration: weight_decay=0, amsgrad=False")
+        # capturable: every step issues the same device work (one counter increment + one kernel over a STATIC table), so
+        # it can be recorded in a CUDA graph.  Needs every parameter's .grad at a fixed address (train.GradBuckets) and
+        # gives all tensors one common step count kept on the device.
+        self.capturable = bool(capturable)
+        self._step_dev = None
         self.defaults = {"lr": float(lr), "betas": tuple(float(b) for b in betas), "eps": float(eps)}
         self.param_groups: List[dict] = []
         self.state: Dict[torch.Tensor, dict] = {}
@@ -90,6 +95,37 @@ class FusedAdam:
             "np": [h.numpy().view(_ENTRY) for h in hosts], "events": [None, None], "slot": 0,
         }
 
+    def _step_capturable(self, items):
+        pl = self._plan
+        beta1, beta2 = self.betas
+        if pl.get("static_ptrs") is None:
+            tab = pl["np"][0]
+            ptrs = []
+            for i, (p, grp) in enumerate(items):
+                if p.grad is None or p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
+                    raise ValueError("capturable FusedAdam needs every .grad allocated at a fixed address (train.GradBuckets)")
+                st = self.state[p]
+                tab[i] = (p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
+                          grp["lr"], 1.0)
+                ptrs.append((p.data_ptr(), p.grad.data_ptr()))
+            pl["table"].copy_(pl["hosts"][0])
+            torch.cuda.current_stream().synchronize()
+            pl["static_ptrs"] = ptrs
+            first = max(int(self.state[p]["step"]) for p, _ in items)
+            self._step_dev = torch.full((1,), first, dtype=torch.int64, device=pl["dev"])
+        elif not torch.cuda.is_current_stream_capturing():
+            if pl["static_ptrs"] != [(p.data_ptr(), p.grad.data_ptr() if p.grad is not None else 0) for p, _ in items]:
+                raise RuntimeError("capturable FusedAdam: a parameter or gradient moved since the table was built")
+        self._step_dev.add_(1)
+        call("l2i_adam_step", pl["table"], pl["chunks"], pl["n_chunks"], CHUNK, beta1, beta2, self.eps, self._step_dev)
+
+    def sync_step_counts(self):
+        """capturable mode keeps the step count on the device; copy it into state[p]['step'] (before state_dict())."""
+        if self._step_dev is not None:
+            t = int(self._step_dev.item())
+            for st in self.state.values():
+                st["step"] = t
+
     @torch.no_grad()
     def step(self):
         items = self._tensors()
@@ -97,6 +133,8 @@ class FusedAdam:
             return
         if self._plan is None or self._plan["ids"] != [id(p) for p, _ in items]:
             self._build_plan(items)
+        if self.capturable:
+            return self._step_capturable(items)
         pl = self._plan
         beta1, beta2 = self.betas
         slot = pl["slot"] = pl["slot"] ^ 1      # two pinned staging tables: never rewrite one still being copied
@@ -120,7 +158,7 @@ class FusedAdam:
         ev = torch.cuda.Event()
         ev.record()
         pl["events"][slot] = ev
-        call("l2i_adam_step", pl["table"], pl["chunks"], pl["n_chunks"], CHUNK, beta1, beta2, self.eps)
+        call("l2i_adam_step", pl["table"], pl["chunks"], pl["n_chunks"], CHUNK, beta1, beta2, self.eps, None)
         # the raw-pointer update bypasses autograd's version counters: bump them so that a stale graph that saved one of
         # these parameters fails loudly in backward instead of silently using the new values
         if _HAS_SET_VERSION:
@@ -140,6 +178,7 @@ class FusedAdam:
     # ------------------------------------------------------------------------------------------
     # torch.optim-compatible (de)serialisation: {"state": {index: {...}}, "param_groups": [{..., "params": [indices]}]}
     def state_dict(self) -> dict:
+        self.sync_step_counts()
         index, groups = {}, []
         for g in self.param_groups:
             ids = []

@@ -14,14 +14,14 @@ import torch.nn.functional as F
 LAMB_OBJ, LAMB_IMG, LAMB_APP = 1.0, 0.1, 1.0       # train_context_app_v2.py:40-46
 
 
-def make_optimizers(netG, netD, g_lr: float = 1e-4, d_lr: float = 1e-4):
+def make_optimizers(netG, netD, g_lr: float = 1e-4, d_lr: float = 1e-4, capturable: bool = False):
     """Adam(betas=(0, 0.999)) with one param group per tensor (train_context_app_v2.py:113-127; 'mapping' parameters
     would get 0.1 x lr there -- the app_v2 generator's mapping is an empty nn.Sequential), executed as one multi-tensor
     kernel per network (optim.FusedAdam -> csrc/optim.cu)."""
     from .optim import FusedAdam
     g_opt = FusedAdam([{"params": [p], "lr": g_lr * (0.1 if "mapping" in n else 1.0)} for n, p in netG.named_parameters()],
-                      betas=(0.0, 0.999))
-    d_opt = FusedAdam([{"params": [p], "lr": d_lr} for p in netD.parameters()], betas=(0.0, 0.999))
+                      betas=(0.0, 0.999), capturable=capturable)
+    d_opt = FusedAdam([{"params": [p], "lr": d_lr} for p in netD.parameters()], betas=(0.0, 0.999), capturable=capturable)
     return g_opt, d_opt
 
 
@@ -42,26 +42,34 @@ class _frozen:
             p.requires_grad_(True)
 
 
-def _obj_mean(x, obj_scale):
-    """Mean over the objects of the GLOBAL batch.  Single process: x.mean().  Data parallel: the reference's DataParallel
-    gathers every replica's (K_r, 1) outputs and takes one mean over sum_r K_r rows (train_context_app_v2.py:159-161);
-    with per-rank losses followed by a gradient AVERAGE over W ranks that is sum_local * W / sum_r K_r
-    (obj_scale = W / sum_r K_r, a device scalar) -- identical to the plain mean when every rank has the same K."""
+def _obj_mean(x, obj_scale, valid=None):
+    """Mean over the (valid) objects of the GLOBAL batch.
+    Single process: x.mean().  Data parallel: the reference's DataParallel gathers every replica's (K_r, 1) outputs and takes
+    one mean over sum_r K_r rows (train_context_app_v2.py:159-161); with per-rank losses followed by a gradient AVERAGE over
+    W ranks that is sum_local * W / sum_r K_r (obj_scale = W / sum_r K_r, a device scalar) -- identical to the plain mean
+    when every rank has the same K.  Fixed-shape discriminator (static_shapes): x has b*o rows, `valid` (b*o,) flags the
+    real objects; dropped rows get weight 0, so nothing flows back into them."""
+    if valid is not None:
+        x = x * valid.view(-1, 1).to(x.dtype)
+        if obj_scale is None:
+            return x.sum() / valid.sum().clamp_min(1).to(x.dtype)
+        return x.sum() * obj_scale
     return x.mean() if obj_scale is None else x.sum() * obj_scale
 
 
-def d_loss_fn(real_out, fake_out, obj_scale=None):
+def d_loss_fn(real_out, fake_out, obj_scale=None, valid=None):
     r_im, r_obj, r_app = real_out
     f_im, f_obj, f_app = fake_out
-    return (LAMB_OBJ * (_obj_mean(F.relu(1.0 - r_obj), obj_scale) + _obj_mean(F.relu(1.0 + f_obj), obj_scale))
+    om = lambda t: _obj_mean(t, obj_scale, valid)
+    return (LAMB_OBJ * (om(F.relu(1.0 - r_obj)) + om(F.relu(1.0 + f_obj)))
             + LAMB_IMG * (F.relu(1.0 - r_im).mean() + F.relu(1.0 + f_im).mean())
-            + LAMB_APP * (_obj_mean(F.relu(1.0 - r_app), obj_scale) + _obj_mean(F.relu(1.0 + f_app), obj_scale)))
+            + LAMB_APP * (om(F.relu(1.0 - r_app)) + om(F.relu(1.0 + f_app))))
 
 
-def g_loss_fn(g_out, fake, real, obj_scale=None, feat_loss=None):
+def g_loss_fn(g_out, fake, real, obj_scale=None, feat_loss=None, valid=None):
     g_im, g_obj, g_app = g_out
-    loss = (-_obj_mean(g_obj, obj_scale) * LAMB_OBJ - g_im.mean() * LAMB_IMG + (fake - real).abs().mean()
-            - LAMB_APP * _obj_mean(g_app, obj_scale))
+    loss = (-_obj_mean(g_obj, obj_scale, valid) * LAMB_OBJ - g_im.mean() * LAMB_IMG + (fake - real).abs().mean()
+            - LAMB_APP * _obj_mean(g_app, obj_scale, valid))
     if feat_loss is not None:                            # train_context_app_v2.py:185-187 (VGGLoss, utils/util.py:49-94)
         loss = loss + feat_loss(fake, real).mean()
     return loss
@@ -205,9 +213,10 @@ def train_step(netG, netD, g_opt, d_opt, real, label, bbox, z, z_im=None, sync_g
     else:
         netD.zero_grad()
     real_out = netD(real, bbox, lab3)
+    valid = getattr(netD, "valid_mask", None)        # fixed-shape discriminator: flags of the real objects (else None)
     fake = netG(z, bbox, z_im, y=label.view(label.shape[0], -1))
     fake_out = netD(fake.detach(), bbox, lab3)
-    d_loss = d_loss_fn(real_out, fake_out, obj_scale)
+    d_loss = d_loss_fn(real_out, fake_out, obj_scale, valid)
     d_loss.backward()
     if sync_d is not None:
         sync_d.finish()
@@ -221,7 +230,7 @@ def train_step(netG, netD, g_opt, d_opt, real, label, bbox, z, z_im=None, sync_g
         netG.zero_grad()
     with _frozen(netD):
         g_out = netD(fake, bbox, lab3)
-        g_loss = g_loss_fn(g_out, fake, real, obj_scale, feat_loss)
+        g_loss = g_loss_fn(g_out, fake, real, obj_scale, feat_loss, valid)
         g_loss.backward()
     if sync_g is not None:
         sync_g.finish()
@@ -229,3 +238,54 @@ def train_step(netG, netD, g_opt, d_opt, real, label, bbox, z, z_im=None, sync_g
         record("g")
     g_opt.step()
     return d_loss.detach(), g_loss.detach(), fake.detach()
+
+
+class GraphedTrainStep:
+    """The whole training iteration (D step + G step, both optimizer updates) recorded ONCE as a CUDA graph and replayed
+    from static input buffers: one graph launch per step instead of ~1 500 kernel launches issued from Python, and no
+    host synchronisation anywhere.  Requirements, all arranged here:
+
+      * the discriminator runs in its fixed-shape form (`static_shapes`: device-side ROI compaction, dropped objects as
+        zero-feature rows that the masked losses ignore) -- the eager form's output size depends on the labels;
+      * gradients live at fixed addresses (GradBuckets views) and the optimizers are `FusedAdam(capturable=True)` (step
+        count on the device, static tensor table).
+
+    Numerically the replay IS the eager fixed-shape step (same kernels, same order).  `__call__` copies the batch into the
+    static buffers (device or pinned-host sources) and replays; it returns the static (d_loss, g_loss, fake) tensors,
+    valid until the next call."""
+
+    def __init__(self, netG, netD, g_opt, d_opt, real, label, bbox, z, z_im, warmup: int = 3, feat_loss=None):
+        if not (getattr(g_opt, "capturable", False) and getattr(d_opt, "capturable", False)):
+            raise ValueError("GraphedTrainStep needs FusedAdam(..., capturable=True) optimizers (make_optimizers(capturable=True))")
+        dev = real.device
+        if dev.type != "cuda":
+            raise RuntimeError("layout2img_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        netD.static_shapes = True
+        self.netG, self.netD, self.g_opt, self.d_opt, self.feat_loss = netG, netD, g_opt, d_opt, feat_loss
+        self.sync_g, self.sync_d = GradBuckets(netG), GradBuckets(netD)
+        self.static = {"real": real.clone(), "label": label.clone(), "bbox": bbox.to(dev).float().clone(), "z": z.clone(),
+                       "z_im": z_im.clone()}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):       # builds every lazily created table / workspace outside the capture
+                self._step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._step()
+        self.warmup_steps = max(1, warmup)        # eager steps already applied to the networks (capture itself executes nothing)
+
+    def _step(self):
+        s = self.static
+        return train_step(self.netG, self.netD, self.g_opt, self.d_opt, s["real"], s["label"], s["bbox"], s["z"], s["z_im"],
+                          sync_g=self.sync_g, sync_d=self.sync_d, feat_loss=self.feat_loss)
+
+    def __call__(self, real, label, bbox, z, z_im):
+        s = self.static
+        for k, v in (("real", real), ("label", label), ("bbox", bbox), ("z", z), ("z_im", z_im)):
+            if v is not s[k]:
+                s[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.out

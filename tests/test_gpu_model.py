@@ -289,3 +289,87 @@ def test_grouped_spectral_norm_equals_per_module_path():
         # the two paths differ by the summation order of the power iteration's atomics (1e-7 relative on sigma); a ReLU
         # input within that distance of 0 flips and moves a gradient element by one pixel's contribution
         close(p1.grad, p2.grad, 1e-3, 1e-3 * max(m, 1e-30), "grad " + n)
+
+
+def test_device_roi_preparation_is_bit_exact():
+    """ops.roi_prepare (csrc/roi_align.cu) against the oracle's restatement of rcnn_discriminator_app.py:402-417,131-146:
+    rois, labels and their [large, small] order bit for bit, dropped (label 0) rows last; no host synchronisation."""
+    from layout2img_b200 import ops
+    dev = torch.device("cuda:0")
+    for b, o, n_pad, seed in ((2, 4, 0, 1), (5, 8, 3, 2), (64, 8, 1, 3), (32, 31, 5, 4)):
+        data = synthetic_layout(b, o, 184, seed=seed, n_pad=n_pad)
+        rois, lab = O.d_rois(data["bbox"], data["label"], 128)
+        small = ((rois[:, 3] - rois[:, 1]) < 64) & ((rois[:, 4] - rois[:, 2]) < 64)
+        want_rois = torch.cat([rois[~small], rois[small]])
+        want_y = torch.cat([lab[~small], lab[small]])
+        g_rois, g_y, level, perm, counts = ops.roi_prepare(data["bbox"].to(dev), data["label"].to(dev).reshape(-1), 128.0)
+        nl, ns = counts.tolist()
+        assert (nl, ns) == (int((~small).sum()), int(small.sum()))
+        k = nl + ns
+        assert torch.equal(g_rois[:k].cpu(), want_rois) and torch.equal(g_y[:k].cpu(), want_y)
+        assert level[:nl].eq(0).all() and level[nl:k].eq(1).all() and level[k:].eq(2).all() and g_y[k:].eq(0).all()
+        assert sorted(perm.tolist()) == list(range(b * o))
+
+
+def test_static_shape_discriminator_equals_dynamic():
+    """CombineDiscriminator128_app.static_shapes (fixed b*o rows, dropped objects zero-filled and masked out of the
+    losses) against the default form (one row per valid object): same outputs on the valid rows, same gradients."""
+    import copy
+    from layout2img_b200.train import d_loss_fn
+    dev = torch.device("cuda:0")
+    z, meta = load_case("Cpad")
+    data = _data(meta)
+    _, D, _, _ = _build(meta, dev)
+    D2 = copy.deepcopy(D)
+    D2.static_shapes = True
+    D.train(); D2.train()
+    real, fake = data["real"].to(dev), (data["real"].flip(0) * 0.5).to(dev)
+    args = (data["bbox"].to(dev), data["label"].to(dev).unsqueeze(-1))
+    o1r, o1f = D(real, *args), D(fake, *args)
+    d_loss_fn(o1r, o1f).backward()
+    o2r, o2f = D2(real, *args), D2(fake, *args)
+    valid = D2.valid_mask
+    k = int(valid.sum())
+    assert o2r[1].shape[0] == meta["batch"] * meta["num_obj"] and k == o1r[1].shape[0] < o2r[1].shape[0]
+    d_loss_fn(o2r, o2f, valid=valid).backward()
+    for a, b in zip(o1r + o1f, o2r + o2f):
+        close(b[:a.shape[0]], a, 1e-5, 1e-6, "static vs dynamic output")
+    for (n, p1), (_, p2) in zip(D.named_parameters(), D2.named_parameters()):
+        m = p1.grad.abs().max().item()
+        close(p2.grad, p1.grad, 1e-3, 1e-3 * max(m, 1e-30), "static vs dynamic grad " + n)
+
+
+def test_graphed_train_step_matches_eager():
+    """train.GraphedTrainStep: the captured-and-replayed iteration must track the eager fixed-shape iteration from the
+    same initial state (same kernels; only the summation order of atomics differs between runs)."""
+    import copy
+    from layout2img_b200.train import GraphedTrainStep, make_optimizers, train_step
+    dev = torch.device("cuda:0")
+    z, meta = load_case("Cpad")
+    data = {k: v.to(dev) for k, v in _data(meta).items()}
+    G, D, _, _ = _build(meta, dev)
+    G.train(); D.train()
+    keep = torch.ones(meta["batch"], 100, device=dev)      # on the device: a host tensor would be copied inside the capture
+    G.res4.conv_mask[0].dropout_mask = keep
+    G2, D2 = copy.deepcopy(G), copy.deepcopy(D)
+    G2.res4.conv_mask[0].dropout_mask = keep
+    D.static_shapes = True
+    g_opt, d_opt = make_optimizers(G, D)
+    g_opt2, d_opt2 = make_optimizers(G2, D2, capturable=True)
+    args = (data["real"], data["label"], data["bbox"], data["z"], data["z_im"])
+    graphed = GraphedTrainStep(G2, D2, g_opt2, d_opt2, *args, warmup=2)
+    for _ in range(graphed.warmup_steps):
+        e = train_step(G, D, g_opt, d_opt, *args)
+    for i in range(2):                                   # replays vs eager steps
+        e = train_step(G, D, g_opt, d_opt, *args)
+        g = graphed(*args)
+        close(g[0], e[0], 2e-3, 2e-3, f"d_loss replay {i}")
+        close(g[1], e[1], 2e-3, 2e-3, f"g_loss replay {i}")
+        close(g[2], e[2], 1e-2, 5e-3, f"fake replay {i}")
+    torch.cuda.synchronize()
+    # the optimizers advanced on the device: warm-up + 2 replays
+    d_opt2.sync_step_counts()
+    assert next(iter(d_opt2.state.values()))["step"] == graphed.warmup_steps + 2
+    sd1, sd2 = D.state_dict(), D2.state_dict()
+    for n in ("obD.block_obj4.conv1.weight_u", "obD.block6.conv2.weight_orig", "obD.l7.weight_orig"):
+        close(sd2[n], sd1[n], 1e-3, 2e-3, "post-replay state " + n)

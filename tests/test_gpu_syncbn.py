@@ -92,8 +92,8 @@ def _worker(rank, world, port, backend, q):
                 if e > 2e-4:
                     msgs.append(f"psp={psp} {k}: {e:.2e}")
             for k, v in pg.items():
-                if rpg[k].abs().max().item() < 1e-6:           # conv biases in front of a batch norm: true gradient is 0
-                    continue
+                if k.endswith(("conv1.bias", "conv_mask.0.bias")) or rpg[k].abs().max().item() < 1e-6:
+                    continue                                   # conv biases in front of a batch norm: the true gradient is 0
                 e = rel(v, rpg[k])
                 if e > 5e-4:
                     msgs.append(f"psp={psp} grad {k}: {e:.2e}")
