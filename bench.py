@@ -349,11 +349,11 @@ def run_ours(args, rank, local_rank, world):
     G.load_state_dict(make_state(schema_of(G), 1))      # same weights on every rank (replicated DP)
     D.load_state_dict(make_state(schema_of(D), 2))
     G.to(dev).train(); D.to(dev).train()
-    use_graph = bool(args.graph) and world == 1
+    use_graph = bool(args.graph)
     g_opt, d_opt = make_optimizers(G, D, capturable=use_graph)
     # zero-copy gradient buckets, all-reduced on a side stream while the backward pass is still running
-    sync_g = GradBuckets(G) if world > 1 else None
-    sync_d = GradBuckets(D) if world > 1 else None
+    sync_g = GradBuckets(G) if (world > 1 and not use_graph) else None      # (graph mode: GraphedTrainStep owns them)
+    sync_d = GradBuckets(D) if (world > 1 and not use_graph) else None
 
     host = synthetic_layout(B, NUM_OBJ, NUM_CLASSES, seed=rank)
     host = {k: v.pin_memory() for k, v in host.items()}

@@ -340,36 +340,46 @@ def test_static_shape_discriminator_equals_dynamic():
 
 
 def test_graphed_train_step_matches_eager():
-    """train.GraphedTrainStep: the captured-and-replayed iteration must track the eager fixed-shape iteration from the
-    same initial state (same kernels; only the summation order of atomics differs between runs)."""
+    """train.GraphedTrainStep: ONE replay of the captured iteration against ONE eager fixed-shape iteration started from
+    the identical state (networks, spectral-norm / batch-norm buffers, Adam moments and step counts copied over).  Same
+    kernels in the same order: losses and the generated batch agree to rounding; post-step parameters agree up to the
+    +-lr sign flips of elements whose gradient is rounding noise (betas = (0, .999))."""
     import copy
     from layout2img_b200.train import GraphedTrainStep, make_optimizers, train_step
     dev = torch.device("cuda:0")
     z, meta = load_case("Cpad")
     data = {k: v.to(dev) for k, v in _data(meta).items()}
-    G, D, _, _ = _build(meta, dev)
-    G.train(); D.train()
+    G2, D2, _, _ = _build(meta, dev)
+    G2.train(); D2.train()
     keep = torch.ones(meta["batch"], 100, device=dev)      # on the device: a host tensor would be copied inside the capture
-    G.res4.conv_mask[0].dropout_mask = keep
-    G2, D2 = copy.deepcopy(G), copy.deepcopy(D)
     G2.res4.conv_mask[0].dropout_mask = keep
-    D.static_shapes = True
-    g_opt, d_opt = make_optimizers(G, D)
     g_opt2, d_opt2 = make_optimizers(G2, D2, capturable=True)
     args = (data["real"], data["label"], data["bbox"], data["z"], data["z_im"])
     graphed = GraphedTrainStep(G2, D2, g_opt2, d_opt2, *args, warmup=2)
-    for _ in range(graphed.warmup_steps):
-        e = train_step(G, D, g_opt, d_opt, *args)
-    for i in range(2):                                   # replays vs eager steps
-        e = train_step(G, D, g_opt, d_opt, *args)
-        g = graphed(*args)
-        close(g[0], e[0], 2e-3, 2e-3, f"d_loss replay {i}")
-        close(g[1], e[1], 2e-3, 2e-3, f"g_loss replay {i}")
-        close(g[2], e[2], 1e-2, 5e-3, f"fake replay {i}")
     torch.cuda.synchronize()
-    # the optimizers advanced on the device: warm-up + 2 replays
+    # eager twin in exactly the post-warm-up state
+    G, D = copy.deepcopy(G2), copy.deepcopy(D2)
+    G.res4.conv_mask[0].dropout_mask = keep
+    assert D.static_shapes
+    g_opt, d_opt = make_optimizers(G, D)
+    g_opt.load_state_dict(copy.deepcopy(g_opt2.state_dict()))
+    d_opt.load_state_dict(copy.deepcopy(d_opt2.state_dict()))
+    assert next(iter(d_opt.state.values()))["step"] == graphed.warmup_steps
+    e = train_step(G, D, g_opt, d_opt, *args)
+    g = graphed(*args)
+    close(g[0], e[0], 1e-4, 1e-5, "d_loss")
+    close(g[1], e[1], 1e-4, 1e-5, "g_loss")
+    close(g[2], e[2], 1e-3, 1e-4, "fake")
+    torch.cuda.synchronize()
+    d_opt2.sync_step_counts()
+    assert next(iter(d_opt2.state.values()))["step"] == graphed.warmup_steps + 1
+    for net_e, net_g, tag in ((D, D2, "D"), (G, G2, "G")):
+        sd1, sd2 = net_e.state_dict(), net_g.state_dict()
+        for n, v in sd1.items():
+            if v.is_floating_point():
+                close(sd2[n], v, 1e-3, 1e-3 if n.endswith(("_u", "_v")) else 2.5e-4, f"post-replay {tag} state {n}")
+    # a second replay runs (the graph is reusable) and keeps advancing the device-side step count
+    graphed(*args)
+    torch.cuda.synchronize()
     d_opt2.sync_step_counts()
     assert next(iter(d_opt2.state.values()))["step"] == graphed.warmup_steps + 2
-    sd1, sd2 = D.state_dict(), D2.state_dict()
-    for n in ("obD.block_obj4.conv1.weight_u", "obD.block6.conv2.weight_orig", "obD.l7.weight_orig"):
-        close(sd2[n], sd1[n], 1e-3, 2e-3, "post-replay state " + n)
