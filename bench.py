@@ -503,6 +503,17 @@ def run_ours(args, rank, local_rank, world):
             line.pop("library_baseline")
         print(json.dumps(line), flush=True)
     if world > 1:
+        # teardown must never hold the run hostage: ncclCommDestroy waits for every CUDA graph that captured the
+        # communicator, so the graph is released first, and a watchdog ends the process if the teardown still stalls
+        def _bail():
+            time.sleep(30)
+            os._exit(0)
+        threading.Thread(target=_bail, daemon=True).start()
+        if graphed is not None:
+            torch.cuda.synchronize()
+            graphed.graph.reset()
+            graphed = None
+        sys.stdout.flush()
         dist.barrier()
         dist.destroy_process_group()
     return line
@@ -515,7 +526,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--ref-batch", type=int, default=0, help="--impl reference: images per CPU step (default 8, 16 for short runs)")
-    ap.add_argument("--graph", type=int, default=0, help="1: replay the whole step as one CUDA graph (single GPU)")
+    ap.add_argument("--graph", type=int, default=1,
+                    help="1 (default): the whole iteration is ONE CUDA graph replayed from static buffers (fixed-shape "
+                         "discriminator, capturable Adam, NCCL all-reduces captured at N > 1); 0: issue it call by call")
     ap.add_argument("--no-library", action="store_true", help="skip the library_baseline leg (reference modules, PyTorch eager, same GPU)")
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (the metric is quoted at 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

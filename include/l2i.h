@@ -88,24 +88,26 @@ int l2i_bn_finalize(const double* sums, double count, int C, float eps, float mo
 int l2i_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean_invstd,
                       void* stream);
 /* out = (sum_o m_o gamma_o/(sum_o m_o + 1e-6) + 1) * xhat + sum_o m_o beta_o/(sum_o m_o + 1e-6).
- * x [B,H,W,C]; mask [B,H,W,O] (pixel-major); gamma, beta [B,O,C].  O == 0: plain batch norm with the
- * optional affine (aff_w, aff_b).  Outputs: out fp32 [B,H,W,C] (nullable) and/or the pair
- * [B,H<<up2,W<<up2,cpad] of relu ? relu(out) : out, nearest-upsampled when up2. */
+ * x [B,H,W,C]; mask [B,H,W,O] (pixel-major); gamma, beta [B,O,C]; O <= 32.  O == 0: plain batch norm with the optional
+ * affine (aff_w, aff_b) and the optional per-(image, channel) factor chan_scale [B,C] (the scaled Dropout2d keep-mask of
+ * the PSP head, resnet_generator_app_v2.py:736: relu(y) * k == relu(y * k) for k >= 0):  y = (xhat aff_w + aff_b) chan_scale.
+ * Outputs: out fp32 [B,H,W,C] (nullable; ReLU'd when relu & 2) and/or the pair [B,H<<up2,W<<up2,cpad] of
+ * (relu & 1) ? relu(y) : y, nearest-upsampled when up2. */
 int l2i_isla_fwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
-                 const float* aff_w, const float* aff_b, int B, int H, int W, int C, int O, float* out, void* hi,
-                 void* lo, int cpad, int relu, int up2, void* stream);
-/* Backward of l2i_isla_fwd followed by (relu) and (nearest x2): dout [B,H<<up2,W<<up2,C].
+                 const float* aff_w, const float* aff_b, const float* chan_scale, int B, int H, int W, int C, int O,
+                 float* out, void* hi, void* lo, int cpad, int relu, int up2, void* stream);
+/* Backward of l2i_isla_fwd followed by (relu != 0: ReLU) and (nearest x2): dout [B,H<<up2,W<<up2,C].
  * Writes dx [B,H,W,C]; for O > 0 dmask [B,H,W,O], dgamma, dbeta [B,O,C]; csum [2C] fp64 receives
  * (sum dxhat, sum dxhat*xhat) for O > 0 or (dbias, dweight) of the affine form for O == 0.
  * gbuf is unused (may be NULL; the backward writes no intermediate tensor: two passes over x and dout, 20 B per
- * element).  train = 0 skips the batch-statistics terms (eval-mode BN).  At most 32 objects per image.
+ * element).  train = 0 skips the batch-statistics terms (eval-mode BN).
  * phase 0 runs everything; for a batch norm whose statistics span several ranks (the reference's multi-GPU
  * SynchronizedBatchNorm2d, sync_batchnorm/batchnorm.py:90-111) call phase 1 (all reductions; dx untouched),
  * all-reduce csum, then phase 2 (dx) with count = the global pixel count (count <= 0: B*H*W). */
 int l2i_isla_bwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
-                 const float* aff_w, const float* aff_b, const float* dout, int B, int H, int W, int C, int O,
-                 int relu, int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum,
-                 float* dx, int phase, double count, void* stream);
+                 const float* aff_w, const float* aff_b, const float* chan_scale, const float* dout, int B, int H, int W,
+                 int C, int O, int relu, int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta,
+                 double* csum, float* dx, int phase, double count, void* stream);
 
 /* ---- layout maps (reference model/resnet_generator_app_v2.py:466-470,697-721, utils/bilinear.py:137-192)
  *      bbox [B*O,4] xywh in [0,1]; maps are [B,O,S,S] unless stated ------------------------------- */
@@ -159,6 +161,11 @@ int l2i_roi_align2_bwd(const float* dout, const float* rois, const int32_t* leve
 /* 2x2 average pooling, NHWC (F.avg_pool2d(x, 2) in the discriminator blocks). */
 int l2i_avgpool2_fwd(const float* x, int N, int H, int W, int C, float* out, void* stream);
 int l2i_avgpool2_bwd(const float* dout, int N, int H, int W, int C, float* dx, void* stream);
+
+/* 2x2 / stride 2 max pooling, NHWC (the VGG19 feature extractor of the perceptual loss, reference utils/util.py:49-94);
+ * the backward sends the gradient to the first maximum of each window, as torch does. */
+int l2i_maxpool2_fwd(const float* x, int N, int H, int W, int C, float* out, void* stream);
+int l2i_maxpool2_bwd(const float* x, const float* dout, int N, int H, int W, int C, float* dx, void* stream);
 
 /* ---- object-context attention (reference model/resnet_generator_app_v2.py:17-120,172-192), one head.
  *      q, k, v, out [B,O,D]; bbox [B,O,4]; y [B,O] int64 (0 = padding key); wg [64], bg [1];
@@ -215,6 +222,23 @@ int l2i_sn_weight_grad(const float* G, const float* W, const float* u, const flo
 int l2i_sn_prepare_group(const void* table, int n_modules, const int* wt_items, int n_wt, int wt_smem_floats,
                          const int* wv_items, int n_wv, int max_cc, const int* prep9_items, int n9, const int* prep1_items,
                          int n1, float* f32, long long f32_floats, void* bf16, int want_dgrad, void* stream);
+
+/* ---- small dense layers (replaces the cuBLAS GEMMs / ATen LayerNorm behind nn.Linear and nn.LayerNorm on the path:
+ *      attention projections resnet_generator_app_v2.py:148-151,208-212, fc :409, mask_regression.py:64, ISLA gamma / beta
+ *      projections norm_module.py:158-159, PSP stage 1x1 convolutions :741-746).  Row-major fp32. ------------------------ */
+/* y [M,N] = x [M,K] w[N,K]^T / sigma[0] + bias[N]   (sigma, bias nullable; sigma = the spectral norm from l2i_sn_sigma). */
+int l2i_linear_fwd(const float* x, const float* w, const float* sigma, const float* bias, int M, int N, int K, float* y,
+                   void* stream);
+/* dx [M,K] = dy w / sigma;  gw [N,K] = dy^T x (= dL/d(w/sigma): pass it to l2i_sn_weight_grad with taps = 1 when the layer
+ * is spectrally normalised);  db [N] = column sums of dy.  Each output nullable. */
+int l2i_linear_bwd(const float* dy, const float* x, const float* w, const float* sigma, int M, int N, int K, float* dx,
+                   float* gw, float* db, void* stream);
+/* y = LayerNorm(a + b) * w + bias over rows of D elements (b nullable); stats [rows,2] = (mean, 1/std) for the backward. */
+int l2i_add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, int rows, int D, float eps,
+                          float* y, float* stats, void* stream);
+/* ds [rows,D] = gradient of (a + b);  dw, dbias [D] (zeroed by the call). */
+int l2i_add_layernorm_bwd(const float* a, const float* b, const float* w, const float* stats, const float* dy, int rows, int D,
+                          float* ds, float* dw, float* dbias, void* stream);
 
 /* ---- discriminator output heads (reference model/rcnn_discriminator_app.py:125-127 image head, :160-166 object head,
  *      :148-157 appearance head).  feat / x: [N, P, C] fp32 (NHWC feature maps, P pixels).  w, emb are the ORIGINAL

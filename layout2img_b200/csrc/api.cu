@@ -91,16 +91,17 @@ int l2i_bn_eval_stats(const float* running_mean, const float* running_var, int C
   return bn_eval_stats(running_mean, running_var, C, eps, mean_invstd, ST(stream));
 }
 int l2i_isla_fwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
-                 const float* aff_w, const float* aff_b, int B, int H, int W, int C, int O, float* out, void* hi,
-                 void* lo, int cpad, int relu, int up2, void* stream) {
-  return isla_fwd(x, mean_invstd, mask, gamma, beta, aff_w, aff_b, B, H, W, C, O, out, hi, lo, cpad, relu, up2, ST(stream));
+                 const float* aff_w, const float* aff_b, const float* chan_scale, int B, int H, int W, int C, int O,
+                 float* out, void* hi, void* lo, int cpad, int relu, int up2, void* stream) {
+  return isla_fwd(x, mean_invstd, mask, gamma, beta, aff_w, aff_b, chan_scale, B, H, W, C, O, out, hi, lo, cpad, relu, up2,
+                  ST(stream));
 }
 int l2i_isla_bwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
-                 const float* aff_w, const float* aff_b, const float* dout, int B, int H, int W, int C, int O,
-                 int relu, int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum,
-                 float* dx, int phase, double count, void* stream) {
-  return isla_bwd(x, mean_invstd, mask, gamma, beta, aff_w, aff_b, dout, B, H, W, C, O, relu, up2, train, gbuf, dmask,
-                  dgamma, dbeta, csum, dx, phase, count, ST(stream));
+                 const float* aff_w, const float* aff_b, const float* chan_scale, const float* dout, int B, int H, int W,
+                 int C, int O, int relu, int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta,
+                 double* csum, float* dx, int phase, double count, void* stream) {
+  return isla_bwd(x, mean_invstd, mask, gamma, beta, aff_w, aff_b, chan_scale, dout, B, H, W, C, O, relu, up2, train, gbuf,
+                  dmask, dgamma, dbeta, csum, dx, phase, count, ST(stream));
 }
 int l2i_bbox_mask(const float* bbox, int BO, int H, int W, float* out, void* stream) {
   return bbox_mask(bbox, BO, H, W, out, ST(stream));
@@ -206,6 +207,32 @@ int l2i_roi_align2_fwd(const float* feat_l, int Hl, int Wl, float scale_l, const
 int l2i_roi_align2_bwd(const float* dout, const float* rois, const int32_t* level, int K, int N, int C, int P, int Hl, int Wl,
                        float scale_l, float* dfeat_l, int Hs, int Ws, float scale_s, float* dfeat_s, void* stream) {
   return roi_align2_bwd(dout, rois, level, K, N, C, P, Hl, Wl, scale_l, dfeat_l, Hs, Ws, scale_s, dfeat_s, ST(stream));
+}
+int l2i_linear_fwd(const float* x, const float* w, const float* sigma, const float* bias, int M, int N, int K, float* y,
+                   void* stream) {
+  return gemm_strided(x, K, 1, w, 1, K, M, N, K, sigma, bias, y, N, 0, ST(stream));          // y = x w^T / sigma + bias
+}
+int l2i_linear_bwd(const float* dy, const float* x, const float* w, const float* sigma, int M, int N, int K, float* dx,
+                   float* gw, float* db, void* stream) {
+  int rc = L2I_OK;
+  if (dx) rc = gemm_strided(dy, N, 1, w, K, 1, M, K, N, sigma, nullptr, dx, K, 0, ST(stream));   // dx = dy w / sigma
+  if (!rc && gw) rc = gemm_strided(dy, 1, N, x, K, 1, N, K, M, nullptr, nullptr, gw, K, 0, ST(stream));   // gw = dy^T x
+  if (!rc && db) rc = colsum(dy, M, N, db, ST(stream));
+  return rc;
+}
+int l2i_add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, int rows, int D, float eps,
+                          float* y, float* stats, void* stream) {
+  return add_layernorm_fwd(a, b, w, bias, rows, D, eps, y, stats, ST(stream));
+}
+int l2i_add_layernorm_bwd(const float* a, const float* b, const float* w, const float* stats, const float* dy, int rows, int D,
+                          float* ds, float* dw, float* dbias, void* stream) {
+  return add_layernorm_bwd(a, b, w, stats, dy, rows, D, ds, dw, dbias, ST(stream));
+}
+int l2i_maxpool2_fwd(const float* x, int N, int H, int W, int C, float* out, void* stream) {
+  return maxpool2_fwd(x, N, H, W, C, out, ST(stream));
+}
+int l2i_maxpool2_bwd(const float* x, const float* dout, int N, int H, int W, int C, float* dx, void* stream) {
+  return maxpool2_bwd(x, dout, N, H, W, C, dx, ST(stream));
 }
 int l2i_head_fwd(const float* feat, int N, int P, int C, const float* w, const float* sigma_w, const float* bias,
                  const float* emb, const float* sigma_e, const int64_t* y, float* s, float* out, void* stream) {

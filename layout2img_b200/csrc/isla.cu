@@ -151,7 +151,8 @@ struct IslaFwdParams {
   const float* beta;        // [B,O,C]
   const float* aff_w;       // [C] or null
   const float* aff_b;       // [C] or null
-  float* out;               // [B,H,W,C] fp32 (pre-ReLU) or null
+  const float* chan_scale;  // [B,C] or null: O == 0 only, y = (xh * aff_w + aff_b) * chan_scale (Dropout2d keep-mask)
+  float* out;               // [B,H,W,C] fp32 (ReLU'd when relu & 2) or null
   __nv_bfloat16* hi;        // [B,H<<up,W<<up,cpad] or null
   __nv_bfloat16* lo;
   int B, H, W, C, O, cpad, relu, up;
@@ -160,7 +161,7 @@ struct IslaFwdParams {
 
 struct IslaBwdParams {
   const float* x; const float* mean_invstd; const float* mask; const float* gamma; const float* beta;
-  const float* aff_w; const float* aff_b;
+  const float* aff_w; const float* aff_b; const float* chan_scale;
   const float* dout;        // [B,H<<up,W<<up,C]
   float* dmask;             // [B,H,W,O]  (zero-initialised when the channels span several blocks)
   float* dgamma;            // [B,O,C]  (zero-initialised, atomics)
@@ -181,10 +182,11 @@ __device__ __forceinline__ float isla_y(float G, float Bt, float invS, float xh)
 template <int OM, int CPT>
 struct IslaLane {
   static constexpr int OMX = OM > 0 ? OM : 1;
-  float mean[CPT], invstd[CPT], gam[OMX][CPT], bet[OMX][CPT], aw[CPT], ab[CPT];
+  float mean[CPT], invstd[CPT], gam[OMX][CPT], bet[OMX][CPT], aw[CPT], ab[CPT], ks[CPT];
   __device__ __forceinline__ void load(const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, const float* __restrict__ aff_w,
-                                       const float* __restrict__ aff_b, int b, int c, int C, int O) {
+                                       const float* __restrict__ aff_b, const float* __restrict__ chan_scale, int b, int c,
+                                       int C, int O) {
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
       const bool ok = c + j < C;
@@ -192,6 +194,7 @@ struct IslaLane {
       invstd[j] = ok ? __ldg(mean_invstd + C + c + j) : 0.f;
       aw[j] = (ok && aff_w) ? __ldg(aff_w + c + j) : 1.f;
       ab[j] = (ok && aff_b) ? __ldg(aff_b + c + j) : 0.f;
+      ks[j] = (ok && chan_scale) ? __ldg(chan_scale + static_cast<size_t>(b) * C + c + j) : 1.f;
 #pragma unroll
       for (int o = 0; o < OMX; ++o) {
         const bool oo = OM > 0 && ok && o < O;
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(256, 2) isla_fwd_kernel(const IslaFwdParams p)
   const bool c_ok = c < p.C;                        // C is a multiple of CPT
   const bool c_pad = p.hi && c < p.cpad;            // a pair's padding channels are written as zeros
   Lane L;
-  L.load(p.mean_invstd, p.gamma, p.beta, p.aff_w, p.aff_b, b, c, p.C, p.O);
+  L.load(p.mean_invstd, p.gamma, p.beta, p.aff_w, p.aff_b, p.chan_scale, b, c, p.C, p.O);
   const int hw = p.H * p.W;
   const int Ho = p.H << p.up, Wo = p.W << p.up;
   const int rep = 1 << p.up;
@@ -294,17 +297,19 @@ __global__ void __launch_bounds__(256, 2) isla_fwd_kernel(const IslaFwdParams p)
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
         const float xh = (xv[u][j] - L.mean[j]) * L.invstd[j];
-        if constexpr (OM > 0) y[j] = isla_y(G[j], Bt[j], invS[u], xh); else y[j] = fmaf(xh, L.aw[j], L.ab[j]);
+        if constexpr (OM > 0) y[j] = isla_y(G[j], Bt[j], invS[u], xh); else y[j] = fmaf(xh, L.aw[j], L.ab[j]) * L.ks[j];
         if (!c_ok) y[j] = 0.f;
       }
       if (outb && c_ok) {
         float* op = outb + static_cast<size_t>(pix) * p.C;
-        if constexpr (CPT == 2) *reinterpret_cast<float2*>(op) = make_float2(y[0], y[1]); else op[0] = y[0];
+        const bool r2 = (p.relu & 2) != 0;
+        if constexpr (CPT == 2) *reinterpret_cast<float2*>(op) = make_float2(r2 ? fmaxf(y[0], 0.f) : y[0], r2 ? fmaxf(y[1], 0.f) : y[1]);
+        else op[0] = r2 ? fmaxf(y[0], 0.f) : y[0];
       }
       if (c_pad) {
         __nv_bfloat16 h[CPT], l[CPT];
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) split_bf16(p.relu ? fmaxf(y[j], 0.f) : y[j], h[j], l[j]);
+        for (int j = 0; j < CPT; ++j) split_bf16((p.relu & 1) ? fmaxf(y[j], 0.f) : y[j], h[j], l[j]);
         const int hh = pix / p.W, ww = pix - hh * p.W;
         for (int dy = 0; dy < rep; ++dy)
           for (int dx = 0; dx < rep; ++dx) {
@@ -334,14 +339,15 @@ static void isla_shape(int cext, int cpt, int* warps_c, int* warps_p, int* chunk
 }
 
 int isla_fwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
-             const float* aff_w, const float* aff_b, int B, int H, int W, int C, int O, float* out, void* hi, void* lo,
-             int cpad, int relu, int up2, cudaStream_t stream) {
+             const float* aff_w, const float* aff_b, const float* chan_scale, int B, int H, int W, int C, int O, float* out,
+             void* hi, void* lo, int cpad, int relu, int up2, cudaStream_t stream) {
   if (!x || !mean_invstd || B <= 0 || H <= 0 || W <= 0 || C <= 0 || O < 0 || (!out && !hi)) { set_error("isla_fwd: bad arguments"); return L2I_ERR_BAD_ARG; }
   if (O > 0 && (!mask || !gamma || !beta)) { set_error("isla_fwd: mask/gamma/beta required when O > 0"); return L2I_ERR_BAD_ARG; }
   if (hi && (!lo || cpad % 8 || cpad < C)) { set_error("isla_fwd: bad pair arguments"); return L2I_ERR_BAD_ARG; }
   if (O > 32) { set_error("isla_fwd: at most 32 objects per image supported (got %d)", O); return L2I_ERR_UNSUPPORTED; }
   IslaFwdParams p;
   p.x = x; p.mean_invstd = mean_invstd; p.mask = mask; p.gamma = gamma; p.beta = beta; p.aff_w = aff_w; p.aff_b = aff_b;
+  p.chan_scale = (O == 0) ? chan_scale : nullptr;
   p.out = out; p.hi = reinterpret_cast<__nv_bfloat16*>(hi); p.lo = reinterpret_cast<__nv_bfloat16*>(lo);
   p.B = B; p.H = H; p.W = W; p.C = C; p.O = O; p.cpad = cpad; p.relu = relu; p.up = up2 ? 1 : 0;
   const int cpt = ((C & 1) == 0 && O <= 8) ? 2 : 1;      // O > 8: the per-lane gamma / beta registers allow one channel
@@ -449,7 +455,7 @@ __global__ void __launch_bounds__(256, 2) isla_bwd_reduce_kernel(const IslaBwdPa
   const int c = blockIdx.y * cb + cl;
   const bool c_ok = c < p.C;
   Lane L;
-  L.load(p.mean_invstd, p.gamma, p.beta, p.aff_w, p.aff_b, b, c, p.C, p.O);
+  L.load(p.mean_invstd, p.gamma, p.beta, p.aff_w, p.aff_b, p.chan_scale, b, c, p.C, p.O);
   const int hw = p.H * p.W;
   const int rep = 1 << p.up;
   const int p0 = blockIdx.x * p.seg, p1 = min(hw, p0 + p.seg);
@@ -489,8 +495,8 @@ __global__ void __launch_bounds__(256, 2) isla_bwd_reduce_kernel(const IslaBwdPa
         y = isla_y(G[j], Bt[j], invS, xh);
         fac = fmaf(G[j], invS, 1.0f);
       } else {
-        y = fmaf(xh, L.aw[j], L.ab[j]);
-        fac = 1.0f;                                  // csum of the affine form = (sum g, sum g*xh) = (d bias, d weight)
+        y = fmaf(xh, L.aw[j], L.ab[j]) * L.ks[j];
+        fac = L.ks[j];                               // csum of the affine form = (sum g ks, sum g ks xh) = (d bias, d weight)
       }
       g[j] = (!c_ok || (p.relu && !(y > 0.f))) ? 0.f : cur.dv[j];
       gx[j] = g[j] * xh;
@@ -587,7 +593,7 @@ __global__ void __launch_bounds__(256, 2) isla_bwd_dx_kernel(const IslaBwdParams
   const int c = ((blockIdx.y * p.warps_c + wc) * 32 + lane) * CPT;
   if (c >= p.C) return;
   Lane L;
-  L.load(p.mean_invstd, p.gamma, p.beta, p.aff_w, p.aff_b, b, c, p.C, p.O);
+  L.load(p.mean_invstd, p.gamma, p.beta, p.aff_w, p.aff_b, p.chan_scale, b, c, p.C, p.O);
   float m1[CPT], m2[CPT];
 #pragma unroll
   for (int j = 0; j < CPT; ++j) {
@@ -626,8 +632,8 @@ __global__ void __launch_bounds__(256, 2) isla_bwd_dx_kernel(const IslaBwdParams
           y = isla_y(G[j], Bt[j], invS, xh);
           fac = fmaf(G[j], invS, 1.0f);
         } else {
-          y = fmaf(xh, L.aw[j], L.ab[j]);
-          fac = L.aw[j];
+          y = fmaf(xh, L.aw[j], L.ab[j]) * L.ks[j];
+          fac = L.aw[j] * L.ks[j];
         }
         const float g = (p.relu && !(y > 0.f)) ? 0.f : q[u].dv[j];
         float dxh = g * fac;
@@ -641,9 +647,9 @@ __global__ void __launch_bounds__(256, 2) isla_bwd_dx_kernel(const IslaBwdParams
 }
 
 int isla_bwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
-             const float* aff_w, const float* aff_b, const float* dout, int B, int H, int W, int C, int O, int relu,
-             int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum, float* dx,
-             int phase, double count, cudaStream_t stream) {
+             const float* aff_w, const float* aff_b, const float* chan_scale, const float* dout, int B, int H, int W, int C,
+             int O, int relu, int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum,
+             float* dx, int phase, double count, cudaStream_t stream) {
   (void)gbuf;                  // no intermediate tensor is written any more; the argument is kept for ABI stability
   if (!x || !mean_invstd || !dout || !csum || !dx || B <= 0 || C <= 0) { set_error("isla_bwd: bad arguments"); return L2I_ERR_BAD_ARG; }
   if (O > 0 && (!mask || !gamma || !beta || !dmask || !dgamma || !dbeta)) { set_error("isla_bwd: null ISLA operand"); return L2I_ERR_BAD_ARG; }
@@ -651,6 +657,7 @@ int isla_bwd(const float* x, const float* mean_invstd, const float* mask, const 
   if (phase < 0 || phase > 2) { set_error("isla_bwd: phase must be 0 (all), 1 (reductions) or 2 (dx)"); return L2I_ERR_BAD_ARG; }
   IslaBwdParams p;
   p.x = x; p.mean_invstd = mean_invstd; p.mask = mask; p.gamma = gamma; p.beta = beta; p.aff_w = aff_w; p.aff_b = aff_b;
+  p.chan_scale = (O == 0) ? chan_scale : nullptr;
   p.dout = dout; p.dmask = dmask; p.dgamma = dgamma; p.dbeta = dbeta; p.csum = csum; p.dx = dx;
   p.count = count > 0 ? count : static_cast<double>(B) * H * W;   // > 0: global count of a cross-rank batch norm
   p.B = B; p.H = H; p.W = W; p.C = C; p.O = O; p.relu = relu; p.up = up2 ? 1 : 0; p.train = train; p.seg = 0;

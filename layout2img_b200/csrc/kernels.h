@@ -27,12 +27,12 @@ int bn_finalize(const double* sums, double count, int C, float eps, float moment
                 float* running_var, float* mean_invstd, cudaStream_t stream);
 int bn_eval_stats(const float* rm, const float* rv, int C, float eps, float* mean_invstd, cudaStream_t stream);
 int isla_fwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
-             const float* aff_w, const float* aff_b, int B, int H, int W, int C, int O, float* out, void* hi, void* lo,
-             int cpad, int relu, int up2, cudaStream_t stream);
+             const float* aff_w, const float* aff_b, const float* chan_scale, int B, int H, int W, int C, int O, float* out,
+             void* hi, void* lo, int cpad, int relu, int up2, cudaStream_t stream);
 int isla_bwd(const float* x, const float* mean_invstd, const float* mask, const float* gamma, const float* beta,
-             const float* aff_w, const float* aff_b, const float* dout, int B, int H, int W, int C, int O, int relu,
-             int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum, float* dx,
-             int phase, double count, cudaStream_t stream);
+             const float* aff_w, const float* aff_b, const float* chan_scale, const float* dout, int B, int H, int W, int C,
+             int O, int relu, int up2, int train, float* gbuf, float* dmask, float* dgamma, float* dbeta, double* csum,
+             float* dx, int phase, double count, cudaStream_t stream);
 
 // layout_ops.cu
 int bbox_mask(const float* bbox, int BO, int H, int W, float* out, cudaStream_t stream);
@@ -62,6 +62,8 @@ int roi_align2_fwd(const float* feat_l, int Hl, int Wl, float scale_l, const flo
                    const float* rois, const int* level, int K, int N, int C, int P, float* out, cudaStream_t stream);
 int roi_align2_bwd(const float* dout, const float* rois, const int* level, int K, int N, int C, int P, int Hl, int Wl,
                    float scale_l, float* dfeat_l, int Hs, int Ws, float scale_s, float* dfeat_s, cudaStream_t stream);
+int maxpool2_fwd(const float* x, int N, int H, int W, int C, float* out, cudaStream_t stream);
+int maxpool2_bwd(const float* x, const float* dout, int N, int H, int W, int C, float* dx, cudaStream_t stream);
 int avgpool2_fwd(const float* x, int N, int H, int W, int C, float* out, cudaStream_t stream);
 int avgpool2_bwd(const float* dout, int N, int H, int W, int C, float* dx, cudaStream_t stream);
 // attention.cu
@@ -108,6 +110,15 @@ int sn_group_sigma(const void* table, int n_modules, const int* wt_items, int n_
                    int n_wv, int max_cc, float* f32, long long f32_floats, cudaStream_t stream);
 int weight_prep_group(const void* table, const int* items9, int n9, const int* items1, int n1, const float* f32, void* bf16,
                       int want_dgrad, cudaStream_t stream);
+
+// linear.cu
+int gemm_strided(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, int M, int N, int K,
+                 const float* sigma, const float* bias, float* C, long long scm, int accumulate, cudaStream_t stream);
+int colsum(const float* X, int M, int N, float* out, cudaStream_t stream);
+int add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, int rows, int D, float eps, float* y,
+                      float* stats, cudaStream_t stream);
+int add_layernorm_bwd(const float* a, const float* b, const float* w, const float* stats, const float* dy, int rows, int D,
+                      float* ds, float* dw, float* dbias, cudaStream_t stream);
 
 // heads.cu
 int head_fwd(const float* feat, int N, int P, int C, const float* w, const float* sigma_w, const float* bias, const float* emb,

@@ -1,0 +1,179 @@
+// The small dense layers of the path as hand-written fp32 kernels (no cuBLAS / ATen on the hot path):
+//   * nn.Linear layers -- the 308-wide attention projections (resnet_generator_app_v2.py:148-151,208-212), the generator's
+//     fc (:409, 128 -> 16384), the mask-regression fc (mask_regression.py:64), the 20 ISLA gamma / beta projections
+//     (norm_module.py:158-159), the 1x1 convolutions of the PSP stages on pooled cells (:741-746) -- are one generic
+//     strided SIMT GEMM:  C[m,n] = (sum_k A(m,k) B(k,n)) / sigma + bias[n]   with arbitrary element strides, which covers
+//     y = x W^T (+ b), dx = dy W and dW = dy^T x without transposing anything.  The GEMMs are tiny (<= 0.003 GMAC per
+//     image): a 64 x 64 x 16 register-tiled fp32 kernel is ample, and keeps fp32 accumulation order deterministic.
+//   * LayerNorm(x + residual) of the attention block (:201-212), forward and backward, one warp per row.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace l2i {
+
+static constexpr int kGT = 64, kGK = 16;      // tile M = N = 64, K step 16; 256 threads, 4 x 4 outputs each
+
+__global__ void __launch_bounds__(256)
+gemm_strided_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ B, long long sbk,
+                    long long sbn, int M, int N, int K, const float* __restrict__ sigma, const float* __restrict__ bias,
+                    float* __restrict__ C, long long scm, int accumulate) {
+  __shared__ float sA[kGK][kGT + 1], sB[kGK][kGT + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * kGT, n0 = blockIdx.x * kGT;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += kGK) {
+    // 64 x 16 elements of each operand, 4 per thread; the faster-varying thread index follows the unit stride
+    for (int e = threadIdx.x; e < kGT * kGK; e += 256) {
+      int mm, kk;
+      if (sak == 1) { kk = e % kGK; mm = e / kGK; } else { mm = e % kGT; kk = e / kGT; }
+      const int m = m0 + mm, k = k0 + kk;
+      sA[kk][mm] = (m < M && k < K) ? __ldg(A + m * sam + k * sak) : 0.f;
+      int nn, kb;
+      if (sbk == 1) { kb = e % kGK; nn = e / kGK; } else { nn = e % kGT; kb = e / kGT; }
+      const int n = n0 + nn, k2 = k0 + kb;
+      sB[kb][nn] = (n < N && k2 < K) ? __ldg(B + k2 * sbk + n * sbn) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kGK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sB[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const float sg = sigma ? __ldg(sigma) : 1.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = sigma ? acc[i][j] / sg : acc[i][j];
+      if (bias) v += __ldg(bias + n);
+      float* o = C + m * scm + n;
+      *o = accumulate ? *o + v : v;
+    }
+  }
+}
+
+int gemm_strided(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, int M, int N, int K,
+                 const float* sigma, const float* bias, float* C, long long scm, int accumulate, cudaStream_t stream) {
+  if (!A || !B || !C || M < 0 || N <= 0 || K <= 0) { set_error("gemm: bad arguments (M=%d N=%d K=%d)", M, N, K); return L2I_ERR_BAD_ARG; }
+  if (M == 0) return L2I_OK;
+  dim3 grid((N + kGT - 1) / kGT, (M + kGT - 1) / kGT);
+  gemm_strided_kernel<<<grid, 256, 0, stream>>>(A, sam, sak, B, sbk, sbn, M, N, K, sigma, bias, C, scm, accumulate);
+  return check_launch("gemm_strided_kernel");
+}
+
+// column sums of a [M, N] row-major matrix (bias gradients): one block per 32 columns
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int M, int N, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (n < N)
+    for (int m = warp; m < M; m += 8) acc += __ldg(X + static_cast<size_t>(m) * N + n);
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    out[n] = t;
+  }
+}
+
+int colsum(const float* X, int M, int N, float* out, cudaStream_t stream) {
+  if (!X || !out || M <= 0 || N <= 0) { set_error("colsum: bad arguments"); return L2I_ERR_BAD_ARG; }
+  colsum_kernel<<<(N + 31) / 32, 256, 0, stream>>>(X, M, N, out);
+  return check_launch("colsum_kernel");
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm(a + b)
+// y = (s - mean) * rstd * w + bias with s = a + b (b nullable), per row of D elements; one warp per row.
+__global__ void __launch_bounds__(256)
+add_layernorm_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ w,
+                         const float* __restrict__ bias, int rows, int D, float eps, float* __restrict__ y,
+                         float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* pa = a + static_cast<size_t>(row) * D;
+  const float* pb = b ? b + static_cast<size_t>(row) * D : nullptr;
+  float s1 = 0.f;
+  for (int i = lane; i < D; i += 32) s1 += __ldg(pa + i) + (pb ? __ldg(pb + i) : 0.f);
+  const float mean = warp_sum(s1) / static_cast<float>(D);
+  float s2 = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    const float d = __ldg(pa + i) + (pb ? __ldg(pb + i) : 0.f) - mean;
+    s2 = fmaf(d, d, s2);
+  }
+  const float rstd = rsqrtf(warp_sum(s2) / static_cast<float>(D) + eps);
+  for (int i = lane; i < D; i += 32) {
+    const float d = __ldg(pa + i) + (pb ? __ldg(pb + i) : 0.f) - mean;
+    y[static_cast<size_t>(row) * D + i] = fmaf(d * rstd, __ldg(w + i), __ldg(bias + i));
+  }
+  if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+}
+
+// ds = rstd * (dy w - mean_D(dy w) - xh mean_D(dy w xh))  (gradient of both a and b);  dw += dy xh;  dbias += dy
+__global__ void __launch_bounds__(256)
+add_layernorm_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ w,
+                         const float* __restrict__ stats, const float* __restrict__ dy, int rows, int D,
+                         float* __restrict__ ds, float* __restrict__ dw, float* __restrict__ dbias) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* pa = a + static_cast<size_t>(row) * D;
+  const float* pb = b ? b + static_cast<size_t>(row) * D : nullptr;
+  const float* pd = dy + static_cast<size_t>(row) * D;
+  const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+  float c1 = 0.f, c2 = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    const float xh = (__ldg(pa + i) + (pb ? __ldg(pb + i) : 0.f) - mean) * rstd;
+    const float g = __ldg(pd + i) * __ldg(w + i);
+    c1 += g;
+    c2 = fmaf(g, xh, c2);
+  }
+  c1 = warp_sum(c1) / static_cast<float>(D);
+  c2 = warp_sum(c2) / static_cast<float>(D);
+  for (int i = lane; i < D; i += 32) {
+    const float xh = (__ldg(pa + i) + (pb ? __ldg(pb + i) : 0.f) - mean) * rstd;
+    const float d = __ldg(pd + i);
+    ds[static_cast<size_t>(row) * D + i] = rstd * (d * __ldg(w + i) - c1 - xh * c2);
+    atomicAdd(dw + i, d * xh);
+    atomicAdd(dbias + i, d);
+  }
+}
+
+int add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, int rows, int D, float eps, float* y,
+                      float* stats, cudaStream_t stream) {
+  if (!a || !w || !bias || !y || !stats || rows <= 0 || D <= 0) { set_error("add_layernorm_fwd: bad arguments"); return L2I_ERR_BAD_ARG; }
+  add_layernorm_fwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(a, b, w, bias, rows, D, eps, y, stats);
+  return check_launch("add_layernorm_fwd_kernel");
+}
+
+int add_layernorm_bwd(const float* a, const float* b, const float* w, const float* stats, const float* dy, int rows, int D,
+                      float* ds, float* dw, float* dbias, cudaStream_t stream) {
+  if (!a || !w || !stats || !dy || !ds || !dw || !dbias || rows <= 0 || D <= 0) { set_error("add_layernorm_bwd: bad arguments"); return L2I_ERR_BAD_ARG; }
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * D, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dbias, 0, sizeof(float) * D, stream);
+  if (e != cudaSuccess) { set_error("add_layernorm_bwd: memset: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
+  add_layernorm_bwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(a, b, w, stats, dy, rows, D, ds, dw, dbias);
+  return check_launch("add_layernorm_bwd_kernel");
+}
+
+}  // namespace l2i

@@ -333,6 +333,63 @@ __global__ void avgpool2_bwd_kernel(const float* __restrict__ dout, int N, int H
     *reinterpret_cast<float4*>(dx + ((1LL * n * H + h) * W + w) * C + c) = make_float4(g.x * 0.25f, g.y * 0.25f, g.z * 0.25f, g.w * 0.25f);
   }
 }
+// 2x2 / stride 2 max pooling, NHWC (torchvision VGG19 features 4, 9, 18, 27 inside the perceptual loss, reference
+// utils/util.py:49-94).  Backward routes the gradient to the FIRST maximum of the window in (row, column) order, as
+// torch's max_pool2d does.
+__global__ void maxpool2_fwd_kernel(const float* __restrict__ x, int N, int H, int W, int C, float* __restrict__ out) {
+  const int c4n = C >> 2, Ho = H >> 1, Wo = W >> 1;
+  const long long total = 1LL * N * Ho * Wo * c4n;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(i % c4n) * 4;
+    const int wo = static_cast<int>((i / c4n) % Wo), ho = static_cast<int>((i / (1LL * c4n * Wo)) % Ho);
+    const int n = static_cast<int>(i / (1LL * c4n * Wo * Ho));
+    const float* p = x + ((1LL * n * H + 2 * ho) * W + 2 * wo) * C + c;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + C));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(p + 1LL * W * C)), e = __ldg(reinterpret_cast<const float4*>(p + 1LL * W * C + C));
+    *reinterpret_cast<float4*>(out + ((1LL * n * Ho + ho) * Wo + wo) * C + c) =
+        make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)),
+                    fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w)));
+  }
+}
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout, int N, int H, int W, int C,
+                                    float* __restrict__ dx) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = 1LL * N * Ho * Wo * C;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int wo = static_cast<int>((i / C) % Wo), ho = static_cast<int>((i / (1LL * C * Wo)) % Ho);
+    const int n = static_cast<int>(i / (1LL * C * Wo * Ho));
+    const long long base = ((1LL * n * H + 2 * ho) * W + 2 * wo) * C + c;
+    const long long off[4] = {0, C, 1LL * W * C, 1LL * W * C + C};
+    float best = __ldg(x + base);
+    int arg = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float v = __ldg(x + base + off[k]);
+      if (v > best) { best = v; arg = k; }
+    }
+    const float g = __ldg(dout + i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dx[base + off[k]] = (k == arg) ? g : 0.f;
+  }
+}
+int maxpool2_fwd(const float* x, int N, int H, int W, int C, float* out, cudaStream_t stream) {
+  if (!x || !out || N <= 0 || (H & 1) || (W & 1) || (C & 3) || C <= 0) { set_error("maxpool2_fwd: need even H, W and C %% 4 == 0"); return L2I_ERR_BAD_ARG; }
+  const long long total = 1LL * N * (H / 2) * (W / 2) * (C / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  maxpool2_fwd_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, N, H, W, C, out);
+  return check_launch("maxpool2_fwd_kernel");
+}
+int maxpool2_bwd(const float* x, const float* dout, int N, int H, int W, int C, float* dx, cudaStream_t stream) {
+  if (!x || !dout || !dx || N <= 0 || (H & 1) || (W & 1) || C <= 0) { set_error("maxpool2_bwd: need even H, W"); return L2I_ERR_BAD_ARG; }
+  const long long total = 1LL * N * (H / 2) * (W / 2) * C;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  maxpool2_bwd_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, dout, N, H, W, C, dx);
+  return check_launch("maxpool2_bwd_kernel");
+}
+
 int avgpool2_fwd(const float* x, int N, int H, int W, int C, float* out, cudaStream_t stream) {
   if (!x || !out || N <= 0 || (H & 1) || (W & 1) || (C & 3) || C <= 0) { set_error("avgpool2_fwd: need even H, W and C %% 4 == 0"); return L2I_ERR_BAD_ARG; }
   const long long total = 1LL * N * (H / 2) * (W / 2) * (C / 4);

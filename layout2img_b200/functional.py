@@ -188,17 +188,14 @@ def _sn_of(conv):
 
 class SNLinearFn(torch.autograd.Function):
     """y = x @ (W_orig / sigma)^T + b for a spectrally normalised nn.Linear (the ISLA gamma/beta projections
-    norm_module.py:158-159, mask_regression.py:64, the generator's fc :409, the discriminator heads).  The power
-    iteration, sigma and the weight_orig gradient are csrc/specnorm.cu (3 + 2 launches instead of the ~15 of the
-    library hook); the two GEMMs are plain library GEMMs."""
+    norm_module.py:158-159, mask_regression.py:64, the generator's fc :409).  The power iteration, sigma and the
+    weight_orig gradient are csrc/specnorm.cu; the three GEMMs csrc/linear.cu (no library kernel)."""
 
     @staticmethod
     def forward(ctx, x, w_orig, bias, u, v, eps, training):
         st = _sigma(w_orig, (u, v, eps, training))
-        x2 = x.reshape(-1, x.shape[-1])
-        y = (x2 @ w_orig.t()) / st.sigma
-        if bias is not None:
-            y = y + bias
+        x2 = _c(x.reshape(-1, x.shape[-1]))
+        y = ops.linear_fwd(x2, _c(w_orig), st.sigma, _c(bias))
         ctx.save_for_backward(x2, w_orig, st.sigma, st.u, st.v)
         ctx.xshape = x.shape
         ctx.has_bias = bias is not None
@@ -207,16 +204,61 @@ class SNLinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x2, w_orig, sigma, u, v = ctx.saved_tensors
-        dy2 = dy.reshape(-1, dy.shape[-1])
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = ((dy2 @ w_orig) / sigma).view(ctx.xshape)
-        if ctx.needs_input_grad[1]:
-            g = (dy2.t() @ x2).contiguous()                       # dL/d(W/sigma), (R, Cc)
+        dy2 = _c(dy.reshape(-1, dy.shape[-1]))
+        need = ctx.needs_input_grad
+        dx, g, db = ops.linear_bwd(dy2, x2, _c(w_orig), sigma, need_dx=need[0], need_gw=need[1], need_db=ctx.has_bias and need[2])
+        dw = None
+        if need[1]:                                                # g = dL/d(W/sigma), (R, Cc)
             dw = ops.sn_weight_grad(g.view(g.shape[0], 1, g.shape[1]), _c(w_orig), ops.SNState(sigma, u, v))
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy2.sum(dim=0)
-        return dx, dw, db, None, None, None, None
+        return (dx.view(ctx.xshape) if dx is not None else None), dw, db, None, None, None, None
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x @ W^T + b for a plain nn.Linear (the attention projections, resnet_generator_app_v2.py:148-151,208-212) and
+    the bias-free 1x1 convolutions of the PSP stages on pooled cells (:741-746): csrc/linear.cu."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        x2 = _c(x.reshape(-1, x.shape[-1]))
+        y = ops.linear_fwd(x2, _c(w), None, _c(bias))
+        ctx.save_for_backward(x2, w)
+        ctx.xshape = x.shape
+        ctx.has_bias = bias is not None
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        dy2 = _c(dy.reshape(-1, dy.shape[-1]))
+        need = ctx.needs_input_grad
+        dx, gw, db = ops.linear_bwd(dy2, x2, _c(w), None, need_dx=need[0], need_gw=need[1], need_db=ctx.has_bias and need[2])
+        return (dx.view(ctx.xshape) if dx is not None else None), gw, db
+
+
+def linear(x, w, bias=None):
+    return LinearFn.apply(x, w, bias)
+
+
+class AddLayerNormFn(torch.autograd.Function):
+    """LayerNorm(a + b) (the two residual LayerNorms of the attention block, resnet_generator_app_v2.py:201-212)."""
+
+    @staticmethod
+    def forward(ctx, a, b, w, bias, eps):
+        a, b = _c(a), _c(b)
+        y, stats = ops.add_layernorm_fwd(a, b, _c(w), _c(bias), eps)
+        ctx.save_for_backward(a, b, w, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, b, w, stats = ctx.saved_tensors
+        ds, dw, db = ops.add_layernorm_bwd(a, b, _c(w), stats, _c(dy))
+        return ds, (ds if b is not None else None), dw, db, None
+
+
+def add_layer_norm(a, b, ln):
+    """ln: an nn.LayerNorm over the last dimension."""
+    return AddLayerNormFn.apply(a, b, ln.weight, ln.bias, ln.eps)
 
 
 class SNWeightFn(torch.autograd.Function):
@@ -250,7 +292,7 @@ def sn_linear(module, x):
     """Apply a (spectrally normalised) nn.Linear through SNLinearFn; plain nn.Linear modules are called as is."""
     w, b, sn = _sn_of(module)
     if sn is None:
-        return module(x)
+        return LinearFn.apply(x, w, b)
     return SNLinearFn.apply(x, w, b, sn[0], sn[1], sn[2], sn[3])
 
 
@@ -356,7 +398,7 @@ class NormConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, mask_pm, gamma, beta, aff_w, aff_b, weight, bias, residual, running_mean, running_var,
-                training, momentum, eps, up2, res_up2, sn):
+                training, momentum, eps, up2, res_up2, sn, chan_scale):
         x = _c(x)
         cout, cin, kh, kw = weight.shape
         taps = kh * kw
@@ -364,18 +406,18 @@ class NormConvFn(torch.autograd.Function):
             mi = ops.bn_batch_stats(x, running_mean, running_var, eps, momentum)
         else:
             mi = ops.bn_eval_stats(running_mean, running_var, eps)
-        mask_pm, gamma, beta = _c(mask_pm), _c(gamma), _c(beta)
-        _, ap = ops.isla_fwd(x, mi, mask_pm, gamma, beta, _c(aff_w), _c(aff_b), relu=True, up2=up2)
+        mask_pm, gamma, beta, chan_scale = _c(mask_pm), _c(gamma), _c(beta), _c(chan_scale)
+        _, ap = ops.isla_fwd(x, mi, mask_pm, gamma, beta, _c(aff_w), _c(aff_b), relu=True, up2=up2, chan_scale=chan_scale)
         st, wp = _sigma_and_prep(weight, sn, True)
         out, _ = ops.conv2d_fwd(ap, wp.f_hi, wp.f_lo, cout, taps, bias=_c(bias), residual=_c(residual), res_up2=res_up2)
-        ctx.save_for_backward(x, mi, mask_pm, gamma, beta, aff_w, aff_b, ap.hi, ap.lo, wp.d_hi, wp.d_lo, weight,
+        ctx.save_for_backward(x, mi, mask_pm, gamma, beta, aff_w, aff_b, ap.hi, ap.lo, wp.d_hi, wp.d_lo, weight, chan_scale,
                               *(st or (None, None, None)))
         ctx.meta = (cout, cin, taps, training, up2, res_up2, bias is not None, residual is not None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, mi, mask_pm, gamma, beta, aff_w, aff_b, ahi, alo, dhi, dlo, weight, sg, u, v = ctx.saved_tensors
+        x, mi, mask_pm, gamma, beta, aff_w, aff_b, ahi, alo, dhi, dlo, weight, chan_scale, sg, u, v = ctx.saved_tensors
         cout, cin, taps, training, up2, res_up2, has_bias, has_res = ctx.meta
         dout = _c(dout)
         dyp, _, colsum = ops.grad_split(dout, want_lo=True, up=False)
@@ -383,7 +425,7 @@ class NormConvFn(torch.autograd.Function):
         g = ops.conv2d_wgrad(dyp, ops.Pair(ahi, alo, cin), taps)
         dw = ops.sn_weight_grad(g, weight, ops.SNState(sg, u, v)) if sg is not None else _dw_to_torch(g, cout, cin, taps)
         dx, dmask, dgamma, dbeta, csum = ops.isla_bwd(x, mi, mask_pm, gamma, beta, _c(aff_w), _c(aff_b), da,
-                                                      relu=True, up2=up2, train=training)
+                                                      relu=True, up2=up2, train=training, chan_scale=chan_scale)
         daw = dab = None
         if aff_w is not None:
             daw = csum[:, 1].float()
@@ -392,13 +434,50 @@ class NormConvFn(torch.autograd.Function):
         dres = None
         if has_res:
             dres = _sum2x2(dout) if res_up2 else dout
-        return dx, dmask, dgamma, dbeta, daw, dab, dw, db, dres, None, None, None, None, None, None, None, None
+        return dx, dmask, dgamma, dbeta, daw, dab, dw, db, dres, None, None, None, None, None, None, None, None, None
 
 
 def norm_conv(x, weight, bias, running_mean, running_var, training, mask_pm=None, gamma=None, beta=None,
-              aff_w=None, aff_b=None, residual=None, up2=False, res_up2=False, momentum=0.1, eps=1e-5, sn=None):
+              aff_w=None, aff_b=None, residual=None, up2=False, res_up2=False, momentum=0.1, eps=1e-5, sn=None,
+              chan_scale=None):
+    """chan_scale (B, C): affine form only -- the scaled Dropout2d keep-mask between the ReLU and the convolution."""
     return NormConvFn.apply(x, mask_pm, gamma, beta, aff_w, aff_b, weight, bias, residual, running_mean, running_var,
-                            training, momentum, eps, up2, res_up2, sn)
+                            training, momentum, eps, up2, res_up2, sn, chan_scale)
+
+
+class BnReluFn(torch.autograd.Function):
+    """relu(batch_norm(x) * w + b) [* chan_scale] on a (..., C) fp32 tensor through the ISLA kernels' affine form
+    (csrc/isla.cu, O = 0): the nn.BatchNorm2d + ReLU of the PSP stages (resnet_generator_app_v2.py:741-746, never
+    synchronised across ranks: sync=False) and the bottleneck's BatchNorm + ReLU + Dropout2d (:736)."""
+
+    @staticmethod
+    def forward(ctx, x, aff_w, aff_b, running_mean, running_var, training, momentum, eps, chan_scale, sync):
+        x = _c(x)
+        x4 = x if x.dim() == 4 else x.reshape(x.shape[0], -1, 1, x.shape[-1])
+        if training:
+            mi = ops.bn_batch_stats(x4, running_mean, running_var, eps, momentum, sync=sync)
+        else:
+            mi = ops.bn_eval_stats(running_mean, running_var, eps)
+        chan_scale = _c(chan_scale)
+        out, _ = ops.isla_fwd(x4, mi, None, None, None, _c(aff_w), _c(aff_b), relu=False, up2=False, want_f32=True,
+                              want_pair=False, chan_scale=chan_scale, relu_f32=True)
+        ctx.save_for_backward(x4, mi, aff_w, aff_b, chan_scale)
+        ctx.meta = (training, sync, x.shape)
+        return out.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x4, mi, aff_w, aff_b, chan_scale = ctx.saved_tensors
+        training, sync, shape = ctx.meta
+        dx, _, _, _, csum = ops.isla_bwd(x4, mi, None, None, None, _c(aff_w), _c(aff_b), _c(dout).view(x4.shape), relu=True,
+                                         up2=False, train=training, chan_scale=chan_scale, sync=sync)
+        return dx.view(shape), csum[:, 1].float(), csum[:, 0].float(), None, None, None, None, None, None, None
+
+
+def bn_relu(x, bn, chan_scale=None, sync=True):
+    """x (..., C) through an nn.BatchNorm2d-like module `bn` (affine) followed by ReLU."""
+    return BnReluFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.training, bn.momentum, bn.eps,
+                          chan_scale, sync)
 
 
 class MaskTrunkFn(torch.autograd.Function):
@@ -536,6 +615,25 @@ class AvgPool2Fn(torch.autograd.Function):
 
 def avgpool2(x):
     return AvgPool2Fn.apply(x)
+
+
+class MaxPool2Fn(torch.autograd.Function):
+    """F.max_pool2d(x, 2) on NHWC (VGG19 feature extractor of the perceptual loss, reference utils/util.py:49-94)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        ctx.save_for_backward(x)
+        return ops.maxpool2_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        return ops.maxpool2_bwd(x, _c(dout))
+
+
+def maxpool2(x):
+    return MaxPool2Fn.apply(x)
 
 
 class RoiAlignFn(torch.autograd.Function):

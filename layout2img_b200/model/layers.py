@@ -28,7 +28,7 @@ class Conv2d(nn.Conv2d):
       norm = (bn_module, mask_pm, gamma, beta): fuse batch-norm/ISLA + ReLU (+ nearest x2) in front.
     """
 
-    def forward(self, x, residual=None, relu_in=False, up2_in=False, res_up2=False, norm=None):
+    def forward(self, x, residual=None, relu_in=False, up2_in=False, res_up2=False, norm=None, chan_scale=None):
         if self.stride != (1, 1) or self.kernel_size not in ((3, 3), (1, 1)) or self.dilation != (1, 1) or self.groups != 1:
             raise ValueError("layout2img_b200 Conv2d supports 3x3/pad 1 and 1x1/pad 0, stride 1 only")
         if norm is None:
@@ -38,7 +38,7 @@ class Conv2d(nn.Conv2d):
         return L.norm_conv(x, w, b, bn.running_mean, bn.running_var, bn.training,
                            mask_pm=mask_pm, gamma=gamma, beta=beta, aff_w=bn.weight if bn.affine else None,
                            aff_b=bn.bias if bn.affine else None, residual=residual, up2=up2_in, res_up2=res_up2,
-                           momentum=bn.momentum, eps=bn.eps, sn=sn)
+                           momentum=bn.momentum, eps=bn.eps, sn=sn, chan_scale=chan_scale)
 
 
 class SynchronizedBatchNorm2d(nn.BatchNorm2d):

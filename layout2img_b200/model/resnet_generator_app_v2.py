@@ -27,7 +27,7 @@ def clones(module, N):
 
 
 class BoxMultiHeadedAttention(nn.Module):
-    """reference :123-214 (h = 1).  Projections and LayerNorms are library GEMMs/ops; the relational
+    """reference :123-214 (h = 1).  Projections (csrc/linear.cu) and residual LayerNorms are libl2i kernels; the relational
     embedding, geometry gate, masked softmax and PV product are one kernel (csrc/attention.cu)."""
 
     def __init__(self, h, d_model, trignometric_embedding=True, legacy_extra_skip=False, dropout=0.1):
@@ -44,40 +44,23 @@ class BoxMultiHeadedAttention(nn.Module):
 
     def forward(self, input_query, input_key, input_value, input_box, mask=None):
         b, o, d = input_query.shape
-        q, k, v = [l(x) for l, x in zip(self.linears, (input_query, input_key, input_value))]
+        q, k, v = [L.linear(x, l.weight, l.bias) for l, x in zip(self.linears, (input_query, input_key, input_value))]
         if mask is None:
             mask = torch.ones((b, o), dtype=torch.int64, device=q.device)
         x = L.box_attention(q, k, v, input_box.to(q.device).float(), mask.to(torch.int64).contiguous(),
                             self.WGs[0].weight, self.WGs[0].bias)
         # reference :197-198: transpose then *view* -- reinterprets the (d,o) matrix as (o,d); kept.
         x = x.transpose(1, 2).contiguous().view(b, -1, self.h * self.d_k)
-        output = self.layer_norm0(x + input_query)
+        output = L.add_layer_norm(x, input_query, self.layer_norm0)           # LayerNorm(x + residual), one kernel
         new_residual = output
-        output = self.dropout(self.linears[-1](output))
-        return self.layer_norm(output + new_residual)
-
-
-def _sync_batch_norm(x, bn):
-    """Affine batch norm of an NHWC tensor with statistics over ALL ranks (sum / sum of squares all-reduced with
-    the differentiable collective, as sync_batchnorm/batchnorm.py:90-125 does across DataParallel replicas)."""
-    import torch.distributed.nn.functional as dfn
-    c = x.shape[-1]
-    x2 = x.reshape(-1, c)
-    world = ops._SYNC_BN["world"]
-    stats = torch.stack([x2.sum(0), (x2 * x2).sum(0)]).double()
-    stats = dfn.all_reduce(stats, group=ops._SYNC_BN["group"])
-    n = x2.shape[0] * world
-    mean = stats[0] / n
-    var = (stats[1] / n - mean * mean).clamp_min(0)
-    with torch.no_grad():
-        bn.running_mean.mul_(1 - bn.momentum).add_(bn.momentum * mean.float())
-        bn.running_var.mul_(1 - bn.momentum).add_(bn.momentum * (var * n / max(n - 1, 1)).float())
-    y = (x2 - mean.float()) * torch.rsqrt(var.float() + bn.eps) * bn.weight + bn.bias
-    return y.view_as(x)
+        output = self.dropout(L.linear(output, self.linears[-1].weight, self.linears[-1].bias))
+        return L.add_layer_norm(output, new_residual, self.layer_norm)
 
 
 class PSPModule(nn.Module):
-    """reference :724-752.  Tiny pooled branches stay library ops; the 528->100 3x3 bottleneck conv is ours."""
+    """reference :724-752.  Pools, stage 1x1 convolutions, their BatchNorm + ReLU, the up-sampling / concatenation, the
+    528 -> 100 3x3 bottleneck convolution and its BatchNorm / ReLU / Dropout2d all run in libl2i.so (csrc/psp.cu,
+    csrc/linear.cu, csrc/isla.cu affine form, csrc/conv_tc.cu); only the Dropout2d keep-mask is drawn by torch's RNG."""
 
     def __init__(self, features, out_features=512, sizes=(1, 2, 3, 6)):
         super().__init__()
@@ -96,30 +79,37 @@ class PSPModule(nn.Module):
         bn = nn.BatchNorm2d(out_features)
         return nn.Sequential(prior, conv, bn, nn.ReLU())
 
-    def forward(self, feats):                       # feats NHWC
+    def _bottleneck(self, feats):
+        """-> (bottleneck conv output (b,h,w,100) before its norm, Dropout2d keep-mask (b,100) scaled by 1/(1-p) or None)."""
         b, h, w, c = feats.shape
         pooled = L.psp_pool(feats)                                      # (b, 50, c): all four adaptive pools
         priors, off = [], 0
         for stage, s in zip(self.stages, self.sizes):
-            p = F.linear(pooled[:, off:off + s * s], stage[1].weight.view(stage[1].out_channels, c))   # 1x1 conv
-            p = stage[2](p.view(b, s, s, -1).permute(0, 3, 1, 2))       # nn.BatchNorm2d over the b*s*s samples
-            priors.append(F.relu(p).permute(0, 2, 3, 1).reshape(b, s * s, -1))
+            p = L.linear(pooled[:, off:off + s * s], stage[1].weight.view(stage[1].out_channels, c))   # 1x1 conv (csrc/linear.cu)
+            # nn.BatchNorm2d over the b*s*s samples + ReLU (csrc/isla.cu affine form); the reference never synchronises
+            # these plain BatchNorm2d layers across GPUs
+            priors.append(L.bn_relu(p, stage[2], sync=False))
+            if stage[2].training and stage[2].track_running_stats:
+                stage[2].num_batches_tracked.add_(1)
             off += s * s
         x = L.psp_bottleneck(feats, torch.cat(priors, dim=1), self.bottleneck[0].weight)   # (b,h,w,100)
-        bn = self.bottleneck[1]
-        if bn.training and ops._SYNC_BN["world"] > 1:
-            x = _sync_batch_norm(x, bn)                  # global-batch statistics (reference multi-GPU semantics)
-        else:
-            x = F.batch_norm(x.view(-1, x.shape[-1]), bn.running_mean, bn.running_var, bn.weight, bn.bias,
-                             bn.training, bn.momentum, bn.eps).view_as(x)
-        x = F.relu(x)
+        keep = None
         if self.training:
             if self.dropout_mask is not None:
-                keep = self.dropout_mask.to(x).view(b, 1, 1, -1)
+                keep = self.dropout_mask.to(x).view(b, -1).contiguous()
             else:
-                keep = (torch.rand((b, 1, 1, x.shape[-1]), device=x.device) >= 0.1).to(x.dtype) / 0.9
-            x = x * keep
-        return x
+                keep = (torch.rand((b, x.shape[-1]), device=x.device) >= 0.1).to(x.dtype) / 0.9
+        return x, keep
+
+    def forward(self, feats):                       # feats NHWC -> BatchNorm + ReLU + Dropout2d of the bottleneck (b,h,w,100)
+        x, keep = self._bottleneck(feats)
+        return L.bn_relu(x, self.bottleneck[1], chan_scale=keep)        # relu(y) * k == relu(y * k) for k >= 0
+
+    def forward_head(self, feats, conv):
+        """PSP head + the following 1x1 convolution (`conv_mask[1]`): the bottleneck's BatchNorm / ReLU / Dropout2d are
+        applied while the convolution's operand pair is written (functional.NormConvFn)."""
+        x, keep = self._bottleneck(feats)
+        return conv.forward(x, norm=(self.bottleneck[1], None, None, None), chan_scale=keep)
 
 
 class ResBlock(nn.Module):
@@ -165,7 +155,7 @@ class ResBlock(nn.Module):
         if not self.predict_mask:
             return out_feat, None
         if self.psp:
-            mask = self.conv_mask[1](self.conv_mask[0](out_feat))
+            mask = self.conv_mask[0].forward_head(out_feat, self.conv_mask[1])
         else:
             t = self.conv_mask[0](out_feat)
             mask = self.conv_mask[3](t, norm=(self.conv_mask[1], None, None, None))

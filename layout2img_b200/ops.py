@@ -214,17 +214,19 @@ def _sync_sum(t: torch.Tensor):
 
 
 def bn_batch_stats(x: torch.Tensor, running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor],
-                   eps: float, momentum: float) -> torch.Tensor:
+                   eps: float, momentum: float, sync: bool = True) -> torch.Tensor:
     """x (..., C) fp32 -> mean_invstd (2, C); updates the running statistics in place (train mode).  With
-    set_sync_bn the sums are all-reduced first, so mean / variance are those of the global batch."""
+    set_sync_bn (and sync=True) the sums are all-reduced first, so mean / variance are those of the global batch."""
     _chk(x)
     c = x.shape[-1]
     pixels = x.numel() // c
     sums = torch.empty((c, 2), dtype=torch.float64, device=x.device)
     call("l2i_bn_stats", x, pixels, c, sums)
-    _sync_sum(sums)
+    world = _SYNC_BN["world"] if sync else 1
+    if world > 1:
+        _sync_sum(sums)
     mi = torch.empty((2, c), dtype=torch.float32, device=x.device)
-    call("l2i_bn_finalize", sums, float(pixels * _SYNC_BN["world"]), c, float(eps), float(momentum), running_mean,
+    call("l2i_bn_finalize", sums, float(pixels * world), c, float(eps), float(momentum), running_mean,
          running_var, mi)
     return mi
 
@@ -237,8 +239,9 @@ def bn_eval_stats(running_mean: torch.Tensor, running_var: torch.Tensor, eps: fl
 
 
 def isla_fwd(x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, relu: bool, up2: bool,
-             want_f32: bool = False, want_pair: bool = True):
-    """x (B,H,W,C); mask_pm (B,H,W,O) or None; gamma/beta (B,O,C) -> (fp32 out or None, Pair or None)."""
+             want_f32: bool = False, want_pair: bool = True, chan_scale=None, relu_f32: bool = False):
+    """x (B,H,W,C); mask_pm (B,H,W,O) or None; gamma/beta (B,O,C) -> (fp32 out or None, Pair or None).  chan_scale (B,C):
+    O == 0 only; relu_f32: the fp32 output is ReLU'd too."""
     _chk(x)
     b, h, w, c = x.shape
     o = 0 if mask_pm is None else mask_pm.shape[-1]
@@ -248,12 +251,13 @@ def isla_fwd(x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, relu: bool, up2
         s = 2 if up2 else 1
         buf = torch.empty((2, b, h * s, w * s, pad8(c)), dtype=torch.bfloat16, device=x.device)
         pair = Pair(buf[0], buf[1], c)
-    call("l2i_isla_fwd", x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, b, h, w, c, o, out,
-         pair.hi if pair else None, pair.lo if pair else None, pad8(c), int(relu), int(up2))
+    call("l2i_isla_fwd", x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, chan_scale, b, h, w, c, o, out,
+         pair.hi if pair else None, pair.lo if pair else None, pad8(c), int(bool(relu)) | (2 if relu_f32 else 0), int(up2))
     return out, pair
 
 
-def isla_bwd(x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, dout, relu: bool, up2: bool, train: bool):
+def isla_bwd(x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, dout, relu: bool, up2: bool, train: bool,
+             chan_scale=None, sync: bool = True):
     """-> dx (B,H,W,C), dmask_pm (B,H,W,O) | None, dgamma, dbeta (B,O,C) | None, csum (C,2) fp64."""
     _chk(x); _chk(dout)
     b, h, w, c = x.shape
@@ -263,9 +267,9 @@ def isla_bwd(x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, dout, relu: boo
     dmask = torch.empty_like(mask_pm) if o else None
     dgamma = torch.empty_like(gamma) if o else None
     dbeta = torch.empty_like(beta) if o else None
-    args = (x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, dout, b, h, w, c, o, int(relu), int(up2), int(train),
-            None, dmask, dgamma, dbeta, csum, dx)
-    if train and _SYNC_BN["world"] > 1:
+    args = (x, mean_invstd, mask_pm, gamma, beta, aff_w, aff_b, chan_scale, dout, b, h, w, c, o, int(relu), int(up2),
+            int(train), None, dmask, dgamma, dbeta, csum, dx)
+    if train and sync and _SYNC_BN["world"] > 1:
         # global-batch norm: reduce (sum d xhat, sum d xhat * xhat) over the ranks between the two phases.  For the
         # affine form (O == 0) csum also carries the LOCAL (d bias, d weight); keep a copy for the caller.
         call("l2i_isla_bwd", *args, 1, 0.0)
@@ -478,6 +482,65 @@ def avgpool2_bwd(dout):
     n, ho, wo, c = dout.shape
     dx = torch.empty((n, ho * 2, wo * 2, c), dtype=torch.float32, device=dout.device)
     call("l2i_avgpool2_bwd", dout, n, ho * 2, wo * 2, c, dx)
+    return dx
+
+
+def linear_fwd(x2, w, sigma=None, bias=None):
+    """x2 (M,K), w (N,K) -> (M,N) = x2 w^T / sigma + bias (csrc/linear.cu)."""
+    _chk(x2); _chk(w)
+    m, k = x2.shape
+    n = w.shape[0]
+    y = torch.empty((m, n), dtype=torch.float32, device=x2.device)
+    call("l2i_linear_fwd", x2, w, sigma, bias, m, n, k, y)
+    return y
+
+
+def linear_bwd(dy2, x2, w, sigma=None, need_dx=True, need_gw=True, need_db=False):
+    _chk(dy2); _chk(x2); _chk(w)
+    m, n = dy2.shape
+    k = x2.shape[1]
+    dev = dy2.device
+    dx = torch.empty((m, k), dtype=torch.float32, device=dev) if need_dx else None
+    gw = torch.empty((n, k), dtype=torch.float32, device=dev) if need_gw else None
+    db = torch.empty((n,), dtype=torch.float32, device=dev) if need_db else None
+    call("l2i_linear_bwd", dy2, x2, w, sigma, m, n, k, dx, gw, db)
+    return dx, gw, db
+
+
+def add_layernorm_fwd(a, b, w, bias, eps: float):
+    _chk(a)
+    d = a.shape[-1]
+    rows = a.numel() // d
+    y = torch.empty_like(a)
+    stats = torch.empty((rows, 2), dtype=torch.float32, device=a.device)
+    call("l2i_add_layernorm_fwd", a, b, w, bias, rows, d, float(eps), y, stats)
+    return y, stats
+
+
+def add_layernorm_bwd(a, b, w, stats, dy):
+    _chk(dy)
+    d = a.shape[-1]
+    rows = a.numel() // d
+    ds = torch.empty_like(a)
+    dw = torch.empty((d,), dtype=torch.float32, device=a.device)
+    db = torch.empty((d,), dtype=torch.float32, device=a.device)
+    call("l2i_add_layernorm_bwd", a, b, w, stats, dy, rows, d, ds, dw, db)
+    return ds, dw, db
+
+
+def maxpool2_fwd(x):
+    _chk(x)
+    n, h, w, c = x.shape
+    out = torch.empty((n, h // 2, w // 2, c), dtype=torch.float32, device=x.device)
+    call("l2i_maxpool2_fwd", x, n, h, w, c, out)
+    return out
+
+
+def maxpool2_bwd(x, dout):
+    _chk(dout)
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    call("l2i_maxpool2_bwd", x, dout, n, h, w, c, dx)
     return dx
 
 

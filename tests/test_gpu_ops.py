@@ -623,3 +623,67 @@ def test_gram_projection_head_matches_reference_formula(dev, training):
     close(app.weight_orig.grad, app_r.weight_orig.grad, 1e-3, 1e-4 * app_r.weight_orig.grad.abs().max().item(), "gram dw")
     close(app.bias.grad, app_r.bias.grad, 1e-3, 1e-4, "gram dbias")
     close(emb.weight_orig.grad, emb_r.weight_orig.grad, 1e-3, 1e-4 * emb_r.weight_orig.grad.abs().max().item(), "gram demb")
+
+
+@pytest.mark.parametrize("M,N,K,bias", [(512, 308, 308, True), (64, 16384, 128, True), (50, 100, 128, False), (7, 65, 33, True)])
+def test_linear_kernels_match_torch(dev, M, N, K, bias):
+    """functional.linear (csrc/linear.cu strided SIMT GEMM: y = x W^T + b, dx = dy W, dW = dy^T x, db) vs fp64."""
+    from layout2img_b200 import functional as L
+    g = torch.Generator().manual_seed(M + N + K)
+    x, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) if bias else None
+    dy = torch.randn(M, N, generator=g)
+    xr, wr = x.double().requires_grad_(), w.double().requires_grad_()
+    br = b.double().requires_grad_() if bias else None
+    ref = F.linear(xr, wr, br)
+    ref.backward(dy.double())
+    xg, wg = x.to(dev).requires_grad_(), w.to(dev).requires_grad_()
+    bg = b.to(dev).requires_grad_() if bias else None
+    out = L.linear(xg.view(1, M, K), wg, bg)                      # leading dimensions are flattened
+    out.backward(dy.to(dev).view(1, M, N))
+    close(out.view(M, N), ref, 1e-4, 1e-5, "linear fwd")
+    close(xg.grad, xr.grad, 1e-4, 1e-5, "linear dx")
+    close(wg.grad, wr.grad, 1e-4, 1e-5 * wr.grad.abs().max().item(), "linear dw")
+    if bias:
+        close(bg.grad, br.grad, 1e-4, 1e-5 * br.grad.abs().max().item(), "linear db")
+
+
+def test_add_layernorm_matches_torch(dev):
+    """functional.add_layer_norm = LayerNorm(a + b) of the attention block (resnet_generator_app_v2.py:201-212)."""
+    from layout2img_b200 import functional as L
+    g = torch.Generator().manual_seed(8)
+    rows, D = 37, 308
+    a, b = torch.randn(3, rows, D, generator=g), torch.randn(3, rows, D, generator=g) * 0.5 + 0.2
+    ln = torch.nn.LayerNorm(D)
+    with torch.no_grad():
+        ln.weight.copy_(torch.rand(D, generator=g) + 0.5); ln.bias.copy_(torch.randn(D, generator=g) * 0.1)
+    import copy
+    ln_r = copy.deepcopy(ln).double()
+    dy = torch.randn(3, rows, D, generator=g)
+    ar, br = a.double().requires_grad_(), b.double().requires_grad_()
+    ref = ln_r(ar + br)
+    ref.backward(dy.double())
+    ln = ln.to(dev)
+    ag, bg = a.to(dev).requires_grad_(), b.to(dev).requires_grad_()
+    out = L.add_layer_norm(ag, bg, ln)
+    out.backward(dy.to(dev))
+    close(out, ref, 1e-4, 1e-5, "layernorm fwd")
+    close(ag.grad, ar.grad, 1e-4, 1e-5, "layernorm da")
+    close(bg.grad, br.grad, 1e-4, 1e-5, "layernorm db")
+    close(ln.weight.grad, ln_r.weight.grad, 1e-4, 1e-4, "layernorm dweight")
+    close(ln.bias.grad, ln_r.bias.grad, 1e-4, 1e-4, "layernorm dbias")
+
+
+def test_maxpool2_matches_torch(dev):
+    from layout2img_b200 import functional as L
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 16, 8, 8, generator=g).round(decimals=1)            # rounded: ties occur
+    xr = x.double().requires_grad_()
+    ref = F.max_pool2d(xr, 2)
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy.double())
+    xg = nhwc(x).to(dev).requires_grad_()
+    out = L.maxpool2(xg)
+    out.backward(nhwc(dy).to(dev))
+    close(out.permute(0, 3, 1, 2), ref, 0, 0, "maxpool fwd")
+    close(xg.grad.permute(0, 3, 1, 2), xr.grad, 0, 1e-12, "maxpool bwd (first maximum wins)")
