@@ -44,7 +44,7 @@ int l2i_act_split(const float* x, int N, int H, int W, int C, int relu, int up2,
 /* Residual-block operand preparation: one read of x [N,H,W,C] fp32 gives pair a = relu_a ? relu(x) : x at
  * full resolution and, for b_mode 1 / 2, pair b = b_scale * x / b_scale * (2x2 sum of x) (never ReLU'd):
  * b_scale 0.25 = avg_pool2d (input of the pooled 1x1 shortcut of rcnn_discriminator_app.py:294-344), 1.0 = the
- * backward of nearest x2 up-sampling (resnet_generator_app_v2.py:665-670). */
+ * backward of nearest x2 up-sampling (resnet_generator_app_v2.py:665-670).  a_hi / a_lo may be NULL (pair b only). */
 int l2i_act_split2(const float* x, int N, int H, int W, int C, int relu_a, void* a_hi, void* a_lo, int b_mode,
                    float b_scale, void* b_hi, void* b_lo, int cpad, void* stream);
 /* Gradient arriving at a block output, g [N,H,W,C] fp32: pair (lo_hi, lo_lo) = g (nullable), pair (up_hi, up_lo)
@@ -69,6 +69,19 @@ int l2i_conv2d_fwd(int N, int H, int W, int cin_pad, int cout, int taps, const v
                    const void* w_hi, const void* w_lo, const float* bias, const float* residual, int res_up2,
                    float res_scale, float out_scale, const void* mask_hi, int mask_cpad, int pool, float* out, void* out_hi,
                    void* out_lo, int cout_pad, int relu_split, void* stream);
+
+/* 3x3 convolutions with <= 4 channels on one side (the discriminator's first convolution 3 -> 64, the generator's RGB
+ * head 64 -> 3) as 1x1 convolutions over a 9C-channel im2col tensor (channel order c*9 + tap = torch's weight order, so
+ * W.view(cout, 9C) is the 1x1 weight); d(tap) = (tap/3 - 1, tap%3 - 1), sign = +1 / -1:
+ *   l2i_im2col3_pair: pair[p, c*9+tap] = x[p + sign d(tap), c] (zero outside), x fp32 [N,H,W,C], pair [N,H,W,cpad] with
+ *                     cpad >= 9C (channels >= 9C zero); colsum [C] (nullable) = sum over pixels of x (a bias gradient)
+ *   l2i_col2im3:      out[q, c] = sum_tap col[q - sign d(tap), c*9+tap] + bias[c] + res_scale * residual[q or q/2, c]
+ *                     (the adjoint of im2col(sign)); col fp32 [N,H,W,ldc], out / residual fp32 [N,H,W,C] ([N,H/2,W/2,C]
+ *                     read with nearest x2 up-sampling when res_up2). */
+int l2i_im2col3_pair(const float* x, int N, int H, int W, int C, int sign, void* hi, void* lo, int cpad, float* colsum,
+                     void* stream);
+int l2i_col2im3(const float* col, int ldc, int N, int H, int W, int C, int sign, const float* bias, const float* residual,
+                int res_up2, float res_scale, float* out, void* stream);
 
 /* dw [cout][taps][cin] fp32 = sum over pixels of dy (x) shifted x.  dy pair [N,H,W,cout_pad],
  * x pair [N,H,W,cin_pad]. */

@@ -208,15 +208,23 @@ int l2i_roi_align2_bwd(const float* dout, const float* rois, const int32_t* leve
                        float scale_l, float* dfeat_l, int Hs, int Ws, float scale_s, float* dfeat_s, void* stream) {
   return roi_align2_bwd(dout, rois, level, K, N, C, P, Hl, Wl, scale_l, dfeat_l, Hs, Ws, scale_s, dfeat_s, ST(stream));
 }
+int l2i_im2col3_pair(const float* x, int N, int H, int W, int C, int sign, void* hi, void* lo, int cpad, float* colsum,
+                     void* stream) {
+  return im2col3_pair(x, N, H, W, C, sign, hi, lo, cpad, colsum, ST(stream));
+}
+int l2i_col2im3(const float* col, int ldc, int N, int H, int W, int C, int sign, const float* bias, const float* residual,
+                int res_up2, float res_scale, float* out, void* stream) {
+  return col2im3(col, ldc, N, H, W, C, sign, bias, residual, res_up2, res_scale, out, ST(stream));
+}
 int l2i_linear_fwd(const float* x, const float* w, const float* sigma, const float* bias, int M, int N, int K, float* y,
                    void* stream) {
-  return gemm_strided(x, K, 1, w, 1, K, M, N, K, sigma, bias, y, N, 0, ST(stream));          // y = x w^T / sigma + bias
+  return gemm_strided(x, K, 1, w, 1, K, M, N, K, sigma, bias, y, N, ST(stream));          // y = x w^T / sigma + bias
 }
 int l2i_linear_bwd(const float* dy, const float* x, const float* w, const float* sigma, int M, int N, int K, float* dx,
                    float* gw, float* db, void* stream) {
   int rc = L2I_OK;
-  if (dx) rc = gemm_strided(dy, N, 1, w, K, 1, M, K, N, sigma, nullptr, dx, K, 0, ST(stream));   // dx = dy w / sigma
-  if (!rc && gw) rc = gemm_strided(dy, 1, N, x, K, 1, N, K, M, nullptr, nullptr, gw, K, 0, ST(stream));   // gw = dy^T x
+  if (dx) rc = gemm_strided(dy, N, 1, w, K, 1, M, K, N, sigma, nullptr, dx, K, ST(stream));   // dx = dy w / sigma
+  if (!rc && gw) rc = gemm_strided(dy, 1, N, x, K, 1, N, K, M, nullptr, nullptr, gw, K, ST(stream));   // gw = dy^T x
   if (!rc && db) rc = colsum(dy, M, N, db, ST(stream));
   return rc;
 }

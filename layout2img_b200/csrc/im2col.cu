@@ -1,0 +1,133 @@
+// 3x3 convolutions with a tiny channel count on one side -- the discriminator's first convolution (3 -> 64,
+// rcnn_discriminator_app.py:297) and the generator's RGB head (64 -> 3, resnet_generator_app_v2.py:418) -- rewritten as
+// 1x1 convolutions over a 9C-channel (C <= 4) im2col tensor, so that the tensor-core kernel runs ONE K chunk per tile
+// instead of nine taps of a 64-wide chunk that is 95 % padding (the padded forms ran at 8-12 TFLOP/s):
+//
+//   small input :  y[p, co] = sum_{c,tap} W[co][c][tap] x[p + d(tap), c]  =  (im2col(+1)(x) [p, c*9+tap]) . W.view(co, 9C)
+//   small output:  y[p, s]  = sum_tap P[p + d(tap), s*9+tap],  P = x . W2^T,  W2[s*9+tap][l] = W[s][l][tap]  =  col2im(-1)(P)
+//
+//   im2col(sign):  col[p, c*9+tap] = x[p + sign * d(tap), c]            (zero outside the image; written as a bf16 pair)
+//   col2im(sign):  out[q, c] = sum_tap col[q - sign * d(tap), c*9+tap]  (the adjoint of im2col(sign))
+// with d(tap) = (tap / 3 - 1, tap % 3 - 1).  The channel order c*9+tap is torch's weight order, so W.view(co, 9C) IS the
+// 1x1 weight and its gradient needs no permutation.  HBM-bound: 4 B per im2col channel written.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace l2i {
+
+// one thread per pixel: 9C values -> cpad-channel bf16 pair (channels >= 9C zero); optional per-channel sums of x
+__global__ void __launch_bounds__(256)
+im2col3_pair_kernel(const float* __restrict__ x, int N, int H, int W, int C, int sign, __nv_bfloat16* __restrict__ hi,
+                    __nv_bfloat16* __restrict__ lo, int cpad, float* __restrict__ colsum) {
+  __shared__ float s_sum[4];
+  if (colsum && threadIdx.x < 4) s_sum[threadIdx.x] = 0.f;
+  if (colsum) __syncthreads();
+  const long long P = 1LL * N * H * W;
+  float csum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long p = blockIdx.x * 1LL * blockDim.x + threadIdx.x; p < P; p += 1LL * gridDim.x * blockDim.x) {
+    const int w = static_cast<int>(p % W), h = static_cast<int>((p / W) % H);
+    const long long n = p / (1LL * W * H);
+    float v[40];
+#pragma unroll
+    for (int j = 0; j < 40; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = h + sign * (tap / 3 - 1), ww = w + sign * (tap % 3 - 1);
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+      const float* src = x + ((n * H + hh) * W + ww) * C;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) v[c * 9 + tap] = __ldg(src + c);
+    }
+    if (colsum) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) csum[c] += v[c * 9 + 4];                   // tap 4 = the pixel itself
+    }
+    __nv_bfloat16* ph = hi + p * cpad;
+    __nv_bfloat16* pl = lo + p * cpad;
+    for (int g = 0; g < (cpad >> 3); ++g) {
+      uint32_t a[4] = {0u, 0u, 0u, 0u}, b[4] = {0u, 0u, 0u, 0u};
+      if (g < 5) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          __nv_bfloat16 ah, al, bh, bl;
+          split_bf16(v[g * 8 + j], ah, al);
+          split_bf16(v[g * 8 + j + 1], bh, bl);
+          a[j >> 1] = pack_bf16x2(ah, bh);
+          b[j >> 1] = pack_bf16x2(al, bl);
+        }
+      }
+      *reinterpret_cast<uint4*>(ph + g * 8) = make_uint4(a[0], a[1], a[2], a[3]);
+      *reinterpret_cast<uint4*>(pl + g * 8) = make_uint4(b[0], b[1], b[2], b[3]);
+    }
+  }
+  if (colsum) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float t = warp_sum(csum[c]);
+      if ((threadIdx.x & 31) == 0 && c < C) atomicAdd(&s_sum[c], t);
+    }
+    __syncthreads();
+    if (threadIdx.x < C) atomicAdd(colsum + threadIdx.x, s_sum[threadIdx.x]);
+  }
+}
+
+// one thread per output element: out[q, c] = sum_tap col[q - sign d(tap), c*9+tap] + bias[c] + res_scale * residual
+__global__ void __launch_bounds__(256)
+col2im3_kernel(const float* __restrict__ col, int ldc, int N, int H, int W, int C, int sign, const float* __restrict__ bias,
+               const float* __restrict__ residual, int res_up2, float res_scale, float* __restrict__ out) {
+  const long long total = 1LL * N * H * W * C;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long q = i / C;
+    const int w = static_cast<int>(q % W), h = static_cast<int>((q / W) % H);
+    const long long n = q / (1LL * W * H);
+    float acc = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = h - sign * (tap / 3 - 1), ww = w - sign * (tap % 3 - 1);
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+      acc += __ldg(col + ((n * H + hh) * W + ww) * ldc + c * 9 + tap);
+    }
+    if (residual) {
+      const long long r = res_up2 ? ((n * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) : q;
+      acc = fmaf(res_scale, __ldg(residual + r * C + c), acc);
+    }
+    out[i] = acc;
+  }
+}
+
+int im2col3_pair(const float* x, int N, int H, int W, int C, int sign, void* hi, void* lo, int cpad, float* colsum,
+                 cudaStream_t stream) {
+  if (!x || !hi || !lo || N <= 0 || H <= 0 || W <= 0 || C <= 0 || C > 4 || cpad % 8 || cpad < 9 * C || (sign != 1 && sign != -1)) {
+    set_error("im2col3: bad arguments (C=%d must be <= 4, cpad=%d)", C, cpad);
+    return L2I_ERR_BAD_ARG;
+  }
+  if (colsum) {
+    cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * C, stream);
+    if (e != cudaSuccess) { set_error("im2col3: memset: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
+  }
+  const long long P = 1LL * N * H * W;
+  long long blocks = (P + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  im2col3_pair_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, N, H, W, C, sign, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                                   reinterpret_cast<__nv_bfloat16*>(lo), cpad, colsum);
+  return check_launch("im2col3_pair_kernel");
+}
+
+int col2im3(const float* col, int ldc, int N, int H, int W, int C, int sign, const float* bias, const float* residual,
+            int res_up2, float res_scale, float* out, cudaStream_t stream) {
+  if (!col || !out || N <= 0 || H <= 0 || W <= 0 || C <= 0 || C > 4 || ldc < 9 * C || (sign != 1 && sign != -1) ||
+      (residual && res_up2 && ((H | W) & 1))) {
+    set_error("col2im3: bad arguments");
+    return L2I_ERR_BAD_ARG;
+  }
+  const long long total = 1LL * N * H * W * C;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  col2im3_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(col, ldc, N, H, W, C, sign, bias, residual, res_up2, res_scale, out);
+  return check_launch("col2im3_kernel");
+}
+
+}  // namespace l2i

@@ -111,9 +111,15 @@ int sn_group_sigma(const void* table, int n_modules, const int* wt_items, int n_
 int weight_prep_group(const void* table, const int* items9, int n9, const int* items1, int n1, const float* f32, void* bf16,
                       int want_dgrad, cudaStream_t stream);
 
+// im2col.cu
+int im2col3_pair(const float* x, int N, int H, int W, int C, int sign, void* hi, void* lo, int cpad, float* colsum,
+                 cudaStream_t stream);
+int col2im3(const float* col, int ldc, int N, int H, int W, int C, int sign, const float* bias, const float* residual,
+            int res_up2, float res_scale, float* out, cudaStream_t stream);
+
 // linear.cu
 int gemm_strided(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, int M, int N, int K,
-                 const float* sigma, const float* bias, float* C, long long scm, int accumulate, cudaStream_t stream);
+                 const float* sigma, const float* bias, float* C, long long scm, cudaStream_t stream);
 int colsum(const float* X, int M, int N, float* out, cudaStream_t stream);
 int add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, int rows, int D, float eps, float* y,
                       float* stats, cudaStream_t stream);

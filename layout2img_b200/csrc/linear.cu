@@ -16,7 +16,7 @@ static constexpr int kGT = 64, kGK = 16;      // tile M = N = 64, K step 16; 256
 __global__ void __launch_bounds__(256)
 gemm_strided_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ B, long long sbk,
                     long long sbn, int M, int N, int K, const float* __restrict__ sigma, const float* __restrict__ bias,
-                    float* __restrict__ C, long long scm, int accumulate) {
+                    float* __restrict__ C, long long scm, int k_per_split) {
   __shared__ float sA[kGK][kGT + 1], sB[kGK][kGT + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * kGT, n0 = blockIdx.x * kGT;
@@ -25,17 +25,19 @@ gemm_strided_kernel(const float* __restrict__ A, long long sam, long long sak, c
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += kGK) {
+  // split-K (gridDim.z > 1): this block reduces k in [kb, ke) and adds its partial with atomics into the zeroed C
+  const int kb = blockIdx.z * k_per_split, ke = min(K, kb + k_per_split);
+  for (int k0 = kb; k0 < ke; k0 += kGK) {
     // 64 x 16 elements of each operand, 4 per thread; the faster-varying thread index follows the unit stride
     for (int e = threadIdx.x; e < kGT * kGK; e += 256) {
       int mm, kk;
       if (sak == 1) { kk = e % kGK; mm = e / kGK; } else { mm = e % kGT; kk = e / kGT; }
       const int m = m0 + mm, k = k0 + kk;
-      sA[kk][mm] = (m < M && k < K) ? __ldg(A + m * sam + k * sak) : 0.f;
-      int nn, kb;
-      if (sbk == 1) { kb = e % kGK; nn = e / kGK; } else { nn = e % kGT; kb = e / kGT; }
-      const int n = n0 + nn, k2 = k0 + kb;
-      sB[kb][nn] = (n < N && k2 < K) ? __ldg(B + k2 * sbk + n * sbn) : 0.f;
+      sA[kk][mm] = (m < M && k < ke) ? __ldg(A + m * sam + k * sak) : 0.f;
+      int nn, kb2;
+      if (sbk == 1) { kb2 = e % kGK; nn = e / kGK; } else { nn = e % kGT; kb2 = e / kGT; }
+      const int n = n0 + nn, k2 = k0 + kb2;
+      sB[kb2][nn] = (n < N && k2 < ke) ? __ldg(B + k2 * sbk + n * sbn) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -62,19 +64,35 @@ gemm_strided_kernel(const float* __restrict__ A, long long sam, long long sak, c
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       float v = sigma ? acc[i][j] / sg : acc[i][j];
-      if (bias) v += __ldg(bias + n);
+      if (bias && blockIdx.z == 0) v += __ldg(bias + n);
       float* o = C + m * scm + n;
-      *o = accumulate ? *o + v : v;
+      if (gridDim.z > 1) atomicAdd(o, v); else *o = v;
     }
   }
 }
 
 int gemm_strided(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, int M, int N, int K,
-                 const float* sigma, const float* bias, float* C, long long scm, int accumulate, cudaStream_t stream) {
+                 const float* sigma, const float* bias, float* C, long long scm, cudaStream_t stream) {
   if (!A || !B || !C || M < 0 || N <= 0 || K <= 0) { set_error("gemm: bad arguments (M=%d N=%d K=%d)", M, N, K); return L2I_ERR_BAD_ARG; }
   if (M == 0) return L2I_OK;
-  dim3 grid((N + kGT - 1) / kGT, (M + kGT - 1) / kGT);
-  gemm_strided_kernel<<<grid, 256, 0, stream>>>(A, sam, sak, B, sbk, sbn, M, N, K, sigma, bias, C, scm, accumulate);
+  const int gx = (N + kGT - 1) / kGT, gy = (M + kGT - 1) / kGT;
+  // few output tiles and a long reduction (dx of the 16384-wide fc: 2 tiles, K = 16384): split K over ~2 waves of CTAs
+  int splits = 1;
+  if (gx * gy < 148 && K >= 256) {
+    splits = (296 + gx * gy - 1) / (gx * gy);
+    if (splits > K / 64) splits = K / 64;
+    if (splits < 1) splits = 1;
+  }
+  int kps = (K + splits - 1) / splits;
+  kps = (kps + kGK - 1) / kGK * kGK;
+  splits = (K + kps - 1) / kps;
+  if (splits > 1) {
+    if (scm != N) { set_error("gemm: split-K needs a dense output"); return L2I_ERR_UNSUPPORTED; }
+    cudaError_t e = cudaMemsetAsync(C, 0, sizeof(float) * static_cast<size_t>(M) * N, stream);
+    if (e != cudaSuccess) { set_error("gemm: memset: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
+  }
+  dim3 grid(gx, gy, splits);
+  gemm_strided_kernel<<<grid, 256, 0, stream>>>(A, sam, sak, B, sbk, sbn, M, N, K, sigma, bias, C, scm, kps);
   return check_launch("gemm_strided_kernel");
 }
 

@@ -262,7 +262,7 @@ __global__ void act_split2_kernel(const float* __restrict__ x, int N, int H, int
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        store_pair8(v, a_hi + pix * cpad + g * 8, a_lo + pix * cpad + g * 8);
+        if (a_hi) store_pair8(v, a_hi + pix * cpad + g * 8, a_lo + pix * cpad + g * 8);
       }
     }
     if (b_mode) {
@@ -275,7 +275,7 @@ __global__ void act_split2_kernel(const float* __restrict__ x, int N, int H, int
 
 int act_split2(const float* x, int N, int H, int W, int C, int relu_a, void* a_hi, void* a_lo, int b_mode, float b_scale,
                void* b_hi, void* b_lo, int cpad, cudaStream_t stream) {
-  if (!x || !a_hi || !a_lo || N <= 0 || H <= 0 || W <= 0 || C <= 0 || cpad < C || cpad % 8 || b_mode < 0 || b_mode > 2 ||
+  if (!x || (!a_hi != !a_lo) || (!a_hi && !b_mode) || N <= 0 || H <= 0 || W <= 0 || C <= 0 || cpad < C || cpad % 8 || b_mode < 0 || b_mode > 2 ||
       (b_mode && (!b_hi || !b_lo)) || (b_mode == 2 && ((H | W) & 1))) {
     set_error("act_split2: bad arguments (N=%d H=%d W=%d C=%d cpad=%d b_mode=%d)", N, H, W, C, cpad, b_mode);
     return L2I_ERR_BAD_ARG;

@@ -24,18 +24,32 @@ def _sigma(weight, sn):
     return ops.sn_sigma(_c(weight), sn[0], sn[1], training=sn[3], eps=sn[2]) if sn else None
 
 
-def _sigma_and_prep(weight, sn, need_dgrad):
+def small_in(weight) -> bool:
+    """3x3 convolution with <= 4 input channels: run as a 1x1 convolution over the 9C-channel im2col tensor (csrc/im2col.cu)."""
+    return weight.shape[1] <= 4 and tuple(weight.shape[2:]) == (3, 3)
+
+
+def small_out(weight) -> bool:
+    """3x3 convolution with <= 4 output channels: 1x1 convolution to 9 * Cout channels + col2im gather (csrc/im2col.cu)."""
+    return weight.shape[0] <= 4 and tuple(weight.shape[2:]) == (3, 3) and weight.shape[1] > 4
+
+
+def _sigma_and_prep(weight, sn, need_dgrad, as_1x1=False):
     """(SNState | None, WeightPair) of a convolution weight, from the grouped launch when available.  The power
     iteration must run exactly once per module call: a prepared state is always used; only missing operand pairs
-    (e.g. the data-gradient pair after a no-grad preparation) are produced here."""
+    (e.g. the data-gradient pair after a no-grad preparation) are produced here.  as_1x1: the (Cout, C, 3, 3) weight of
+    a small-input convolution is prepared as the (Cout, 9C, 1, 1) weight of the im2col form (same memory)."""
+    w = _c(weight)
+    if as_1x1:
+        w = w.view(w.shape[0], -1, 1, 1)
     pre = take_prepared(weight)
     if pre is not None and (pre[0] is not None) == (sn is not None):
         st, wp = pre
-        if wp is None or (need_dgrad and wp.d_hi is None):
-            wp = ops.conv_weight_prep(_c(weight), st.sigma if st else None, need_dgrad=need_dgrad)
+        if wp is None or (need_dgrad and wp.d_hi is None) or wp.taps != w.shape[2] * w.shape[3]:
+            wp = ops.conv_weight_prep(w, st.sigma if st else None, need_dgrad=need_dgrad)
         return st, wp
     st = ops.sn_sigma(_c(weight), sn[0], sn[1], training=sn[3], eps=sn[2]) if sn else None
-    return st, ops.conv_weight_prep(_c(weight), st.sigma if st else None, need_dgrad=need_dgrad)
+    return st, ops.conv_weight_prep(w, st.sigma if st else None, need_dgrad=need_dgrad)
 
 
 def _dw_to_torch(dw, cout, cin, taps):
@@ -59,27 +73,37 @@ class ConvFn(torch.autograd.Function):
         x = _c(x)
         cout, cin, kh, kw = weight.shape
         taps = kh * kw
-        xp = ops.act_split(x, relu=relu_in, up2=up2_in)
-        st, wp = _sigma_and_prep(weight, sn, ctx.needs_input_grad[0])
+        im2col = small_in(weight) and not relu_in and not up2_in
+        if im2col:                       # 3 -> Cout: one K chunk over the 27-channel im2col pair instead of nine padded taps
+            xp, _ = ops.im2col3(x, 1)
+            st, wp = _sigma_and_prep(weight, sn, ctx.needs_input_grad[0], as_1x1=True)
+            taps = 1
+        else:
+            xp = ops.act_split(x, relu=relu_in, up2=up2_in)
+            st, wp = _sigma_and_prep(weight, sn, ctx.needs_input_grad[0])
         out, _ = ops.conv2d_fwd(xp, wp.f_hi, wp.f_lo, cout, taps, bias=_c(bias), residual=_c(residual), res_up2=res_up2)
         ctx.save_for_backward(xp.hi, xp.lo, wp.d_hi, wp.d_lo, weight, *(st or (None, None, None)))
-        ctx.meta = (cout, cin, taps, relu_in, up2_in, res_up2, bias is not None, residual is not None)
+        ctx.meta = (cout, cin, taps, relu_in, up2_in, res_up2, bias is not None, residual is not None, im2col)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         xhi, xlo, dhi, dlo, weight, sg, u, v = ctx.saved_tensors
-        cout, cin, taps, relu_in, up2_in, res_up2, has_bias, has_res = ctx.meta
+        cout, cin, taps, relu_in, up2_in, res_up2, has_bias, has_res, im2col = ctx.meta
         dout = _c(dout)
         # one read of dout: operand pair + per-channel sums (bias gradient)
         dyp, _, colsum = ops.grad_split(dout, want_lo=True, up=False)
         dx = dw = db = dres = None
+        kin = 9 * cin if im2col else cin                  # channels of the saved operand pair
         if ctx.needs_input_grad[0]:
             # ReLU derivative from the saved (ReLU'd) input pair, 2x2 sum = backward of the nearest x2, both in the epilogue
-            dx, _ = ops.conv2d_fwd(dyp, dhi, dlo, cin, taps, mask_hi=xhi if relu_in else None, pool=2 if up2_in else 0)
+            dx, _ = ops.conv2d_fwd(dyp, dhi, dlo, kin, taps, mask_hi=xhi if relu_in else None, pool=2 if up2_in else 0)
+            if im2col:
+                dx = ops.col2im3(dx, cin, 1)
         if ctx.needs_input_grad[1]:
-            g = ops.conv2d_wgrad(dyp, ops.Pair(xhi, xlo, cin), taps)
-            dw = ops.sn_weight_grad(g, weight, ops.SNState(sg, u, v)) if sg is not None else _dw_to_torch(g, cout, cin, taps)
+            g = ops.conv2d_wgrad(dyp, ops.Pair(xhi, xlo, kin), taps)
+            dw = (ops.sn_weight_grad(g, weight, ops.SNState(sg, u, v)) if sg is not None
+                  else _dw_to_torch(g, cout, kin, taps).reshape(weight.shape))
         if has_bias and ctx.needs_input_grad[2]:
             db = colsum
         if has_res and ctx.needs_input_grad[3]:
@@ -112,12 +136,19 @@ class DBlockFn(torch.autograd.Function):
         if down and not has_sc:
             raise ValueError("a down-sampling block needs its 1x1 shortcut")
         need_dx = ctx.needs_input_grad[0]
-        a0, s0 = ops.act_split2(x, relu_a=not optimized, b_mode=(2 if down else 1) if has_sc else 0)
         c1, cin = w1.shape[0], w1.shape[1]
         c2 = w2.shape[0]
-        st1, wp1 = _sigma_and_prep(w1, sn1, need_dx)
+        im2col = optimized and small_in(w1)       # the image block: conv1 as a 1x1 convolution over the 27-channel im2col pair
+        b_mode = ((2 if down else 1) if has_sc else 0)
+        if im2col:
+            a0, _ = ops.im2col3(x, 1)
+            _, s0 = ops.act_split2(x, relu_a=False, b_mode=b_mode, want_a=False) if b_mode else (None, None)
+        else:
+            a0, s0 = ops.act_split2(x, relu_a=not optimized, b_mode=b_mode)
+        st1, wp1 = _sigma_and_prep(w1, sn1, need_dx, as_1x1=im2col)
         st2, wp2 = _sigma_and_prep(w2, sn2, True)
-        _, a1 = ops.conv2d_fwd(a0, wp1.f_hi, wp1.f_lo, c1, 9, bias=_c(b1), want_f32=False, want_pair=True, relu_pair=True)
+        _, a1 = ops.conv2d_fwd(a0, wp1.f_hi, wp1.f_lo, c1, 1 if im2col else 9, bias=_c(b1), want_f32=False, want_pair=True,
+                               relu_pair=True)
         if has_sc:
             stsc, wps = _sigma_and_prep(wsc, snsc, need_dx)
             sc, _ = ops.conv2d_fwd(s0, wps.f_hi, wps.f_lo, c2, 1, bias=_c(bsc))
@@ -129,25 +160,25 @@ class DBlockFn(torch.autograd.Function):
                               wp1.d_hi, wp1.d_lo, wp2.d_hi, wp2.d_lo, wps.d_hi if has_sc else None,
                               wps.d_lo if has_sc else None, w1, w2, wsc, *(st1 or none3), *(st2 or none3),
                               *(stsc or none3))
-        ctx.meta = (cin, c1, c2, down, optimized, has_sc)
+        ctx.meta = (cin, c1, c2, down, optimized, has_sc, im2col)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         (a0h, a0l, s0h, s0l, a1h, a1l, d1h, d1l, d2h, d2l, dsh, dsl, w1, w2, wsc,
          sg1, u1, v1, sg2, u2, v2, sgs, us, vs) = ctx.saved_tensors
-        cin, c1, c2, down, optimized, has_sc = ctx.meta
+        cin, c1, c2, down, optimized, has_sc, im2col = ctx.meta
         need = ctx.needs_input_grad
         dout = _c(dout)
         g_lo, g_up, colsum = ops.grad_split(dout, want_lo=has_sc or not down, up=down, up_scale=0.25)
         g_full = g_up if down else g_lo                      # gradient at conv2's output resolution
-        a0, a1 = ops.Pair(a0h, a0l, cin), ops.Pair(a1h, a1l, c1)
+        a0, a1 = ops.Pair(a0h, a0l, 9 * cin if im2col else cin), ops.Pair(a1h, a1l, c1)
 
         def wgrad(dy, xin, taps, w, sg, u, v):
             g = ops.conv2d_wgrad(dy, xin, taps)              # (Cout, taps, Cin)
             if sg is not None:
                 return ops.sn_weight_grad(g, w, ops.SNState(sg, u, v))
-            return _dw_to_torch(g, g.shape[0], g.shape[2], taps)
+            return _dw_to_torch(g, g.shape[0], g.shape[2], taps).reshape(w.shape)
 
         dw1 = db1 = dw2 = db2 = dwsc = dbsc = dx = None
         if need[3]:
@@ -161,7 +192,7 @@ class DBlockFn(torch.autograd.Function):
         if need[0] or need[1] or need[2]:
             _, d1 = ops.conv2d_fwd(g_full, d2h, d2l, c1, 9, mask_hi=a1h, want_f32=False, want_pair=True)
             if need[1]:
-                dw1 = wgrad(d1, a0, 9, w1, sg1, u1, v1)
+                dw1 = wgrad(d1, a0, 1 if im2col else 9, w1, sg1, u1, v1)
             if need[2]:
                 db1 = ops.pair_colsum(d1)
             if need[0]:
@@ -169,8 +200,12 @@ class DBlockFn(torch.autograd.Function):
                     r, _ = ops.conv2d_fwd(g_lo, dsh, dsl, cin, 1)
                 else:
                     r = dout
-                dx, _ = ops.conv2d_fwd(d1, d1h, d1l, cin, 9, mask_hi=None if optimized else a0h, residual=r,
-                                       res_up2=down, res_scale=0.25 if down else 1.0)
+                if im2col:        # 64 -> 27 im2col-channel gradient, gathered back to the 3 image channels with the shortcut's term
+                    dcol, _ = ops.conv2d_fwd(d1, d1h, d1l, 9 * cin, 1)
+                    dx = ops.col2im3(dcol, cin, 1, residual=r, res_up2=down, res_scale=0.25 if down else 1.0)
+                else:
+                    dx, _ = ops.conv2d_fwd(d1, d1h, d1l, cin, 9, mask_hi=None if optimized else a0h, residual=r,
+                                           res_up2=down, res_scale=0.25 if down else 1.0)
         return dx, dw1, db1, dw2, db2, dwsc, dbsc, None, None, None, None, None
 
 
@@ -408,21 +443,37 @@ class NormConvFn(torch.autograd.Function):
             mi = ops.bn_eval_stats(running_mean, running_var, eps)
         mask_pm, gamma, beta, chan_scale = _c(mask_pm), _c(gamma), _c(beta), _c(chan_scale)
         _, ap = ops.isla_fwd(x, mi, mask_pm, gamma, beta, _c(aff_w), _c(aff_b), relu=True, up2=up2, chan_scale=chan_scale)
-        st, wp = _sigma_and_prep(weight, sn, True)
-        out, _ = ops.conv2d_fwd(ap, wp.f_hi, wp.f_lo, cout, taps, bias=_c(bias), residual=_c(residual), res_up2=res_up2)
+        gather = small_out(weight) and residual is None
+        if gather:
+            # Cin -> 3 (the RGB head): a 1x1 convolution to the 27 (output channel, tap) products, then each pixel gathers
+            # its nine neighbours' terms (col2im) -- instead of nine taps whose N tile would be 95 % padding
+            st = _sigma(weight, sn)
+            w_eff = weight.detach().permute(0, 2, 3, 1).reshape(cout * 9, cin, 1, 1).contiguous()   # [(s, tap)][l]
+            wp = ops.conv_weight_prep(w_eff, st.sigma if st else None, need_dgrad=True)
+            prod, _ = ops.conv2d_fwd(ap, wp.f_hi, wp.f_lo, cout * 9, 1)
+            out = ops.col2im3(prod, cout, -1, bias=_c(bias))
+        else:
+            st, wp = _sigma_and_prep(weight, sn, True)
+            out, _ = ops.conv2d_fwd(ap, wp.f_hi, wp.f_lo, cout, taps, bias=_c(bias), residual=_c(residual), res_up2=res_up2)
         ctx.save_for_backward(x, mi, mask_pm, gamma, beta, aff_w, aff_b, ap.hi, ap.lo, wp.d_hi, wp.d_lo, weight, chan_scale,
                               *(st or (None, None, None)))
-        ctx.meta = (cout, cin, taps, training, up2, res_up2, bias is not None, residual is not None)
+        ctx.meta = (cout, cin, taps, training, up2, res_up2, bias is not None, residual is not None, gather)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, mi, mask_pm, gamma, beta, aff_w, aff_b, ahi, alo, dhi, dlo, weight, chan_scale, sg, u, v = ctx.saved_tensors
-        cout, cin, taps, training, up2, res_up2, has_bias, has_res = ctx.meta
+        cout, cin, taps, training, up2, res_up2, has_bias, has_res, gather = ctx.meta
         dout = _c(dout)
-        dyp, _, colsum = ops.grad_split(dout, want_lo=True, up=False)
-        da, _ = ops.conv2d_fwd(dyp, dhi, dlo, cin, taps)
-        g = ops.conv2d_wgrad(dyp, ops.Pair(ahi, alo, cin), taps)
+        if gather:
+            # adjoint of the col2im gather: the (s, tap) product gradients as an operand pair, then two 1x1 launches
+            dyp, colsum = ops.im2col3(dout, -1, want_colsum=has_bias)
+            da, _ = ops.conv2d_fwd(dyp, dhi, dlo, cin, 1)
+            g = ops.conv2d_wgrad(dyp, ops.Pair(ahi, alo, cin), 1).view(cout, 9, cin)     # [(s, tap)][l] == (Cout, taps, Cin)
+        else:
+            dyp, _, colsum = ops.grad_split(dout, want_lo=True, up=False)
+            da, _ = ops.conv2d_fwd(dyp, dhi, dlo, cin, taps)
+            g = ops.conv2d_wgrad(dyp, ops.Pair(ahi, alo, cin), taps)
         dw = ops.sn_weight_grad(g, weight, ops.SNState(sg, u, v)) if sg is not None else _dw_to_torch(g, cout, cin, taps)
         dx, dmask, dgamma, dbeta, csum = ops.isla_bwd(x, mi, mask_pm, gamma, beta, _c(aff_w), _c(aff_b), da,
                                                       relu=True, up2=up2, train=training, chan_scale=chan_scale)

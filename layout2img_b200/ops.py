@@ -107,7 +107,7 @@ def act_split(x: torch.Tensor, relu: bool = False, up2: bool = False) -> Pair:
     return Pair(out[0], out[1], c)
 
 
-def act_split2(x: torch.Tensor, relu_a: bool, b_mode: int, b_scale: Optional[float] = None):
+def act_split2(x: torch.Tensor, relu_a: bool, b_mode: int, b_scale: Optional[float] = None, want_a: bool = True):
     """x (N,H,W,C) -> (pair a = relu_a ? relu(x) : x, pair b = None | x | avgpool2(x))  [b_mode 0 | 1 | 2];
     b_scale overrides b's factor (default 1 for b_mode 1, 0.25 = average for b_mode 2; 1.0 there = 2x2 sum)."""
     if b_scale is None:
@@ -115,15 +115,40 @@ def act_split2(x: torch.Tensor, relu_a: bool, b_mode: int, b_scale: Optional[flo
     _chk(x)
     n, h, w, c = x.shape
     cp = pad8(c)
-    a = torch.empty((2, n, h, w, cp), dtype=torch.bfloat16, device=x.device)
+    a = torch.empty((2, n, h, w, cp), dtype=torch.bfloat16, device=x.device) if want_a else None
     b = None
     if b_mode == 1:
         b = torch.empty((2, n, h, w, cp), dtype=torch.bfloat16, device=x.device)
     elif b_mode == 2:
         b = torch.empty((2, n, h // 2, w // 2, cp), dtype=torch.bfloat16, device=x.device)
-    call("l2i_act_split2", x, n, h, w, c, int(relu_a), a[0], a[1], int(b_mode), float(b_scale),
-         b[0] if b is not None else None, b[1] if b is not None else None, cp)
-    return Pair(a[0], a[1], c), (Pair(b[0], b[1], c) if b is not None else None)
+    call("l2i_act_split2", x, n, h, w, c, int(relu_a), a[0] if want_a else None, a[1] if want_a else None, int(b_mode),
+         float(b_scale), b[0] if b is not None else None, b[1] if b is not None else None, cp)
+    return (Pair(a[0], a[1], c) if want_a else None), (Pair(b[0], b[1], c) if b is not None else None)
+
+
+def im2col3(x: torch.Tensor, sign: int = 1, want_colsum: bool = False):
+    """x (N,H,W,C<=4) fp32 -> Pair over 9C channels (order c*9+tap), pair[p] = x[p + sign*d(tap)]; optional colsum (C,)."""
+    _chk(x)
+    n, h, w, c = x.shape
+    cp = pad8(9 * c)
+    buf = torch.empty((2, n, h, w, cp), dtype=torch.bfloat16, device=x.device)
+    colsum = torch.empty((c,), dtype=torch.float32, device=x.device) if want_colsum else None
+    call("l2i_im2col3_pair", x, n, h, w, c, int(sign), buf[0], buf[1], cp, colsum)
+    return Pair(buf[0], buf[1], 9 * c), colsum
+
+
+def col2im3(col: torch.Tensor, c: int, sign: int = 1, bias=None, residual=None, res_up2: bool = False, res_scale: float = 1.0):
+    """col (N,H,W,ldc>=9c) fp32 -> (N,H,W,c): out[q] = sum_tap col[q - sign*d(tap), c*9+tap] + bias + res_scale*residual."""
+    _chk(col)
+    n, h, w, ldc = col.shape
+    out = torch.empty((n, h, w, c), dtype=torch.float32, device=col.device)
+    if residual is not None:
+        _chk(residual)
+        exp = (n, h // 2, w // 2, c) if res_up2 else (n, h, w, c)
+        if tuple(residual.shape) != exp:
+            raise ValueError(f"col2im3: residual shape {tuple(residual.shape)} != {exp}")
+    call("l2i_col2im3", col, ldc, n, h, w, c, int(sign), bias, residual, int(res_up2), float(res_scale), out)
+    return out
 
 
 def grad_split(g: torch.Tensor, want_lo: bool = True, up: bool = False, up_scale: float = 0.25):

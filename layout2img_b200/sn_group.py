@@ -61,8 +61,15 @@ class SNGroup:
             if hook is None and not is_conv:
                 continue
             w = m.weight_orig if hook is not None else m.weight
-            self.mods.append({"m": m, "hook": hook, "conv": is_conv, "R": w.shape[0], "Cc": w.numel() // w.shape[0],
-                              "cin": w.shape[1] if is_conv else 0, "taps": (w.shape[2] * w.shape[3]) if is_conv else 0})
+            cin, taps, pairs = 0, 0, is_conv
+            if is_conv:
+                cin, taps = w.shape[1], w.shape[2] * w.shape[3]
+                if taps == 9 and cin <= 4:
+                    cin, taps = 9 * cin, 1       # small-input 3x3: prepared as the 1x1 weight of its im2col form (same memory)
+                elif taps == 9 and w.shape[0] <= 4:
+                    pairs = False                # small-output 3x3: its consumer prepares the permuted (Cout*9, Cin) weight
+            self.mods.append({"m": m, "hook": hook, "conv": pairs, "R": w.shape[0], "Cc": w.numel() // w.shape[0],
+                              "cin": cin if pairs else 0, "taps": taps if pairs else 0})
         # static layout of the two per-call buffers
         f_off = b_off = 0
         self.f32_sizes, self.bf_sizes = [], []

@@ -387,8 +387,11 @@ def test_graphed_train_step_matches_eager():
 
 def test_vgg_perceptual_loss_matches_torchvision():
     """vgg_loss.VGGLoss (13 tensor-core convolutions + max-pool kernels) against the reference's construction
-    (utils/util.py:49-94) on torchvision's VGG19 with the same (random: no network for the ImageNet file) weights, in
-    fp64: loss value and its gradient with respect to the generated images."""
+    (utils/util.py:49-94) on torchvision's VGG19 with the same (random: no network for the ImageNet file) weights: the
+    loss value at the north-star tolerance, its gradient with respect to the generated images with the noise-aware
+    comparison of the end-to-end tests (a ReLU / max-pool / |.| kink within rounding distance flips in any
+    implementation; the fp32 torchvision model's own deviation from fp64 measures that)."""
+    import copy
     import torchvision
     from layout2img_b200.vgg_loss import VGGLoss
     dev = torch.device("cuda:0")
@@ -398,31 +401,36 @@ def test_vgg_perceptual_loss_matches_torchvision():
         for m in tv:
             if isinstance(m, torch.nn.Conv2d):
                 m.bias.normal_(0, 0.05)
+            if isinstance(m, torch.nn.ReLU):
+                m.inplace = False
     ours = VGGLoss()
     ours.vgg.load_state_dict({"features." + k: v for k, v in tv.state_dict().items()})
     ours.to(dev)
     g = torch.Generator().manual_seed(4)
     x = (torch.rand(2, 3, 64, 64, generator=g) * 2 - 1)
     y = (torch.rand(2, 3, 64, 64, generator=g) * 2 - 1)
-    tvd = tv.double()
-    for m in tvd:
-        if isinstance(m, torch.nn.ReLU):
-            m.inplace = False
 
-    def feats(t):
-        out, h = [], t
-        for i, m in enumerate(tvd):
-            h = m(h)
-            if i in (1, 6, 11, 20, 29):
-                out.append(h)
-        return out
+    def reference(dtype):
+        net = copy.deepcopy(tv).to(dtype)
 
-    xr = x.double().requires_grad_()
-    fx, fy = feats(xr), feats(y.double())
-    ref = sum(w * (a - b.detach()).abs().mean() for w, a, b in zip([1 / 32, 1 / 16, 1 / 8, 1 / 4, 1.0], fx, fy))
-    ref.backward()
+        def feats(t):
+            out, h = [], t
+            for i, m in enumerate(net):
+                h = m(h)
+                if i in (1, 6, 11, 20, 29):
+                    out.append(h)
+            return out
+
+        xr = x.to(dtype).requires_grad_()
+        fx, fy = feats(xr), feats(y.to(dtype))
+        ref = sum(w * (a - b.detach()).abs().mean() for w, a, b in zip([1 / 32, 1 / 16, 1 / 8, 1 / 4, 1.0], fx, fy))
+        ref.backward()
+        return ref.detach(), xr.grad
+
+    l64, g64 = reference(torch.float64)
+    l32, g32 = reference(torch.float32)
     xg = x.to(dev).requires_grad_()
     loss = ours(xg, y.to(dev))
     loss.backward()
-    assert abs(loss.item() - ref.item()) <= 1e-4 + 1e-3 * abs(ref.item()), (loss.item(), ref.item())
-    close(xg.grad, xr.grad, 2e-3, 2e-3 * xr.grad.abs().max().item(), "d loss / d fake")
+    assert abs(loss.item() - l64.item()) <= 1e-4 + 1e-3 * abs(l64.item()), (loss.item(), l64.item())
+    grad_close(xg.grad, g32, g64, "d loss / d fake")
