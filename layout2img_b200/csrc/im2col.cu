@@ -15,52 +15,47 @@
 
 namespace l2i {
 
-// one thread per pixel: 9C values -> cpad-channel bf16 pair (channels >= 9C zero); optional per-channel sums of x
+// one thread per (pixel, group of 8 im2col channels): consecutive threads write consecutive 16-byte pieces of both halves
+// (channels >= 9C are written as zeros); optional per-channel sums of x (group 0 threads, the centre tap)
 __global__ void __launch_bounds__(256)
 im2col3_pair_kernel(const float* __restrict__ x, int N, int H, int W, int C, int sign, __nv_bfloat16* __restrict__ hi,
                     __nv_bfloat16* __restrict__ lo, int cpad, float* __restrict__ colsum) {
   __shared__ float s_sum[4];
   if (colsum && threadIdx.x < 4) s_sum[threadIdx.x] = 0.f;
   if (colsum) __syncthreads();
-  const long long P = 1LL * N * H * W;
+  const int groups = cpad >> 3;
+  const long long total = 1LL * N * H * W * groups;
   float csum[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long p = blockIdx.x * 1LL * blockDim.x + threadIdx.x; p < P; p += 1LL * gridDim.x * blockDim.x) {
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    const long long p = i / groups;
     const int w = static_cast<int>(p % W), h = static_cast<int>((p / W) % H);
     const long long n = p / (1LL * W * H);
-    float v[40];
+    float v[8];
 #pragma unroll
-    for (int j = 0; j < 40; ++j) v[j] = 0.f;
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;                   // im2col channel = c * 9 + tap
+      const int c = k / 9, tap = k - c * 9;
       const int hh = h + sign * (tap / 3 - 1), ww = w + sign * (tap % 3 - 1);
-      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-      const float* src = x + ((n * H + hh) * W + ww) * C;
+      v[j] = (c < C && hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(x + ((n * H + hh) * W + ww) * C + c) : 0.f;
+    }
+    if (colsum && g == 0) {
+      const float* src = x + p * C;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        if (c < C) v[c * 9 + tap] = __ldg(src + c);
+        if (c < C) csum[c] += __ldg(src + c);
     }
-    if (colsum) {
+    uint32_t a[4], b[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < C) csum[c] += v[c * 9 + 4];                   // tap 4 = the pixel itself
+    for (int j = 0; j < 8; j += 2) {
+      __nv_bfloat16 ah, al, bh, bl;
+      split_bf16(v[j], ah, al);
+      split_bf16(v[j + 1], bh, bl);
+      a[j >> 1] = pack_bf16x2(ah, bh);
+      b[j >> 1] = pack_bf16x2(al, bl);
     }
-    __nv_bfloat16* ph = hi + p * cpad;
-    __nv_bfloat16* pl = lo + p * cpad;
-    for (int g = 0; g < (cpad >> 3); ++g) {
-      uint32_t a[4] = {0u, 0u, 0u, 0u}, b[4] = {0u, 0u, 0u, 0u};
-      if (g < 5) {
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          __nv_bfloat16 ah, al, bh, bl;
-          split_bf16(v[g * 8 + j], ah, al);
-          split_bf16(v[g * 8 + j + 1], bh, bl);
-          a[j >> 1] = pack_bf16x2(ah, bh);
-          b[j >> 1] = pack_bf16x2(al, bl);
-        }
-      }
-      *reinterpret_cast<uint4*>(ph + g * 8) = make_uint4(a[0], a[1], a[2], a[3]);
-      *reinterpret_cast<uint4*>(pl + g * 8) = make_uint4(b[0], b[1], b[2], b[3]);
-    }
+    *reinterpret_cast<uint4*>(hi + p * cpad + g * 8) = make_uint4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<uint4*>(lo + p * cpad + g * 8) = make_uint4(b[0], b[1], b[2], b[3]);
   }
   if (colsum) {
 #pragma unroll
@@ -108,9 +103,9 @@ int im2col3_pair(const float* x, int N, int H, int W, int C, int sign, void* hi,
     cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * C, stream);
     if (e != cudaSuccess) { set_error("im2col3: memset: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
   }
-  const long long P = 1LL * N * H * W;
-  long long blocks = (P + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  const long long total = 1LL * N * H * W * (cpad >> 3);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
   im2col3_pair_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, N, H, W, C, sign, reinterpret_cast<__nv_bfloat16*>(hi),
                                                                    reinterpret_cast<__nv_bfloat16*>(lo), cpad, colsum);
   return check_launch("im2col3_pair_kernel");

@@ -4,7 +4,7 @@
 //     (norm_module.py:158-159), the 1x1 convolutions of the PSP stages on pooled cells (:741-746) -- are one generic
 //     strided SIMT GEMM:  C[m,n] = (sum_k A(m,k) B(k,n)) / sigma + bias[n]   with arbitrary element strides, which covers
 //     y = x W^T (+ b), dx = dy W and dW = dy^T x without transposing anything.  The GEMMs are tiny (<= 0.003 GMAC per
-//     image): a 64 x 64 x 16 register-tiled fp32 kernel is ample, and keeps fp32 accumulation order deterministic.
+//     image): a 64 x 64 x 16 register-tiled fp32 kernel is ample; the forward form accumulates in a fixed order.
 //   * LayerNorm(x + residual) of the attention block (:201-212), forward and backward, one warp per row.
 #include "common.cuh"
 #include "kernels.h"
@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256)
 gemm_strided_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ B, long long sbk,
                     long long sbn, int M, int N, int K, const float* __restrict__ sigma, const float* __restrict__ bias,
                     float* __restrict__ C, long long scm, int k_per_split) {
-  __shared__ float sA[kGK][kGT + 1], sB[kGK][kGT + 1];
+  __shared__ __align__(16) float sA[kGK][kGT + 4], sB[kGK][kGT + 4];      // rows 16-byte aligned: float4 reads below
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * kGT, n0 = blockIdx.x * kGT;
   float acc[4][4];
@@ -42,11 +42,9 @@ gemm_strided_kernel(const float* __restrict__ A, long long sam, long long sak, c
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < kGK; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = sB[kk][tx * 4 + j];
+      const float4 a4 = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&sB[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -72,13 +70,14 @@ gemm_strided_kernel(const float* __restrict__ A, long long sam, long long sak, c
 }
 
 int gemm_strided(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, int M, int N, int K,
-                 const float* sigma, const float* bias, float* C, long long scm, cudaStream_t stream) {
+                 const float* sigma, const float* bias, float* C, long long scm, int allow_split, cudaStream_t stream) {
   if (!A || !B || !C || M < 0 || N <= 0 || K <= 0) { set_error("gemm: bad arguments (M=%d N=%d K=%d)", M, N, K); return L2I_ERR_BAD_ARG; }
   if (M == 0) return L2I_OK;
   const int gx = (N + kGT - 1) / kGT, gy = (M + kGT - 1) / kGT;
   // few output tiles and a long reduction (dx of the 16384-wide fc: 2 tiles, K = 16384): split K over ~2 waves of CTAs
   int splits = 1;
-  if (gx * gy < 148 && K >= 256) {
+  // (backward GEMMs only: the forward stays bit-reproducible from run to run)
+  if (allow_split && gx * gy < 148 && K >= 256) {
     splits = (296 + gx * gy - 1) / (gx * gy);
     if (splits > K / 64) splits = K / 64;
     if (splits < 1) splits = 1;

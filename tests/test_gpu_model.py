@@ -421,8 +421,8 @@ def test_vgg_perceptual_loss_matches_torchvision():
                     out.append(h)
             return out
 
-        xr = x.to(dtype).requires_grad_()
-        fx, fy = feats(xr), feats(y.to(dtype))
+        xr = x.clone().to(dtype).requires_grad_()
+        fx, fy = feats(xr), feats(y.clone().to(dtype))
         ref = sum(w * (a - b.detach()).abs().mean() for w, a, b in zip([1 / 32, 1 / 16, 1 / 8, 1 / 4, 1.0], fx, fy))
         ref.backward()
         return ref.detach(), xr.grad
