@@ -27,19 +27,31 @@ gemm_strided_kernel(const float* __restrict__ A, long long sam, long long sak, c
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   // split-K (gridDim.z > 1): this block reduces k in [kb, ke) and adds its partial with atomics into the zeroed C
   const int kb = blockIdx.z * k_per_split, ke = min(K, kb + k_per_split);
-  for (int k0 = kb; k0 < ke; k0 += kGK) {
-    // 64 x 16 elements of each operand, 4 per thread; the faster-varying thread index follows the unit stride
-    for (int e = threadIdx.x; e < kGT * kGK; e += 256) {
-      int mm, kk;
-      if (sak == 1) { kk = e % kGK; mm = e / kGK; } else { mm = e % kGT; kk = e / kGT; }
-      const int m = m0 + mm, k = k0 + kk;
-      sA[kk][mm] = (m < M && k < ke) ? __ldg(A + m * sam + k * sak) : 0.f;
-      int nn, kb2;
-      if (sbk == 1) { kb2 = e % kGK; nn = e / kGK; } else { nn = e % kGT; kb2 = e / kGT; }
-      const int n = n0 + nn, k2 = k0 + kb2;
-      sB[kb2][nn] = (n < N && k2 < ke) ? __ldg(B + k2 * sbk + n * sbn) : 0.f;
+  // each thread stages 4 elements of each operand per K step; the faster-varying index follows the unit stride.  The
+  // global loads of step i + 1 are issued before the FMAs of step i (register prefetch), so their latency is hidden.
+  int am[4], ak[4], bn[4], bk[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int e = threadIdx.x + r * 256;
+    if (sak == 1) { ak[r] = e % kGK; am[r] = e / kGK; } else { am[r] = e % kGT; ak[r] = e / kGT; }
+    if (sbk == 1) { bk[r] = e % kGK; bn[r] = e / kGK; } else { bn[r] = e % kGT; bk[r] = e / kGT; }
+  }
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int m = m0 + am[r], k = k0 + ak[r];
+      ra[r] = (m < M && k < ke) ? __ldg(A + m * sam + k * sak) : 0.f;
+      const int n = n0 + bn[r], k2 = k0 + bk[r];
+      rb[r] = (n < N && k2 < ke) ? __ldg(B + k2 * sbk + n * sbn) : 0.f;
     }
+  };
+  if (kb < ke) fetch(kb);
+  for (int k0 = kb; k0 < ke; k0 += kGK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { sA[ak[r]][am[r]] = ra[r]; sB[bk[r]][bn[r]] = rb[r]; }
     __syncthreads();
+    if (k0 + kGK < ke) fetch(k0 + kGK);
 #pragma unroll
     for (int kk = 0; kk < kGK; ++kk) {
       const float4 a4 = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]);

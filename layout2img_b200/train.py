@@ -272,9 +272,12 @@ class GraphedTrainStep:
                 self._step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        from ._lib import lib
         self.graph = torch.cuda.CUDAGraph()
+        lib().l2i_launch_count(1)
         with torch.cuda.graph(self.graph):
             self.out = self._step()
+        self.kernels_per_replay = lib().l2i_launch_count(1)      # libl2i kernel nodes recorded in the graph
         self.warmup_steps = max(1, warmup)        # eager steps already applied to the networks (capture itself executes nothing)
 
     def _step(self):

