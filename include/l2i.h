@@ -236,16 +236,8 @@ int l2i_sn_prepare_group(const void* table, int n_modules, const int* wt_items, 
                          const int* wv_items, int n_wv, int max_cc, const int* prep9_items, int n9, const int* prep1_items,
                          int n1, float* f32, long long f32_floats, void* bf16, int want_dgrad, void* stream);
 
-/* ---- small dense layers (replaces the cuBLAS GEMMs / ATen LayerNorm behind nn.Linear and nn.LayerNorm on the path:
- *      attention projections resnet_generator_app_v2.py:148-151,208-212, fc :409, mask_regression.py:64, ISLA gamma / beta
- *      projections norm_module.py:158-159, PSP stage 1x1 convolutions :741-746).  Row-major fp32. ------------------------ */
-/* y [M,N] = x [M,K] w[N,K]^T / sigma[0] + bias[N]   (sigma, bias nullable; sigma = the spectral norm from l2i_sn_sigma). */
-int l2i_linear_fwd(const float* x, const float* w, const float* sigma, const float* bias, int M, int N, int K, float* y,
-                   void* stream);
-/* dx [M,K] = dy w / sigma;  gw [N,K] = dy^T x (= dL/d(w/sigma): pass it to l2i_sn_weight_grad with taps = 1 when the layer
- * is spectrally normalised);  db [N] = column sums of dy.  Each output nullable. */
-int l2i_linear_bwd(const float* dy, const float* x, const float* w, const float* sigma, int M, int N, int K, float* dx,
-                   float* gw, float* db, void* stream);
+/* ---- LayerNorm of the attention block (replaces nn.LayerNorm -> ATen at resnet_generator_app_v2.py:201-212; the
+ *      nn.Linear layers of the path run as 1x1 convolutions through l2i_conv2d_fwd / l2i_conv2d_wgrad). ------------------ */
 /* y = LayerNorm(a + b) * w + bias over rows of D elements (b nullable); stats [rows,2] = (mean, 1/std) for the backward. */
 int l2i_add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, int rows, int D, float eps,
                           float* y, float* stats, void* stream);

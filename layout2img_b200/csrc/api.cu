@@ -216,18 +216,6 @@ int l2i_col2im3(const float* col, int ldc, int N, int H, int W, int C, int sign,
                 int res_up2, float res_scale, float* out, void* stream) {
   return col2im3(col, ldc, N, H, W, C, sign, bias, residual, res_up2, res_scale, out, ST(stream));
 }
-int l2i_linear_fwd(const float* x, const float* w, const float* sigma, const float* bias, int M, int N, int K, float* y,
-                   void* stream) {
-  return gemm_strided(x, K, 1, w, 1, K, M, N, K, sigma, bias, y, N, 0, ST(stream));          // y = x w^T / sigma + bias
-}
-int l2i_linear_bwd(const float* dy, const float* x, const float* w, const float* sigma, int M, int N, int K, float* dx,
-                   float* gw, float* db, void* stream) {
-  int rc = L2I_OK;
-  if (dx) rc = gemm_strided(dy, N, 1, w, K, 1, M, K, N, sigma, nullptr, dx, K, 1, ST(stream));   // dx = dy w / sigma
-  if (!rc && gw) rc = gemm_strided(dy, 1, N, x, K, 1, N, K, M, nullptr, nullptr, gw, K, 1, ST(stream));   // gw = dy^T x
-  if (!rc && db) rc = colsum(dy, M, N, db, ST(stream));
-  return rc;
-}
 int l2i_add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, int rows, int D, float eps,
                           float* y, float* stats, void* stream) {
   return add_layernorm_fwd(a, b, w, bias, rows, D, eps, y, stats, ST(stream));

@@ -15,47 +15,54 @@
 
 namespace l2i {
 
-// one thread per (pixel, group of 8 im2col channels): consecutive threads write consecutive 16-byte pieces of both halves
-// (channels >= 9C are written as zeros); optional per-channel sums of x (group 0 threads, the centre tap)
+// A block takes 256 consecutive pixels.  Phase 1: thread t gathers the 9C values of pixel t (its 3 x 3 neighbourhood,
+// L1-resident) and parks their (hi, lo) halves in shared memory; phase 2: the block streams the [256][cpad] tile of
+// each half out in consecutive 16-byte pieces (channels >= 9C as zeros).  Optional per-channel sums of x.
+static constexpr int kColCh = 40;          // 9 * 4 = 36 im2col channels, rounded to whole 8-channel groups
 __global__ void __launch_bounds__(256)
 im2col3_pair_kernel(const float* __restrict__ x, int N, int H, int W, int C, int sign, __nv_bfloat16* __restrict__ hi,
                     __nv_bfloat16* __restrict__ lo, int cpad, float* __restrict__ colsum) {
+  __shared__ __align__(16) __nv_bfloat16 s_hi[256][kColCh], s_lo[256][kColCh];
   __shared__ float s_sum[4];
-  if (colsum && threadIdx.x < 4) s_sum[threadIdx.x] = 0.f;
-  if (colsum) __syncthreads();
+  if (threadIdx.x < 4) s_sum[threadIdx.x] = 0.f;
+  const long long P = 1LL * N * H * W;
   const int groups = cpad >> 3;
-  const long long total = 1LL * N * H * W * groups;
   float csum[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
-    const int g = static_cast<int>(i % groups);
-    const long long p = i / groups;
-    const int w = static_cast<int>(p % W), h = static_cast<int>((p / W) % H);
-    const long long n = p / (1LL * W * H);
-    float v[8];
+  for (long long p0 = blockIdx.x * 256LL; p0 < P; p0 += 256LL * gridDim.x) {
+    const long long p = p0 + threadIdx.x;
+    __syncthreads();                                   // previous tile fully streamed out (and s_sum initialised)
+    if (p < P) {
+      const int w = static_cast<int>(p % W), h = static_cast<int>((p / W) % H);
+      const long long n = p / (1LL * W * H);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;                   // im2col channel = c * 9 + tap
-      const int c = k / 9, tap = k - c * 9;
-      const int hh = h + sign * (tap / 3 - 1), ww = w + sign * (tap % 3 - 1);
-      v[j] = (c < C && hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(x + ((n * H + hh) * W + ww) * C + c) : 0.f;
-    }
-    if (colsum && g == 0) {
-      const float* src = x + p * C;
+      for (int c = 0; c < 4; ++c) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < C) csum[c] += __ldg(src + c);
-    }
-    uint32_t a[4], b[4];
+        for (int tap = 0; tap < 9; ++tap) {
+          const int hh = h + sign * (tap / 3 - 1), ww = w + sign * (tap % 3 - 1);
+          float v = 0.f;
+          if (c < C && hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + ((n * H + hh) * W + ww) * C + c);
+          if (tap == 4) csum[c] += v;
+          __nv_bfloat16 a, b;
+          split_bf16(v, a, b);
+          s_hi[threadIdx.x][c * 9 + tap] = a;
+          s_lo[threadIdx.x][c * 9 + tap] = b;
+        }
+      }
 #pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-      __nv_bfloat16 ah, al, bh, bl;
-      split_bf16(v[j], ah, al);
-      split_bf16(v[j + 1], bh, bl);
-      a[j >> 1] = pack_bf16x2(ah, bh);
-      b[j >> 1] = pack_bf16x2(al, bl);
+      for (int k = 36; k < kColCh; ++k) { s_hi[threadIdx.x][k] = __float2bfloat16(0.f); s_lo[threadIdx.x][k] = __float2bfloat16(0.f); }
     }
-    *reinterpret_cast<uint4*>(hi + p * cpad + g * 8) = make_uint4(a[0], a[1], a[2], a[3]);
-    *reinterpret_cast<uint4*>(lo + p * cpad + g * 8) = make_uint4(b[0], b[1], b[2], b[3]);
+    __syncthreads();
+    const int npix = static_cast<int>(min(256LL, P - p0));
+    for (int i = threadIdx.x; i < npix * groups; i += 256) {
+      const int px = i / groups, g = i - px * groups;
+      uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+      if (g * 8 < kColCh) {
+        a = *reinterpret_cast<const uint4*>(&s_hi[px][g * 8]);
+        b = *reinterpret_cast<const uint4*>(&s_lo[px][g * 8]);
+      }
+      *reinterpret_cast<uint4*>(hi + (p0 + px) * cpad + g * 8) = a;
+      *reinterpret_cast<uint4*>(lo + (p0 + px) * cpad + g * 8) = b;
+    }
   }
   if (colsum) {
 #pragma unroll
@@ -103,9 +110,8 @@ int im2col3_pair(const float* x, int N, int H, int W, int C, int sign, void* hi,
     cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * C, stream);
     if (e != cudaSuccess) { set_error("im2col3: memset: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
   }
-  const long long total = 1LL * N * H * W * (cpad >> 3);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  long long blocks = (1LL * N * H * W + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
   im2col3_pair_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, N, H, W, C, sign, reinterpret_cast<__nv_bfloat16*>(hi),
                                                                    reinterpret_cast<__nv_bfloat16*>(lo), cpad, colsum);
   return check_launch("im2col3_pair_kernel");

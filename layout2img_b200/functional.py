@@ -40,7 +40,7 @@ def _sigma_and_prep(weight, sn, need_dgrad, as_1x1=False):
     (e.g. the data-gradient pair after a no-grad preparation) are produced here.  as_1x1: the (Cout, C, 3, 3) weight of
     a small-input convolution is prepared as the (Cout, 9C, 1, 1) weight of the im2col form (same memory)."""
     w = _c(weight)
-    if as_1x1:
+    if as_1x1 or w.dim() == 2:
         w = w.view(w.shape[0], -1, 1, 1)
     pre = take_prepared(weight)
     if pre is not None and (pre[0] is not None) == (sn is not None):
@@ -221,57 +221,46 @@ def _sn_of(conv):
     return conv.weight, getattr(conv, "bias", None), None
 
 
-class SNLinearFn(torch.autograd.Function):
-    """y = x @ (W_orig / sigma)^T + b for a spectrally normalised nn.Linear (the ISLA gamma/beta projections
-    norm_module.py:158-159, mask_regression.py:64, the generator's fc :409).  The power iteration, sigma and the
-    weight_orig gradient are csrc/specnorm.cu; the three GEMMs csrc/linear.cu (no library kernel)."""
-
-    @staticmethod
-    def forward(ctx, x, w_orig, bias, u, v, eps, training):
-        st = _sigma(w_orig, (u, v, eps, training))
-        x2 = _c(x.reshape(-1, x.shape[-1]))
-        y = ops.linear_fwd(x2, _c(w_orig), st.sigma, _c(bias))
-        ctx.save_for_backward(x2, w_orig, st.sigma, st.u, st.v)
-        ctx.xshape = x.shape
-        ctx.has_bias = bias is not None
-        return y.view(*x.shape[:-1], w_orig.shape[0])
-
-    @staticmethod
-    def backward(ctx, dy):
-        x2, w_orig, sigma, u, v = ctx.saved_tensors
-        dy2 = _c(dy.reshape(-1, dy.shape[-1]))
-        need = ctx.needs_input_grad
-        dx, g, db = ops.linear_bwd(dy2, x2, _c(w_orig), sigma, need_dx=need[0], need_gw=need[1], need_db=ctx.has_bias and need[2])
-        dw = None
-        if need[1]:                                                # g = dL/d(W/sigma), (R, Cc)
-            dw = ops.sn_weight_grad(g.view(g.shape[0], 1, g.shape[1]), _c(w_orig), ops.SNState(sigma, u, v))
-        return (dx.view(ctx.xshape) if dx is not None else None), dw, db, None, None, None, None
-
-
 class LinearFn(torch.autograd.Function):
-    """y = x @ W^T + b for a plain nn.Linear (the attention projections, resnet_generator_app_v2.py:148-151,208-212) and
-    the bias-free 1x1 convolutions of the PSP stages on pooled cells (:741-746): csrc/linear.cu."""
+    """y = x @ W^T + b (W = weight_orig / sigma when spectrally normalised) for every nn.Linear of the path -- the ISLA
+    gamma / beta projections (norm_module.py:158-159), mask_regression.py:64, the generator's fc
+    (resnet_generator_app_v2.py:409), the attention projections (:148-151,208-212) and the PSP stages' 1x1 convolutions on
+    pooled cells (:741-746) -- on the tensor-core convolution kernel: a linear layer over M rows is a 1x1 convolution over
+    M images of 1 x 1 pixels, so forward, dx and dW reuse conv2d_fwd / conv2d_wgrad (fp32-class bf16-pair arithmetic) and
+    the weight's operand pairs come from the network's grouped preparation.  sn = None | (u, v, eps, training)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias):
-        x2 = _c(x.reshape(-1, x.shape[-1]))
-        y = ops.linear_fwd(x2, _c(w), None, _c(bias))
-        ctx.save_for_backward(x2, w)
-        ctx.xshape = x.shape
-        ctx.has_bias = bias is not None
-        return y.view(*x.shape[:-1], w.shape[0])
+    def forward(ctx, x, weight, bias, sn):
+        n_out, k = weight.shape
+        x2 = _c(x.reshape(-1, k))
+        m = x2.shape[0]
+        xp = ops.act_split(x2.view(m, 1, 1, k))
+        st, wp = _sigma_and_prep(weight, sn, ctx.needs_input_grad[0], as_1x1=True)
+        y, _ = ops.conv2d_fwd(xp, wp.f_hi, wp.f_lo, n_out, 1, bias=_c(bias))
+        ctx.save_for_backward(xp.hi, xp.lo, wp.d_hi, wp.d_lo, weight, *(st or (None, None, None)))
+        ctx.meta = (tuple(x.shape), n_out, k, bias is not None)
+        return y.view(*x.shape[:-1], n_out)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, w = ctx.saved_tensors
-        dy2 = _c(dy.reshape(-1, dy.shape[-1]))
+        xhi, xlo, dhi, dlo, weight, sg, u, v = ctx.saved_tensors
+        xshape, n_out, k, has_bias = ctx.meta
         need = ctx.needs_input_grad
-        dx, gw, db = ops.linear_bwd(dy2, x2, _c(w), None, need_dx=need[0], need_gw=need[1], need_db=ctx.has_bias and need[2])
-        return (dx.view(ctx.xshape) if dx is not None else None), gw, db
+        dy2 = _c(dy.reshape(-1, n_out))
+        m = dy2.shape[0]
+        dyp, _, colsum = ops.grad_split(dy2.view(m, 1, 1, n_out), want_lo=True, up=False)
+        dx = dw = None
+        if need[0]:
+            dx, _ = ops.conv2d_fwd(dyp, dhi, dlo, k, 1)
+            dx = dx.view(xshape)
+        if need[1]:
+            g = ops.conv2d_wgrad(dyp, ops.Pair(xhi, xlo, k), 1)                 # (n_out, 1, k) = dL/d(W / sigma)
+            dw = ops.sn_weight_grad(g, _c(weight), ops.SNState(sg, u, v)) if sg is not None else g.view(n_out, k)
+        return dx, dw, (colsum if (has_bias and need[2]) else None), None
 
 
 def linear(x, w, bias=None):
-    return LinearFn.apply(x, w, bias)
+    return LinearFn.apply(x, w, bias, None)
 
 
 class AddLayerNormFn(torch.autograd.Function):
@@ -326,9 +315,7 @@ def sn_weight(module):
 def sn_linear(module, x):
     """Apply a (spectrally normalised) nn.Linear through SNLinearFn; plain nn.Linear modules are called as is."""
     w, b, sn = _sn_of(module)
-    if sn is None:
-        return LinearFn.apply(x, w, b)
-    return SNLinearFn.apply(x, w, b, sn[0], sn[1], sn[2], sn[3])
+    return LinearFn.apply(x, w, b, sn)
 
 
 def d_block(x, conv1, conv2, c_sc=None, down=False, optimized=False):

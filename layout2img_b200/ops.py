@@ -510,28 +510,6 @@ def avgpool2_bwd(dout):
     return dx
 
 
-def linear_fwd(x2, w, sigma=None, bias=None):
-    """x2 (M,K), w (N,K) -> (M,N) = x2 w^T / sigma + bias (csrc/linear.cu)."""
-    _chk(x2); _chk(w)
-    m, k = x2.shape
-    n = w.shape[0]
-    y = torch.empty((m, n), dtype=torch.float32, device=x2.device)
-    call("l2i_linear_fwd", x2, w, sigma, bias, m, n, k, y)
-    return y
-
-
-def linear_bwd(dy2, x2, w, sigma=None, need_dx=True, need_gw=True, need_db=False):
-    _chk(dy2); _chk(x2); _chk(w)
-    m, n = dy2.shape
-    k = x2.shape[1]
-    dev = dy2.device
-    dx = torch.empty((m, k), dtype=torch.float32, device=dev) if need_dx else None
-    gw = torch.empty((n, k), dtype=torch.float32, device=dev) if need_gw else None
-    db = torch.empty((n,), dtype=torch.float32, device=dev) if need_db else None
-    call("l2i_linear_bwd", dy2, x2, w, sigma, m, n, k, dx, gw, db)
-    return dx, gw, db
-
-
 def add_layernorm_fwd(a, b, w, bias, eps: float):
     _chk(a)
     d = a.shape[-1]

@@ -58,10 +58,13 @@ class SNGroup:
         for m in net.modules():
             hook = _sn_hook(m)
             is_conv = isinstance(m, Conv2d)
-            if hook is None and not is_conv:
+            is_lin = isinstance(m, torch.nn.Linear)
+            if hook is None and not is_conv and not is_lin:
                 continue
             w = m.weight_orig if hook is not None else m.weight
             cin, taps, pairs = 0, 0, is_conv
+            if is_lin and w.shape[0] > 1:        # linear layers run as 1x1 convolutions over M one-pixel images (functional.LinearFn)
+                cin, taps, pairs = w.shape[1], 1, True
             if is_conv:
                 cin, taps = w.shape[1], w.shape[2] * w.shape[3]
                 if taps == 9 and cin <= 4:
@@ -132,6 +135,7 @@ class SNGroup:
                     wt += [(i, cb, r0, min(R, r0 + rps)) for cb in range(col_blocks)]
                 wv += [(i, rb) for rb in range((R + 7) // 8)]
             if d["conv"]:
+                # (linear weights (R, K) have the memory layout of a (R, K, 1, 1) convolution weight)
                 gx = (pad8(d["cin"]) + 31) // 32
                 gy = (pad8(R) + 31) // 32
                 (p9 if d["taps"] == 9 else p1).extend((i, tx, ty, 0) for ty in range(gy) for tx in range(gx))

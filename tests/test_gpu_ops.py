@@ -627,7 +627,8 @@ def test_gram_projection_head_matches_reference_formula(dev, training):
 
 @pytest.mark.parametrize("M,N,K,bias", [(512, 308, 308, True), (64, 16384, 128, True), (50, 100, 128, False), (7, 65, 33, True)])
 def test_linear_kernels_match_torch(dev, M, N, K, bias):
-    """functional.linear (csrc/linear.cu strided SIMT GEMM: y = x W^T + b, dx = dy W, dW = dy^T x, db) vs fp64."""
+    """functional.linear (a linear layer as a 1x1 tensor-core convolution over M one-pixel images: y = x W^T + b, dx = dy W,
+    dW = dy^T x, db) vs fp64."""
     from layout2img_b200 import functional as L
     g = torch.Generator().manual_seed(M + N + K)
     x, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
@@ -641,11 +642,11 @@ def test_linear_kernels_match_torch(dev, M, N, K, bias):
     bg = b.to(dev).requires_grad_() if bias else None
     out = L.linear(xg.view(1, M, K), wg, bg)                      # leading dimensions are flattened
     out.backward(dy.to(dev).view(1, M, N))
-    close(out.view(M, N), ref, 1e-4, 1e-5, "linear fwd")
-    close(xg.grad, xr.grad, 1e-4, 1e-5 * max(1.0, xr.grad.abs().max().item()), "linear dx")
-    close(wg.grad, wr.grad, 1e-4, 1e-5 * wr.grad.abs().max().item(), "linear dw")
+    close(out.view(M, N), ref, 1e-4, 2e-5 * ref.abs().max().item(), "linear fwd")
+    close(xg.grad, xr.grad, 1e-4, 2e-5 * xr.grad.abs().max().item(), "linear dx")
+    close(wg.grad, wr.grad, 1e-4, 2e-5 * wr.grad.abs().max().item(), "linear dw")
     if bias:
-        close(bg.grad, br.grad, 1e-4, 1e-5 * br.grad.abs().max().item(), "linear db")
+        close(bg.grad, br.grad, 1e-4, 2e-5 * br.grad.abs().max().item(), "linear db")
 
 
 def test_add_layernorm_matches_torch(dev):
