@@ -238,6 +238,8 @@ int l2i_sn_prepare_group(const void* table, int n_modules, const int* wt_items, 
 
 /* ---- LayerNorm of the attention block (replaces nn.LayerNorm -> ATen at resnet_generator_app_v2.py:201-212; the
  *      nn.Linear layers of the path run as 1x1 convolutions through l2i_conv2d_fwd / l2i_conv2d_wgrad). ------------------ */
+/* out [N] = column sums of x [M,N] (row-major): the bias gradient of a linear layer wider than l2i_grad_split's 2048. */
+int l2i_colsum(const float* x, int M, int N, float* out, void* stream);
 /* y = LayerNorm(a + b) * w + bias over rows of D elements (b nullable); stats [rows,2] = (mean, 1/std) for the backward. */
 int l2i_add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, int rows, int D, float eps,
                           float* y, float* stats, void* stream);

@@ -216,6 +216,7 @@ int l2i_col2im3(const float* col, int ldc, int N, int H, int W, int C, int sign,
                 int res_up2, float res_scale, float* out, void* stream) {
   return col2im3(col, ldc, N, H, W, C, sign, bias, residual, res_up2, res_scale, out, ST(stream));
 }
+int l2i_colsum(const float* x, int M, int N, float* out, void* stream) { return colsum(x, M, N, out, ST(stream)); }
 int l2i_add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, int rows, int D, float eps,
                           float* y, float* stats, void* stream) {
   return add_layernorm_fwd(a, b, w, bias, rows, D, eps, y, stats, ST(stream));

@@ -118,6 +118,7 @@ int col2im3(const float* col, int ldc, int N, int H, int W, int C, int sign, con
             int res_up2, float res_scale, float* out, cudaStream_t stream);
 
 // linear.cu
+int colsum(const float* X, int M, int N, float* out, cudaStream_t stream);
 int add_layernorm_fwd(const float* a, const float* b, const float* w, const float* bias, int rows, int D, float eps, float* y,
                       float* stats, cudaStream_t stream);
 int add_layernorm_bwd(const float* a, const float* b, const float* w, const float* stats, const float* dy, int rows, int D,

@@ -6,6 +6,30 @@
 
 namespace l2i {
 
+// column sums of a [M, N] row-major matrix (the bias gradient of a wide linear layer): one block per 32 columns
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int M, int N, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (n < N)
+    for (int m = warp; m < M; m += 8) acc += __ldg(X + static_cast<size_t>(m) * N + n);
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    out[n] = t;
+  }
+}
+
+int colsum(const float* X, int M, int N, float* out, cudaStream_t stream) {
+  if (!X || !out || M <= 0 || N <= 0) { set_error("colsum: bad arguments"); return L2I_ERR_BAD_ARG; }
+  colsum_kernel<<<(N + 31) / 32, 256, 0, stream>>>(X, M, N, out);
+  return check_launch("colsum_kernel");
+}
+
 // ------------------------------------------------------------------------------------------ LayerNorm(a + b)
 // y = (s - mean) * rstd * w + bias with s = a + b (b nullable), per row of D elements; one warp per row.
 __global__ void __launch_bounds__(256)

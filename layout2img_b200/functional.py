@@ -248,7 +248,11 @@ class LinearFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         dy2 = _c(dy.reshape(-1, n_out))
         m = dy2.shape[0]
-        dyp, _, colsum = ops.grad_split(dy2.view(m, 1, 1, n_out), want_lo=True, up=False)
+        if ops.pad8(n_out) <= 2048:
+            dyp, _, colsum = ops.grad_split(dy2.view(m, 1, 1, n_out), want_lo=True, up=False)     # pair + bias gradient in one read
+        else:                                                     # fc (16384 wide), mask-regression fc (4096)
+            dyp = ops.act_split(dy2.view(m, 1, 1, n_out))
+            colsum = ops.colsum(dy2) if (has_bias and need[2]) else None
         dx = dw = None
         if need[0]:
             dx, _ = ops.conv2d_fwd(dyp, dhi, dlo, k, 1)

@@ -510,6 +510,15 @@ def avgpool2_bwd(dout):
     return dx
 
 
+def colsum(x2: torch.Tensor) -> torch.Tensor:
+    """(M, N) fp32 -> (N,) column sums."""
+    _chk(x2)
+    m, n = x2.shape
+    out = torch.empty((n,), dtype=torch.float32, device=x2.device)
+    call("l2i_colsum", x2, m, n, out)
+    return out
+
+
 def add_layernorm_fwd(a, b, w, bias, eps: float):
     _chk(a)
     d = a.shape[-1]
