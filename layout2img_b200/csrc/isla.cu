@@ -224,7 +224,7 @@ __device__ __forceinline__ float isla_masks(const float* __restrict__ mp, int O,
 #pragma unroll
     for (int o = 0; o < OM; ++o) S += m[o];
   }
-  return 1.0f / S;
+  return __frcp_rn(S);
 }
 
 template <int CPT>
@@ -310,10 +310,21 @@ __global__ void __launch_bounds__(256, 2) isla_fwd_kernel(const IslaFwdParams p)
         __nv_bfloat16 h[CPT], l[CPT];
 #pragma unroll
         for (int j = 0; j < CPT; ++j) split_bf16((p.relu & 1) ? fmaxf(y[j], 0.f) : y[j], h[j], l[j]);
-        const int hh = pix / p.W, ww = pix - hh * p.W;
-        for (int dy = 0; dy < rep; ++dy)
-          for (int dx = 0; dx < rep; ++dx) {
-            const size_t op = ((static_cast<size_t>(b) * Ho + (hh << p.up) + dy) * Wo + (ww << p.up) + dx) * p.cpad + c;
+        if (rep == 1) {                         // same resolution: the output pixel index is the input's
+          const size_t op = (static_cast<size_t>(b) * hw + pix) * p.cpad + c;
+          if constexpr (CPT == 2) {
+            *reinterpret_cast<uint32_t*>(hib + op) = pack_bf16x2(h[0], h[1]);
+            *reinterpret_cast<uint32_t*>(lob + op) = pack_bf16x2(l[0], l[1]);
+          } else {
+            hib[op] = h[0];
+            lob[op] = l[0];
+          }
+        } else {
+          const int hh = pix / p.W, ww = pix - hh * p.W;
+          const size_t o00 = ((static_cast<size_t>(b) * Ho + 2 * hh) * Wo + 2 * ww) * p.cpad + c;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const size_t op = o00 + (static_cast<size_t>(q >> 1) * Wo + (q & 1)) * p.cpad;
             if constexpr (CPT == 2) {
               *reinterpret_cast<uint32_t*>(hib + op) = pack_bf16x2(h[0], h[1]);
               *reinterpret_cast<uint32_t*>(lob + op) = pack_bf16x2(l[0], l[1]);
@@ -322,6 +333,7 @@ __global__ void __launch_bounds__(256, 2) isla_fwd_kernel(const IslaFwdParams p)
               lob[op] = l[0];
             }
           }
+        }
       }
     }
   }
@@ -439,7 +451,7 @@ __device__ __forceinline__ float isla_inv_s(const float (&m)[OM > 0 ? OM : 1]) {
 #pragma unroll
     for (int o = 0; o < OM; ++o) S += m[o];
   }
-  return 1.0f / S;
+  return __frcp_rn(S);
 }
 
 template <int OM, int CPT>
