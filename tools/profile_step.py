@@ -16,9 +16,14 @@ G = ResnetGenerator128_context(num_classes=184, output_dim=3)
 D = CombineDiscriminator128_app(num_classes=184)
 G.load_state_dict(make_state(schema_of(G), 1)); D.load_state_dict(make_state(schema_of(D), 2))
 G.to(dev).train(); D.to(dev).train()
-g_opt, d_opt = make_optimizers(G, D)
+# the step bench.py records into its CUDA graph, issued call by call so that the profiler sees every launch: fixed-shape
+# discriminator (device-side ROI preparation, no host sync), gradients in flat buckets, capturable Adam
+from layout2img_b200.train import GradBuckets
+D.static_shapes = True
+g_opt, d_opt = make_optimizers(G, D, capturable=True)
+sg, sd = GradBuckets(G), GradBuckets(D)
 d = {k: v.to(dev) for k, v in synthetic_layout(B, 8, 184, seed=0).items()}
-step = lambda: train_step(G, D, g_opt, d_opt, d["real"], d["label"], d["bbox"], d["z"], d["z_im"])
+step = lambda: train_step(G, D, g_opt, d_opt, d["real"], d["label"], d["bbox"], d["z"], d["z_im"], sync_g=sg, sync_d=sd)
 for _ in range(warm):
     step()
 torch.cuda.synchronize()
