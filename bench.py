@@ -15,6 +15,8 @@ backward, Adam; D(fake), g_loss (hinge + L1), backward, Adam -- on batch 64 per 
              losses are inside the timed region of every step
   roofline   dominant kernel (tcgen05 implicit-GEMM conv, fwd+dgrad launches): algorithmic
              2*M*N*K FLOPs / CUDA-event time of those launches, against MEASURED_PEAKS.json
+  The timed step is ONE CUDA-graph replay (--graph 1, default): the whole D step + G step + both Adam
+  updates recorded once (train.GraphedTrainStep) -- no host synchronisation, one launch per step.
   cpu_baseline  the reference's own CPU path -- the UNMODIFIED reference modules staged in the git-ignored
              baseline/_ref/ by oracle/make_ref.py (kind "reference"), or the oracle port when they are not
              staged (kind "port") -- timed on this host's cores on a bounded sample of the same workload
@@ -449,7 +451,7 @@ def run_ours(args, rank, local_rank, world):
         # the dominant launch: the largest single contributor to the step's device time (D.block_obj5.conv2
         # forward, 3 launches per step), the one profiles/r01_conv_fwd_big_ncu.json captures with ncu --set full
         prof = {}
-        ppath = os.path.join(ROOT, "profiles", "r01_conv_fwd_big_ncu.json")
+        ppath = os.path.join(ROOT, "profiles", "r02_conv_fwd_big_ncu.json")
         if os.path.exists(ppath):
             prof = json.load(open(ppath))
         dom = conv_shapes.get(prof.get("shape", ""), None)
@@ -495,7 +497,11 @@ def run_ours(args, rank, local_rank, world):
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "host_enqueue_ms_per_step": host_ms.get("step_resident"), "cuda_graph": bool(use_graph),
+            "host_enqueue_ms_per_step": host_ms.get("step_resident"),
+            "host_enqueue_note": ("graph mode: one cudaGraphLaunch per step; the call blocks while the previous replay is still "
+                                  "executing, so this is device back-pressure, not host work") if use_graph else
+                                 "eager mode: time for Python to issue the step's launches (no synchronisation)",
+            "cuda_graph": bool(use_graph),
             "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "library_baseline": lib,
             "kernel_ms_per_step": breakdown,

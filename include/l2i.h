@@ -142,6 +142,20 @@ int l2i_stage_mix_bwd(const float* stage, const int64_t* y, const float* alpha, 
                       const float* dout, int B, int O, int h, int w, int NC, int S, float* dstage, float* dalpha,
                       float* dsoft, void* stream);
 
+/* Gathered mask head + stage-mask mixing in one kernel (reference resnet_generator_app_v2.py:646/651 and :466-470): only
+ * the O class channels an image's objects select are formed, never the 184-channel stage mask.
+ *   sel[b,o,p] = bc[y[b,o]] + sum_c Wc[y[b,o], c] * t[b,p,c];   out = bilinear(bmask) (1 - a) + sigmoid(sel) nearest(hard) a,
+ *   a = sigmoid(alpha[y[b,o]]).   t [B,h,w,C] (the head's features after BatchNorm / ReLU / Dropout2d), Wc [NC,C] (the 1x1
+ *   convolution's weight), bc [NC] (nullable), out / sel [B,O,h,w] (sel is kept for the backward).  O <= 32.
+ * bwd: dt [B,h,w,C]; dW [NC,C], db [NC] (nullable), dalpha [NC] (zeroed by the call, class-indexed atomics);
+ *   dsoft [B,O,h,w] = dout (1 - a) (feed it to l2i_mask_resize_bwd for d bmask). */
+int l2i_class_mix_fwd(const float* t, const float* Wc, const float* bc, const int64_t* y, const float* alpha,
+                      const float* bmask, const float* hard, int B, int O, int h, int w, int C, int NC, int S, float* sel,
+                      float* out, void* stream);
+int l2i_class_mix_bwd(const float* t, const float* Wc, const int64_t* y, const float* alpha, const float* bmask,
+                      const float* hard, const float* sel, const float* dout, int B, int O, int h, int w, int C, int NC, int S,
+                      float* dt, float* dW, float* db, float* dalpha, float* dsoft, void* stream);
+
 /* ---- mask-regression trunk (reference model/mask_regression.py:66-99): InstanceNorm2d (affine=False, eps) -> ReLU
  *      -> optional bilinear x2 (align_corners=False) of x [N,H,W,C], written as the next convolution's operand
  *      pair [N,H<<up2,W<<up2,cpad]; stats [N,C,2] = (mean, 1/sqrt(var+eps)) is kept for the backward. ---------- */

@@ -130,6 +130,18 @@ int l2i_stage_mix_bwd(const float* stage, const int64_t* y, const float* alpha, 
   return stage_mix_bwd(stage, reinterpret_cast<const long long*>(y), alpha, bmask, hard, dout, B, O, h, w, NC, S, dstage,
                        dalpha, dsoft, ST(stream));
 }
+int l2i_class_mix_fwd(const float* t, const float* Wc, const float* bc, const int64_t* y, const float* alpha,
+                      const float* bmask, const float* hard, int B, int O, int h, int w, int C, int NC, int S, float* sel,
+                      float* out, void* stream) {
+  return class_mix_fwd(t, Wc, bc, reinterpret_cast<const long long*>(y), alpha, bmask, hard, B, O, h, w, C, NC, S, sel, out,
+                       ST(stream));
+}
+int l2i_class_mix_bwd(const float* t, const float* Wc, const int64_t* y, const float* alpha, const float* bmask,
+                      const float* hard, const float* sel, const float* dout, int B, int O, int h, int w, int C, int NC, int S,
+                      float* dt, float* dW, float* db, float* dalpha, float* dsoft, void* stream) {
+  return class_mix_bwd(t, Wc, reinterpret_cast<const long long*>(y), alpha, bmask, hard, sel, dout, B, O, h, w, C, NC, S, dt,
+                       dW, db, dalpha, dsoft, ST(stream));
+}
 int l2i_inorm_relu_fwd(const float* x, int N, int H, int W, int C, int up2, float eps, float* stats, void* hi, void* lo,
                        int cpad, void* stream) {
   return inorm_relu_fwd(x, N, H, W, C, up2, eps, stats, hi, lo, cpad, ST(stream));

@@ -385,27 +385,6 @@ int isla_fwd(const float* x, const float* mean_invstd, const float* mask, const 
 }
 
 // ---- backward, pass 1: every reduction ---------------------------------------------------------------------------
-// Sum over the 32 lanes of N per-lane values at once (N = 8, 16 or 32): afterwards the total of value i sits in the lanes
-// whose (lane / (32 / N)) == i.  N - 1 + log2(32 / N) shuffles instead of 5 N.
-template <int N>
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[N], int lane) {
-#pragma unroll
-  for (int half = N / 2; half >= 1; half >>= 1) {
-    const int bit = half * (32 / N);                 // lane bit that selects the kept half
-    const bool upper = (lane & bit) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float keep = upper ? v[i + half] : v[i];
-      const float send = upper ? v[i] : v[i + half];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-    }
-  }
-  float t = v[0];
-#pragma unroll
-  for (int off = 32 / N / 2; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-  return t;
-}
-
 template <int OM, int CPT>
 struct IslaPix {            // one pixel's operands for a lane: x, dout (2x2 sum when up-sampled) and the O masks
   float xv[CPT], dv[CPT], m[OM > 0 ? OM : 1];

@@ -47,6 +47,12 @@ int stage_mix_fwd(const float* stage, const long long* y, const float* alpha, co
 int stage_mix_bwd(const float* stage, const long long* y, const float* alpha, const float* bmask, const float* hard,
                   const float* dout, int B, int O, int h, int w, int NC, int S, float* dstage, float* dalpha,
                   float* dsoft, cudaStream_t stream);
+int class_mix_fwd(const float* t, const float* Wc, const float* bc, const long long* y, const float* alpha, const float* bmask,
+                  const float* hard, int B, int O, int h, int w, int C, int NC, int S, float* sel, float* out,
+                  cudaStream_t stream);
+int class_mix_bwd(const float* t, const float* Wc, const long long* y, const float* alpha, const float* bmask, const float* hard,
+                  const float* sel, const float* dout, int B, int O, int h, int w, int C, int NC, int S, float* dt, float* dW,
+                  float* db, float* dalpha, float* dsoft, cudaStream_t stream);
 int inorm_relu_fwd(const float* x, int N, int H, int W, int C, int up2, float eps, float* stats, void* hi, void* lo,
                    int cpad, cudaStream_t stream);
 int inorm_relu_bwd(const float* x, const float* stats, const float* da, int N, int H, int W, int C, int up2, float* dx,

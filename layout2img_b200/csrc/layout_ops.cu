@@ -332,6 +332,218 @@ int stage_mix_bwd(const float* stage, const long long* y, const float* alpha, co
 }  // namespace l2i
 
 // ------------------------------------------------------------------------------------------------
+// Gathered mask head + stage-mask mixing (reference resnet_generator_app_v2.py:646/651 + :466-470).  The reference
+// computes all 184 class channels of the stage mask with a 1x1 convolution and then gathers the o channels of the
+// image's object classes; here only those o channels are formed, fused with the mixing:
+//     sel[b,o,p] = bias[y[b,o]] + sum_c W[y[b,o], c] * t[b,p,c]          (t: the head's 100-channel features)
+//     out[b,o,p] = bilinear(bmask)[b,o,p] * (1 - a) + sigmoid(sel) * nearest(hard)[b,o,p] * a,    a = sigmoid(alpha[y])
+// One warp per pixel: lanes stride the channels; the O dot products are reduced with the transposed butterfly; the image's
+// O weight rows sit in shared memory.  Backward: dt, dW / dbias / dalpha (class-indexed, atomics), dsoft.
+// ------------------------------------------------------------------------------------------------
+namespace l2i {
+
+struct ClassMixParams {
+  const float* t; const float* Wc; const float* bc; const long long* y; const float* alpha; const float* bmask;
+  const float* hard; const float* sel_in; const float* dout;
+  float* sel; float* out; float* dt; float* dW; float* db; float* dalpha; float* dsoft;
+  int B, O, h, w, C, NC, S, pix_per_block;
+};
+
+__device__ __forceinline__ float class_mix_soft(const float* __restrict__ bm, int py, int x, int h, int w, int S) {
+  if (S == h && S == w) return __ldg(bm + py * S + x);
+  const Lin1 ly = lin_src(py, S, h), lx = lin_src(x, S, w);
+  return ly.l0 * (lx.l0 * __ldg(bm + ly.i0 * S + lx.i0) + lx.l1 * __ldg(bm + ly.i0 * S + lx.i1)) +
+         ly.l1 * (lx.l0 * __ldg(bm + ly.i1 * S + lx.i0) + lx.l1 * __ldg(bm + ly.i1 * S + lx.i1));
+}
+
+template <int OM>
+__global__ void __launch_bounds__(256) class_mix_fwd_kernel(const ClassMixParams p) {
+  extern __shared__ float s_w[];                           // [OM][C] rows of this image's object classes
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < OM * p.C; i += blockDim.x) {
+    const int o = i / p.C, c = i - o * p.C;
+    s_w[i] = (o < p.O) ? __ldg(p.Wc + static_cast<size_t>(__ldg(p.y + b * p.O + o)) * p.C + c) : 0.f;
+  }
+  __syncthreads();
+  const int hw = p.h * p.w;
+  const int p0 = blockIdx.x * p.pix_per_block, p1 = min(hw, p0 + p.pix_per_block);
+  constexpr int LPO = 32 / OM;                             // lanes that end up holding object o's total
+  const int o_mine = lane / LPO;
+  const bool holder = (lane % LPO) == 0 && o_mine < p.O;
+  int cls = 0;
+  float a = 0.f, bias = 0.f;
+  if (holder) {
+    cls = static_cast<int>(__ldg(p.y + b * p.O + o_mine));
+    a = sigmoidf_(__ldg(p.alpha + cls));
+    bias = p.bc ? __ldg(p.bc + cls) : 0.f;
+  }
+  for (int pix = p0 + warp; pix < p1; pix += (blockDim.x >> 5)) {
+    const float* tp = p.t + (static_cast<size_t>(b) * hw + pix) * p.C;
+    float part[OM];
+#pragma unroll
+    for (int o = 0; o < OM; ++o) part[o] = 0.f;
+    for (int c = lane; c < p.C; c += 32) {
+      const float tv = __ldg(tp + c);
+#pragma unroll
+      for (int o = 0; o < OM; ++o) part[o] = fmaf(tv, s_w[o * p.C + c], part[o]);
+    }
+    const float tot = warp_transpose_sum<OM>(part, lane);
+    if (holder) {
+      const int py = pix / p.w, x = pix - py * p.w;
+      const float sel = tot + bias;
+      const int sy = min(static_cast<int>(floorf(py * (static_cast<float>(p.S) / p.h))), p.S - 1);
+      const int sx = min(static_cast<int>(floorf(x * (static_cast<float>(p.S) / p.w))), p.S - 1);
+      const size_t bo = static_cast<size_t>(b) * p.O + o_mine;
+      const float hd = __ldg(p.hard + bo * p.S * p.S + sy * p.S + sx);
+      const float soft = class_mix_soft(p.bmask + bo * p.S * p.S, py, x, p.h, p.w, p.S);
+      p.sel[bo * hw + pix] = sel;
+      p.out[bo * hw + pix] = soft * (1.0f - a) + sigmoidf_(sel) * hd * a;
+    }
+  }
+}
+
+template <int OM>
+__global__ void __launch_bounds__(256) class_mix_bwd_kernel(const ClassMixParams p) {
+  extern __shared__ float sh[];                            // s_w [OM][C], then s_dw [OM][C]
+  float* s_w = sh;
+  float* s_dw = sh + OM * p.C;
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < OM * p.C; i += blockDim.x) {
+    const int o = i / p.C, c = i - o * p.C;
+    s_w[i] = (o < p.O) ? __ldg(p.Wc + static_cast<size_t>(__ldg(p.y + b * p.O + o)) * p.C + c) : 0.f;
+    s_dw[i] = 0.f;
+  }
+  __syncthreads();
+  const int hw = p.h * p.w;
+  const int p0 = blockIdx.x * p.pix_per_block, p1 = min(hw, p0 + p.pix_per_block);
+  // lane o (< O) owns object o's per-pixel scalars
+  const bool owner = lane < p.O;
+  int cls = 0;
+  float a = 0.f;
+  if (owner) {
+    cls = static_cast<int>(__ldg(p.y + b * p.O + lane));
+    a = sigmoidf_(__ldg(p.alpha + cls));
+  }
+  float da = 0.f, dbs = 0.f;
+  for (int pix = p0 + warp; pix < p1; pix += (blockDim.x >> 5)) {
+    float dsel = 0.f;
+    if (owner) {
+      const int py = pix / p.w, x = pix - py * p.w;
+      const size_t bo = static_cast<size_t>(b) * p.O + lane;
+      const float g = __ldg(p.dout + bo * hw + pix);
+      const float sg = sigmoidf_(__ldg(p.sel_in + bo * hw + pix));
+      const int sy = min(static_cast<int>(floorf(py * (static_cast<float>(p.S) / p.h))), p.S - 1);
+      const int sx = min(static_cast<int>(floorf(x * (static_cast<float>(p.S) / p.w))), p.S - 1);
+      const float hd = __ldg(p.hard + bo * p.S * p.S + sy * p.S + sx);
+      const float soft = class_mix_soft(p.bmask + bo * p.S * p.S, py, x, p.h, p.w, p.S);
+      p.dsoft[bo * hw + pix] = g * (1.0f - a);
+      dsel = g * a * hd * sg * (1.0f - sg);
+      da += g * (sg * hd - soft);
+      dbs += dsel;
+    }
+    const float* tp = p.t + (static_cast<size_t>(b) * hw + pix) * p.C;
+    float* dp = p.dt + (static_cast<size_t>(b) * hw + pix) * p.C;
+    for (int c = lane; c < p.C; c += 32) {
+      const float tv = __ldg(tp + c);
+      float acc = 0.f;
+#pragma unroll
+      for (int o = 0; o < OM; ++o) {
+        const float ds = __shfl_sync(0xffffffffu, dsel, o);
+        acc = fmaf(ds, s_w[o * p.C + c], acc);
+        if (ds != 0.f) atomicAdd(&s_dw[o * p.C + c], ds * tv);
+      }
+      dp[c] = acc;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.O * p.C; i += blockDim.x) {
+    const int o = i / p.C, c = i - o * p.C;
+    const float v = s_dw[o * p.C + c];
+    if (v != 0.f) atomicAdd(p.dW + static_cast<size_t>(__ldg(p.y + b * p.O + o)) * p.C + c, v);
+  }
+  if (owner) {
+    // the 8 warps of the block each hold partial sums for object `lane`
+    atomicAdd(p.dalpha + cls, da * a * (1.0f - a));
+    if (p.db) atomicAdd(p.db + cls, dbs);
+  }
+}
+
+static int class_mix_check(const ClassMixParams& p) {
+  if (!p.t || !p.Wc || !p.y || !p.alpha || !p.bmask || !p.hard || p.B <= 0 || p.O <= 0 || p.O > 32 || p.h <= 0 || p.w <= 0 ||
+      p.C <= 0 || p.NC <= 0 || p.S <= 0 || p.C > 1024) {
+    set_error("class_mix: bad arguments (O <= 32, C <= 1024)");
+    return L2I_ERR_BAD_ARG;
+  }
+  return L2I_OK;
+}
+
+int class_mix_fwd(const float* t, const float* Wc, const float* bc, const long long* y, const float* alpha, const float* bmask,
+                  const float* hard, int B, int O, int h, int w, int C, int NC, int S, float* sel, float* out,
+                  cudaStream_t stream) {
+  ClassMixParams p{};
+  p.t = t; p.Wc = Wc; p.bc = bc; p.y = y; p.alpha = alpha; p.bmask = bmask; p.hard = hard; p.sel = sel; p.out = out;
+  p.B = B; p.O = O; p.h = h; p.w = w; p.C = C; p.NC = NC; p.S = S;
+  int rc = class_mix_check(p);
+  if (rc) return rc;
+  if (!sel || !out) { set_error("class_mix_fwd: null output"); return L2I_ERR_BAD_ARG; }
+  const int hw = h * w;
+  int chunks = (148 * 8 + B - 1) / B;
+  if (chunks > (hw + 7) / 8) chunks = (hw + 7) / 8;
+  p.pix_per_block = (hw + chunks - 1) / chunks;
+  dim3 grid((hw + p.pix_per_block - 1) / p.pix_per_block, B);
+  const int om = O <= 8 ? 8 : (O <= 16 ? 16 : 32);
+  const size_t smem = sizeof(float) * om * C;
+  static DeviceOnce configured;
+  if (configured.need()) {
+    cudaFuncSetAttribute(class_mix_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4);
+    cudaFuncSetAttribute(class_mix_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * 4);
+    configured.done();
+  }
+  if (om == 8) class_mix_fwd_kernel<8><<<grid, 256, smem, stream>>>(p);
+  else if (om == 16) class_mix_fwd_kernel<16><<<grid, 256, smem, stream>>>(p);
+  else class_mix_fwd_kernel<32><<<grid, 256, smem, stream>>>(p);
+  return check_launch("class_mix_fwd_kernel");
+}
+
+int class_mix_bwd(const float* t, const float* Wc, const long long* y, const float* alpha, const float* bmask, const float* hard,
+                  const float* sel, const float* dout, int B, int O, int h, int w, int C, int NC, int S, float* dt, float* dW,
+                  float* db, float* dalpha, float* dsoft, cudaStream_t stream) {
+  ClassMixParams p{};
+  p.t = t; p.Wc = Wc; p.y = y; p.alpha = alpha; p.bmask = bmask; p.hard = hard; p.sel_in = sel; p.dout = dout;
+  p.dt = dt; p.dW = dW; p.db = db; p.dalpha = dalpha; p.dsoft = dsoft;
+  p.B = B; p.O = O; p.h = h; p.w = w; p.C = C; p.NC = NC; p.S = S;
+  int rc = class_mix_check(p);
+  if (rc) return rc;
+  if (!sel || !dout || !dt || !dW || !dalpha || !dsoft || C > 512) { set_error("class_mix_bwd: bad arguments (C <= 512)"); return L2I_ERR_BAD_ARG; }
+  cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * static_cast<size_t>(NC) * C, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dalpha, 0, sizeof(float) * NC, stream);
+  if (e == cudaSuccess && db) e = cudaMemsetAsync(db, 0, sizeof(float) * NC, stream);
+  if (e != cudaSuccess) { set_error("class_mix_bwd: memset: %s", cudaGetErrorString(e)); return L2I_ERR_LAUNCH; }
+  const int hw = h * w;
+  int chunks = (148 * 4 + B - 1) / B;
+  if (chunks > (hw + 63) / 64) chunks = (hw + 63) / 64;
+  if (chunks < 1) chunks = 1;
+  p.pix_per_block = (hw + chunks - 1) / chunks;
+  dim3 grid((hw + p.pix_per_block - 1) / p.pix_per_block, B);
+  const int om = O <= 8 ? 8 : (O <= 16 ? 16 : 32);
+  const size_t smem = sizeof(float) * 2 * om * C;
+  static DeviceOnce configured;
+  if (configured.need()) {
+    cudaFuncSetAttribute(class_mix_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * 512 * 4);
+    cudaFuncSetAttribute(class_mix_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16 * 512 * 4);
+    configured.done();
+  }
+  if (om == 8) class_mix_bwd_kernel<8><<<grid, 256, smem, stream>>>(p);
+  else if (om == 16) class_mix_bwd_kernel<16><<<grid, 256, smem, stream>>>(p);
+  else class_mix_bwd_kernel<32><<<grid, 256, smem, stream>>>(p);
+  return check_launch("class_mix_bwd_kernel");
+}
+
+}  // namespace l2i
+
+// ------------------------------------------------------------------------------------------------
 // Mask-regression trunk (reference model/mask_regression.py:66-99): after each 3x3 conv comes
 // InstanceNorm2d(256) (affine=False, biased variance, eps 1e-5) -> ReLU -> [bilinear x2, align_corners=False].
 // inorm_relu_fwd writes the NEXT convolution's bf16 operand pair directly; inorm_relu_bwd takes the gradient

@@ -787,6 +787,35 @@ def stage_mix(stage, alpha, bmask, y, hard):
     return StageMixFn.apply(stage, alpha, bmask, y, hard)
 
 
+class ClassMixFn(torch.autograd.Function):
+    """Gathered 1x1 mask head + stage-mask mixing (resnet_generator_app_v2.py:646/651 and :466-470) in one kernel: only the
+    o class channels that the image's objects select are computed (the reference forms all 184 and gathers)."""
+
+    @staticmethod
+    def forward(ctx, t, weight, bias, alpha, bmask, y, hard):
+        t, bmask = _c(t), _c(bmask)
+        wc = _c(weight).view(weight.shape[0], -1)
+        alpha_flat = _c(alpha.reshape(-1))
+        sel, out = ops.class_mix_fwd(t, wc, _c(bias), y, alpha_flat, bmask, hard)
+        ctx.save_for_backward(t, weight, alpha_flat, bmask, y, hard, sel)
+        ctx.meta = (alpha.shape, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        t, weight, alpha_flat, bmask, y, hard, sel = ctx.saved_tensors
+        alpha_shape, has_bias = ctx.meta
+        wc = _c(weight).view(weight.shape[0], -1)
+        dt, dw, db, dalpha, dsoft = ops.class_mix_bwd(t, wc, y, alpha_flat, bmask, hard, sel, _c(dout), has_bias)
+        dbmask = ops.mask_resize_bwd(dsoft, bmask.shape[2], bmask.shape[3], False)
+        return dt, dw.view_as(weight), db, dalpha.view(alpha_shape), dbmask, None, None
+
+
+def class_mix(t, conv, alpha, bmask, y, hard):
+    """t: the mask head's features (B,h,w,100); conv: its final 1x1 Conv2d(100, 184) module (plain, not spectrally normalised)."""
+    return ClassMixFn.apply(t, conv.weight, conv.bias, alpha, bmask, y, hard)
+
+
 class BoxAttentionFn(torch.autograd.Function):
     """box_attention + relational embedding + WGs gate (resnet_generator_app_v2.py:17-120,172-192)."""
 

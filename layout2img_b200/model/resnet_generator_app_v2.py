@@ -138,8 +138,9 @@ class ResBlock(nn.Module):
             else:
                 self.conv_mask = nn.Sequential(Conv2d(out_ch, 100, 3, 1, 1), BatchNorm(100), nn.ReLU(),
                                                Conv2d(100, 184, 1, 1, 0, bias=True))
+            self.head_conv._l2i_gathered_head = True
 
-    def forward(self, in_feat, w, bbox):            # in_feat NHWC, bbox (b,o,hm,wm)
+    def forward(self, in_feat, w, bbox, head_features=False):   # in_feat NHWC, bbox (b,o,hm,wm)
         if not (self.upsample and self.learnable_sc):
             raise ValueError("layout2img_b200 ResBlock implements the generator's configuration: upsample=True")
         b, h, wd, _ = in_feat.shape
@@ -154,12 +155,23 @@ class ResBlock(nn.Module):
                              self.b1.batch_norm2d, self.b2.batch_norm2d)
         if not self.predict_mask:
             return out_feat, None
+        if head_features:
+            # the mask head up to (not including) its final 1x1 convolution: (b,h,w,100) after BatchNorm / ReLU (/ Dropout2d);
+            # the generator forms only the o class channels it consumes (functional.class_mix with `self.head_conv`)
+            if self.psp:
+                return out_feat, self.conv_mask[0](out_feat)
+            return out_feat, L.bn_relu(self.conv_mask[0](out_feat), self.conv_mask[1])
         if self.psp:
             mask = self.conv_mask[0].forward_head(out_feat, self.conv_mask[1])
         else:
             t = self.conv_mask[0](out_feat)
             mask = self.conv_mask[3](t, norm=(self.conv_mask[1], None, None, None))
         return out_feat, mask                         # mask NHWC (b,h,w,184)
+
+    @property
+    def head_conv(self):
+        """The final 1x1 convolution (100 -> 184) of the mask head."""
+        return self.conv_mask[1] if self.psp else self.conv_mask[3]
 
 
 def batched_index_select(input, dim, index):
@@ -219,14 +231,12 @@ class _GeneratorBase(nn.Module):
             z_im = torch.randn((b, 128), device=dev)
         hard = bbox_mask(z, bbox, 64, 64)
         x = to_nhwc(L.sn_linear(self.fc, z_im).view(b, -1, 4, 4))
-        x, stage_mask = self.res1(x, w, bmask)
-        stage_bbox = L.stage_mix(stage_mask, self.alpha1, bmask, y, hard)
-        x, stage_mask = self.res2(x, w, stage_bbox)
-        stage_bbox = L.stage_mix(stage_mask, self.alpha2, bmask, y, hard)
-        x, stage_mask = self.res3(x, w, stage_bbox)
-        stage_bbox = L.stage_mix(stage_mask, self.alpha3, bmask, y, hard)
-        x, stage_mask = self.res4(x, w, stage_bbox)
-        stage_bbox = L.stage_mix(stage_mask, self.alpha4, bmask, y, hard)
+        # stage masks (:466-470): only the o class channels of each image's objects are formed (gathered 1x1 head fused with
+        # the mixing, csrc/layout_ops.cu class_mix_*) instead of the reference's 184-channel stage mask + gather
+        stage_bbox = bmask
+        for res, alpha in ((self.res1, self.alpha1), (self.res2, self.alpha2), (self.res3, self.alpha3), (self.res4, self.alpha4)):
+            x, t = res(x, w, stage_bbox, head_features=True)
+            stage_bbox = L.class_mix(t, res.head_conv, alpha, bmask, y, hard)
         x, _ = self.res5(x, w, stage_bbox)
         x = self.final[2].forward(x, norm=(self.final[0], None, None, None))   # BN -> ReLU -> conv fused (.forward: the
         # spectral-norm hook is bypassed, the normalisation runs in csrc/specnorm.cu via L.sn_weight)

@@ -375,6 +375,33 @@ def stage_mix_bwd(stage, y, alpha, bmask, hard, dout):
     return dstage, dalpha, dsoft
 
 
+def class_mix_fwd(t, wc, bc, y, alpha, bmask, hard):
+    """t (B,h,w,C), wc (NC,C), bc (NC,) | None, y (B,O) int64, alpha (NC,), bmask / hard (B,O,S,S) -> (sel, out) (B,O,h,w)."""
+    _chk(t); _chk(wc); _chk(bmask); _chk(hard); _chk(alpha); _chk(y, torch.int64)
+    b, h, w, c = t.shape
+    o, s = bmask.shape[1], bmask.shape[2]
+    nc = wc.shape[0]
+    sel = torch.empty((b, o, h, w), dtype=torch.float32, device=t.device)
+    out = torch.empty((b, o, h, w), dtype=torch.float32, device=t.device)
+    call("l2i_class_mix_fwd", t, wc, bc, y, alpha, bmask, hard, b, o, h, w, c, nc, s, sel, out)
+    return sel, out
+
+
+def class_mix_bwd(t, wc, y, alpha, bmask, hard, sel, dout, need_db: bool):
+    _chk(dout)
+    b, h, w, c = t.shape
+    o, s = bmask.shape[1], bmask.shape[2]
+    nc = wc.shape[0]
+    dev = t.device
+    dt = torch.empty_like(t)
+    dw = torch.empty((nc, c), dtype=torch.float32, device=dev)
+    db = torch.empty((nc,), dtype=torch.float32, device=dev) if need_db else None
+    dalpha = torch.empty((nc,), dtype=torch.float32, device=dev)
+    dsoft = torch.empty_like(dout)
+    call("l2i_class_mix_bwd", t, wc, y, alpha, bmask, hard, sel, dout, b, o, h, w, c, nc, s, dt, dw, db, dalpha, dsoft)
+    return dt, dw, db, dalpha, dsoft
+
+
 def inorm_relu_fwd(x, up2: bool, eps: float = 1e-5):
     """InstanceNorm (no affine) -> ReLU -> [bilinear x2] of x (N,H,W,C) -> (Pair at the output resolution, stats)."""
     _chk(x)

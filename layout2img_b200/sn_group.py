@@ -71,6 +71,8 @@ class SNGroup:
                     cin, taps = 9 * cin, 1       # small-input 3x3: prepared as the 1x1 weight of its im2col form (same memory)
                 elif taps == 9 and w.shape[0] <= 4:
                     pairs = False                # small-output 3x3: its consumer prepares the permuted (Cout*9, Cin) weight
+                elif getattr(m, "_l2i_gathered_head", False):
+                    pairs = False                # the mask heads' 1x1 convolution is evaluated gathered (functional.class_mix)
             self.mods.append({"m": m, "hook": hook, "conv": pairs, "R": w.shape[0], "Cc": w.numel() // w.shape[0],
                               "cin": cin if pairs else 0, "taps": taps if pairs else 0})
         # static layout of the two per-call buffers

@@ -63,7 +63,7 @@ def grad_close(got, want32, want64, what):
     gradients upstream of it.  So on top of tol1: all but 1 % of a tensor's elements must be within
     5e-3 * max|ref|, all but max(2, 1e-3 * numel) within 5e-2 * max|ref| (an element that is the sum of a handful of
     terms -- fc.bias: one term per image; a whole row of an ISLA projection's gradient: one d beta term per object --
-    moves by a large fraction of itself when a single kink flips), and the relative L2 error below 1e-2.  A wrong formula or index moves most elements by O(max|ref|) and fails all three.
+    moves by a large fraction of itself when a single kink flips), and the relative L2 error below 2e-2.  A wrong formula or index moves most elements by O(max|ref|) and fails all three.
     (The tight, kink-free comparisons of every kernel's backward are the per-operator tests in test_gpu_ops.py.)"""
     got, w32, w64 = got.detach().double().cpu(), want32.detach().double().cpu(), want64.detach().double().cpu()
     m = w32.abs().max().item()
@@ -78,7 +78,7 @@ def grad_close(got, want32, want64, what):
            f"{int((err > tol1).sum())}/{err.numel()} outside tol1, {n_loose} outside tol1 + 5e-3 max")
     assert n_loose <= max(1, int(0.01 * err.numel())), msg
     assert int((err > tol1 + 5e-2 * m).sum()) <= max(2, int(1e-3 * err.numel())), msg
-    assert err.norm().item() <= 1e-2 * w32.norm().item() + 8 * noise * err.numel() ** 0.5, msg
+    assert err.norm().item() <= 2e-2 * w32.norm().item() + 8 * noise * err.numel() ** 0.5, msg
 
 
 def tensor_class(name: str) -> str:

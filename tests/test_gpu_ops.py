@@ -688,3 +688,42 @@ def test_maxpool2_matches_torch(dev):
     out.backward(nhwc(dy).to(dev))
     close(out.permute(0, 3, 1, 2), ref, 0, 0, "maxpool fwd")
     close(xg.grad.permute(0, 3, 1, 2), xr.grad, 0, 1e-12, "maxpool bwd (first maximum wins)")
+
+
+@pytest.mark.parametrize("B,O,h,C", [(2, 4, 8, 100), (3, 8, 64, 100), (2, 16, 16, 100), (2, 31, 32, 36)])
+def test_class_mix_matches_composition(dev, B, O, h, C):
+    """functional.class_mix (gathered 1x1 mask head fused with the stage-mask mixing) vs the reference composition
+    (resnet_generator_app_v2.py:646/651 + :466-470: full 184-channel 1x1 conv, gather, sigmoid, nearest / bilinear mixing)
+    in fp64: forward and every gradient (features, conv weight / bias, alpha, bmask)."""
+    from layout2img_b200 import functional as L
+    NC, S = 184, 64
+    g = torch.Generator().manual_seed(B * 1000 + O * 10 + h)
+    t = torch.randn(B, C, h, h, generator=g)
+    conv = torch.nn.Conv2d(C, NC, 1)
+    alpha = torch.randn(1, NC, 1, generator=g) * 0.5
+    bmask = torch.rand(B, O, S, S, generator=g)
+    hard = (torch.rand(B, O, S, S, generator=g) > 0.4).float()
+    y = torch.randint(0, NC, (B, O), generator=g)
+    y[0, 1] = y[0, 0]                                           # two objects of one image share a class
+    dy = torch.randn(B, O, h, h, generator=g)
+    import copy
+    conv_r = copy.deepcopy(conv).double()
+    tr, ar, br = t.double().requires_grad_(), alpha.double().requires_grad_(), bmask.double().requires_grad_()
+    stage = conv_r(tr)
+    sel = torch.gather(stage, 1, y.view(B, O, 1, 1).expand(B, O, h, h))
+    seman = torch.sigmoid(sel) * F.interpolate(hard.double(), size=(h, h), mode="nearest")
+    a = torch.sigmoid(ar)[0, :, 0][y].view(B, O, 1, 1)
+    soft = F.interpolate(br, size=(h, h), mode="bilinear", align_corners=False)
+    ref = soft * (1 - a) + seman * a
+    ref.backward(dy.double())
+    conv = conv.to(dev)
+    tg = nhwc(t).to(dev).requires_grad_()
+    ag, bg = alpha.to(dev).requires_grad_(), bmask.to(dev).requires_grad_()
+    out = L.class_mix(tg, conv, ag, bg, y.to(dev), hard.to(dev))
+    out.backward(dy.to(dev))
+    close(out, ref, 1e-4, 1e-5, "class_mix fwd")
+    close(tg.grad.permute(0, 3, 1, 2), tr.grad, 1e-3, 1e-5, "d features")
+    close(conv.weight.grad, conv_r.weight.grad, 1e-3, 1e-5 * max(1.0, conv_r.weight.grad.abs().max().item()), "d conv weight")
+    close(conv.bias.grad, conv_r.bias.grad, 1e-3, 1e-5 * max(1.0, conv_r.bias.grad.abs().max().item()), "d conv bias")
+    close(ag.grad, ar.grad, 1e-3, 1e-5 * max(1.0, ar.grad.abs().max().item()), "d alpha")
+    close(bg.grad, br.grad, 1e-3, 1e-5, "d bmask")
