@@ -445,14 +445,16 @@ __global__ void __launch_bounds__(256) class_mix_bwd_kernel(const ClassMixParams
     }
     const float* tp = p.t + (static_cast<size_t>(b) * hw + pix) * p.C;
     float* dp = p.dt + (static_cast<size_t>(b) * hw + pix) * p.C;
+    float ds[OM];                                          // every lane gets all objects' d sel (all 32 lanes take part)
+#pragma unroll
+    for (int o = 0; o < OM; ++o) ds[o] = __shfl_sync(0xffffffffu, dsel, o);
     for (int c = lane; c < p.C; c += 32) {
       const float tv = __ldg(tp + c);
       float acc = 0.f;
 #pragma unroll
       for (int o = 0; o < OM; ++o) {
-        const float ds = __shfl_sync(0xffffffffu, dsel, o);
-        acc = fmaf(ds, s_w[o * p.C + c], acc);
-        if (ds != 0.f) atomicAdd(&s_dw[o * p.C + c], ds * tv);
+        acc = fmaf(ds[o], s_w[o * p.C + c], acc);
+        if (ds[o] != 0.f) atomicAdd(&s_dw[o * p.C + c], ds[o] * tv);
       }
       dp[c] = acc;
     }
