@@ -99,7 +99,10 @@ class GradBuckets:
     On a single process it only provides the flat gradient buffer (zero_grad = one memset).  Works with NCCL (streams,
     ReduceOp.AVG) and with gloo on CPU tensors (synchronous; used by the CPU tests)."""
 
-    def __init__(self, module: torch.nn.Module, bucket_mb: float = 48.0, group=None, broadcast: bool = True):
+    def __init__(self, module: torch.nn.Module, bucket_mb: Optional[float] = None, group=None, broadcast: bool = True):
+        if bucket_mb is None:
+            import os
+            bucket_mb = float(os.environ.get("L2I_BUCKET_MB", "48"))
         self.params: List[torch.nn.Parameter] = [p for p in module.parameters() if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
