@@ -434,6 +434,26 @@ def run_ours(args, rank, local_rank, world):
         return train_step(G, D, g_opt, d_opt, devd["real"], devd["label"], devd["bbox"], devd["z"], devd["z_im"],
                           sync_g=graphed.sync_g, sync_d=graphed.sync_d)
 
+    if args.timeline:
+        # device timeline of two steps (CUPTI through torch.profiler; every rank steps, rank 0 writes): which kernels
+        # ran when, on which stream -- used to see how the NCCL all-reduces interleave with the backward pass
+        from torch.profiler import ProfilerActivity, profile
+        barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step_resident()
+            step_resident()
+            torch.cuda.synchronize()
+        if rank == 0:
+            evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
+                         key=lambda e: e.time_range.start)
+            with open(args.timeline, "w") as f:
+                f.write("start_us,dur_us,stream,name\n")
+                t0 = evs[0].time_range.start if evs else 0
+                for e in evs:
+                    f.write(f"{e.time_range.start - t0:.1f},{e.time_range.end - e.time_range.start:.1f},"
+                            f"{getattr(e, 'device_resource_id', -1)},\"{e.name[:80]}\"\n")
+        barrier()
+
     agg, step_ms = kernel_breakdown(step_eager if graphed is not None else step_resident)
     conv_shapes = agg.pop("_conv_shapes")
     if rank == 0 and args.shapes_file:
@@ -541,6 +561,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (the metric is quoted at 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--shapes-file", default=None, help="write the per-shape convolution timing table here")
+    ap.add_argument("--timeline", default=None, help="write a CSV device timeline (kernel, stream, start, duration) of two steps here")
     ap.add_argument("--sync-bn", action="store_true",
                     help="N>1: batch-norm statistics over the global batch (the reference's multi-GPU SynchronizedBatchNorm2d) "
                          "instead of per-rank statistics")

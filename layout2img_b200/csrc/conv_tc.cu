@@ -31,6 +31,7 @@
 // of the tile's columns -- with one warp per SM sub-partition the epilogue, not the tensor core, paced every
 // layer with K <= 2304), 4 in the weight-gradient kernel.
 #include <stdlib.h>
+#include <atomic>
 #include "common.cuh"
 #include "conv_tc.h"
 
@@ -80,9 +81,19 @@ __device__ __forceinline__ void add_pass_chunk(uint32_t taddr, bool first, float
   }
 }
 
-// Persistent kernel: gridDim.x CTAs (one per SM) walk the (m_tile, n_tile) list with stride gridDim.x.
+// Persistent kernel: gridDim.x CTAs (one per SM) walk the (m_tile, n_tile) list.
 // The TMA producer and the MMA issuer run ahead across tile boundaries (the smem ring never drains);
 // with two TMEM accumulator buffers the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Tile order: the producer lane is the CTA's scheduler.  It takes tile numbers from a device-wide counter (work
+// stealing; p.sched_slot >= 0) or with stride gridDim.x (p.sched_slot < 0) and hands them to the MMA issuer and the
+// epilogue warps through a small shared-memory queue.  With the counter a CTA that starts late -- its SM was held by
+// another kernel, e.g. an NCCL all-reduce overlapping the backward pass -- finds the list already drained by its
+// peers and exits, where a static stride would leave its whole share of tiles for a second wave (measured: the
+// overlapped all-reduces cost as much as exposed ones).  The last producer to retire zeroes the slot.
+constexpr int kSchedSlots = 1024;              // launches take slots round-robin; a slot is busy for one kernel's lifetime
+__device__ int g_tile_sched[2 * kSchedSlots];  // [slot] = {next tile, CTAs finished}
+constexpr int kSched = 4;                      // depth of the per-CTA tile queue
 template <int BN, bool HALO>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -100,12 +111,21 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   uint64_t* bempty_bar = bfull_bar + kNBarB;
   uint64_t* tfull_bar = bempty_bar + kNBarB;          // [2] accumulator buffer complete
   uint64_t* tempty_bar = tfull_bar + 2;               // [2] accumulator buffer drained by the epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* sfull_bar = tempty_bar + 2;               // [kSched] tile queue entry written by the producer lane
+  uint64_t* sempty_bar = sfull_bar + kSched;          // [kSched] ... read by the MMA issuer and every epilogue thread
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty_bar + kSched);
+  volatile int* sched_tile = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [kSched]
+  static_assert((kNBarA + kNBarB) * 2 * 8 + 4 * 8 + 2 * kSched * 8 + 4 + kSched * 4 <= 256, "barrier area");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int k_iters = HALO ? p.kchunks : p.taps * p.kchunks;   // halo: one iteration = one chunk, all nine taps
   const int total_tiles = p.m_tiles * p.n_tiles;
+
+  // the first tile number is requested before the set-up below, which hides the atomic's round trip
+  int* const sched = p.sched_slot >= 0 ? g_tile_sched + 2 * p.sched_slot : nullptr;
+  int t_first = blockIdx.x;
+  if (sched && threadIdx.x == 0) t_first = atomicAdd(sched, 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
@@ -124,6 +144,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], kFwdThreads - 64);
     }
+    for (int s = 0; s < kSched; ++s) {
+      mbar_init(&sfull_bar[s], 1);
+      mbar_init(&sempty_bar[s], kFwdThreads - 64 + 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -131,6 +155,37 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // ---- tile queue.  Producer side: fetch() = next tile number of this CTA, publish() = hand it to the consumers
+  // (a number >= total_tiles tells them to stop).  Consumer side: next_tile().
+  int sq = 0;                                       // queue position of this thread (producer or consumer)
+  auto fetch = [&](int cur) -> int { return sched ? atomicAdd(sched, 1) : cur + static_cast<int>(gridDim.x); };
+  // producer lane, after its last fetch: this CTA will not touch the counter again.  The CTA that counts gridDim.x - 1
+  // others before it leaves the slot zeroed for the launch that reuses it (the consumers are still busy with the last
+  // tile, so this costs nothing at the end of the kernel).
+  auto retire = [&]() {
+    if (!sched) return;
+    __threadfence();
+    if (atomicAdd(sched + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+    }
+  };
+  auto publish = [&](int t) {
+    const int s = sq % kSched;
+    mbar_wait(&sempty_bar[s], ((sq / kSched) & 1) ^ 1);
+    sched_tile[s] = t;
+    mbar_arrive(&sfull_bar[s]);                     // release: the store above is visible to whoever sees this phase
+    ++sq;
+  };
+  auto next_tile = [&]() -> int {
+    const int s = sq % kSched;
+    mbar_wait(&sfull_bar[s], (sq / kSched) & 1);
+    const int t = sched_tile[s];
+    mbar_arrive(&sempty_bar[s]);
+    ++sq;
+    return t;
+  };
 
   if (warp == 0) {
     if (lane == 0 && HALO) {
@@ -151,12 +206,16 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         tma_load_4d(st + Cfg::kHaloBytes, &tm_a_lo, &full_bar[s], kc * kBK, w0 - 1, h0 - 1, n0);
         ++ja;
       };
-      if (blockIdx.x < total_tiles) load_a(blockIdx.x, 0);
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int t = t_first;
+      if (t < total_tiles) load_a(t, 0);
+      for (;;) {
+        publish(t);
+        if (t >= total_tiles) break;
+        const int t_next = fetch(t);
         const int co0 = (t % p.n_tiles) * BN;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           if (kc + 1 < p.kchunks) load_a(t, kc + 1);
-          else if (t + static_cast<int>(gridDim.x) < total_tiles) load_a(t + gridDim.x, 0);
+          else if (t_next < total_tiles) load_a(t_next, 0);
           for (int tap = 0; tap < 9; ++tap, ++jb) {
             const int s = jb % Cfg::kBStages;
             mbar_wait(&bempty_bar[s], ((jb / Cfg::kBStages) & 1) ^ 1);
@@ -166,10 +225,15 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             tma_load_2d(st + Cfg::kBBytes, &tm_b_lo, &bfull_bar[s], tap * p.cin_pad + kc * kBK, co0);
           }
         }
+        t = t_next;
       }
+      retire();
     } else if (lane == 0) {
       int ring = 0;                               // stage counter, runs on across tiles
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_first;;) {
+        publish(t);
+        if (t >= total_tiles) break;
+        const int t_next = fetch(t);              // requested before this tile's loads: the atomic's latency hides behind them
         const int nt = t % p.n_tiles;
         const int mt = t / p.n_tiles;
         const int w0 = (mt % p.tiles_w) * p.TW;
@@ -197,7 +261,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             tma_load_2d(st + 2 * kTileBytes + Cfg::kBBytes, &tm_b_lo, &full_bar[s], tap * p.cin_pad + kc * kBK, co0);
           }
         }
+        t = t_next;
       }
+      retire();
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -205,7 +271,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       constexpr uint32_t idesc2 = umma_idesc_bf16(128, 2 * BN, 0, 0);
       int ring = 0, ring_b = 0, pass_i = 0;       // smem stage counters / accumulator pass counter (run across tiles)
       (void)ring_b;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = next_tile(); t < total_tiles; t = next_tile()) {
         int it = 0;
         for (int ps = 0; ps < p.n_pass; ++ps, ++pass_i) {
           const int buf = pass_i & 1;
@@ -305,7 +371,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const float pool_scale = (p.pool == 1) ? 0.25f : 1.0f;
     int pass_i = 0;
     float acc[HN];
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = next_tile(); t < total_tiles; t = next_tile()) {
       const int nt = t % p.n_tiles;
       const int mt = t / p.n_tiles;
       const int w = (mt % p.tiles_w) * p.TW + tw;
@@ -839,6 +905,12 @@ int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream) {
   p.mask_hi = reinterpret_cast<const __nv_bfloat16*>(a.mask_hi); p.mask_cpad = a.mask_cpad; p.pool = a.pool;
   static const int ncat_enabled = env_int("L2I_CONV_NCAT", 1);
   p.ncat = ncat_enabled;
+  // L2I_CONV_DYNAMIC=1 hands the tiles out through the device-wide counter.  Off by default: measured on B200 it is
+  // 0.3 % slower than the static stride on one GPU and gains nothing at 4 GPUs with the all-reduces overlapping the
+  // backward pass (88.6 vs 89.0 ms / step) -- the NCCL kernels do not displace enough CTAs for long enough to matter.
+  static const int dynamic_enabled = env_int("L2I_CONV_DYNAMIC", 0);
+  static std::atomic<unsigned> next_slot{0};
+  p.sched_slot = dynamic_enabled ? static_cast<int>(next_slot.fetch_add(1, std::memory_order_relaxed) % kSchedSlots) : -1;
   const int BN = (a.cout > 64) ? 128 : 64;
   p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
   p.n_tiles = (a.cout + BN - 1) / BN;

@@ -16,6 +16,7 @@ struct ConvFwdParams {          // device-side view
   float res_scale;
   int pair_maps;                // 1: tm_a_hi / tm_b_hi are (hi, lo) pair maps (one TMA instruction per operand tile)
   int ncat;                     // 1: a_hi x [b_hi ; b_lo] as one N = 2 BN instruction (2 MMAs per k16 step instead of 3)
+  int sched_slot;               // >= 0: tiles are handed out by a device-wide counter (slot of g_tile_sched); -1: static stride
   const float* bias;            // [cout] or null
   const float* residual;        // [N,H,W,cout] (res_shift=0) or [N,H/2,W/2,cout] nearest-x2 (res_shift=1), or null
   int res_shift;

@@ -98,6 +98,9 @@ class FusedAdam:
     def _step_capturable(self, items):
         pl = self._plan
         beta1, beta2 = self.betas
+        if pl.get("static_ptrs") is not None and not torch.cuda.is_current_stream_capturing() and \
+                pl["static_ptrs"] != [(p.data_ptr(), p.grad.data_ptr() if p.grad is not None else 0) for p, _ in items]:
+            pl["static_ptrs"] = None          # a gradient moved (GradBuckets re-cut its buckets): rebuild the table, keep the count
         if pl.get("static_ptrs") is None:
             tab = pl["np"][0]
             ptrs = []
@@ -111,11 +114,9 @@ class FusedAdam:
             pl["table"].copy_(pl["hosts"][0])
             torch.cuda.current_stream().synchronize()
             pl["static_ptrs"] = ptrs
-            first = max(int(self.state[p]["step"]) for p, _ in items)
-            self._step_dev = torch.full((1,), first, dtype=torch.int64, device=pl["dev"])
-        elif not torch.cuda.is_current_stream_capturing():
-            if pl["static_ptrs"] != [(p.data_ptr(), p.grad.data_ptr() if p.grad is not None else 0) for p, _ in items]:
-                raise RuntimeError("capturable FusedAdam: a parameter or gradient moved since the table was built")
+            if self._step_dev is None:
+                first = max(int(self.state[p]["step"]) for p, _ in items)
+                self._step_dev = torch.full((1,), first, dtype=torch.int64, device=pl["dev"])
         self._step_dev.add_(1)
         call("l2i_adam_step", pl["table"], pl["chunks"], pl["n_chunks"], CHUNK, beta1, beta2, self.eps, self._step_dev)
 
@@ -209,6 +210,7 @@ class FusedAdam:
                              "exp_avg": st["exp_avg"].to(p.device, torch.float32).reshape(p.shape).clone(),
                              "exp_avg_sq": st["exp_avg_sq"].to(p.device, torch.float32).reshape(p.shape).clone()}
         self._plan = None                     # the next step moves the loaded moments into flat buffers
+        self._step_dev = None                 # (capturable) the device-side count restarts from the loaded one
 
 
 _HAS_SET_VERSION = hasattr(torch._C._autograd, "_unsafe_set_version_counter")

@@ -89,53 +89,86 @@ class GradBuckets:
 
     * every parameter's .grad is a VIEW into one flat fp32 buffer -- autograd accumulates into it in place, the
       optimizer kernel reads it in place; there are no flatten / unflatten copies;
-    * the flat buffer is cut into buckets in reverse parameter order (the order in which backward finishes them); a
-      bucket's all-reduce (average) is launched on a side stream from the post-accumulate hook of its last parameter,
-      so it overlaps the rest of the backward pass; `finish()` reduces whatever is left and makes the compute stream
-      wait for the side stream;
+    * the flat buffer is laid out in the order in which the backward pass finishes the gradients and cut into buckets
+      along it; a bucket's all-reduce (average) is launched on a side stream from the post-accumulate hook of its last
+      parameter, so it overlaps the rest of the backward pass; `finish()` reduces whatever is left and makes the compute
+      stream wait for the side stream.  The order starts as reverse registration order and is replaced, once, by the
+      order OBSERVED in the first backward pass (rank 0's, broadcast) -- in the generator the mask-regression network is
+      registered last but finishes last too (every stage feeds it), and a bucket waits for its slowest member.  The
+      last few MB of the order form their own small bucket: it is the only all-reduce nothing can overlap;
     * parameters and buffers (spectral-norm u / v, batch-norm running statistics) are broadcast from rank 0 at
       construction, so the replicas start identical even if their initialisation was not.
 
     On a single process it only provides the flat gradient buffer (zero_grad = one memset).  Works with NCCL (streams,
     ReduceOp.AVG) and with gloo on CPU tensors (synchronous; used by the CPU tests)."""
 
-    def __init__(self, module: torch.nn.Module, bucket_mb: Optional[float] = None, group=None, broadcast: bool = True):
+    def __init__(self, module: torch.nn.Module, bucket_mb: Optional[float] = None, group=None, broadcast: bool = True,
+                 tail_mb: Optional[float] = None, reorder: bool = True):
+        import os
         if bucket_mb is None:
-            import os
             bucket_mb = float(os.environ.get("L2I_BUCKET_MB", "48"))
+        if tail_mb is None:
+            tail_mb = min(float(os.environ.get("L2I_BUCKET_TAIL_MB", "4")), bucket_mb)
         self.params: List[torch.nn.Parameter] = [p for p in module.parameters() if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        dev = self.params[0].device
-        self.cuda = dev.type == "cuda"
-        offs, total = [], 0
-        for p in self.params:
-            offs.append(total)
-            total += (p.numel() + 3) // 4 * 4                  # 16-byte aligned slices
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, self.params)]
-        # buckets: contiguous ranges of the flat buffer, filled from the LAST parameter backwards
-        limit = int(bucket_mb * (1 << 20) / 4)
-        self.buckets, self.bucket_of = [], {}
-        end = total
-        members: List[int] = []
-        for i in range(len(self.params) - 1, -1, -1):
-            members.append(i)
-            if end - offs[i] >= limit or i == 0:
-                self.buckets.append({"range": (offs[i], end), "members": members, "pending": 0, "launched": False})
-                for m in members:
-                    self.bucket_of[m] = len(self.buckets) - 1
-                end, members = offs[i], []
-        self.comm_stream = torch.cuda.Stream(device=dev) if (self.cuda and self.world > 1) else None
+        self.dev = self.params[0].device
+        self.cuda = self.dev.type == "cuda"
+        self.limit = max(1, int(bucket_mb * (1 << 20) / 4))
+        self.tail_limit = max(1, int(tail_mb * (1 << 20) / 4))
+        self.comm_stream = torch.cuda.Stream(device=self.dev) if (self.cuda and self.world > 1) else None
         self.works = []
-        self._attach()
+        if os.environ.get("L2I_BUCKET_REORDER", "1") == "0":      # A/B switch for measurements
+            reorder = False
+        self.reordered = not (reorder and self.world > 1)        # single process: nothing to overlap, keep the layout
+        self._fired: List[int] = []
+        self._observed: Optional[List[int]] = None
+        self._layout(list(range(len(self.params) - 1, -1, -1)))
         if self.world > 1:
             for i, p in enumerate(self.params):
                 p.register_post_accumulate_grad_hook(lambda _p, i=i: self._ready(i))
             if broadcast:
                 with torch.no_grad():
                     for t in list(module.parameters()) + list(module.buffers()):
-                        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+                        dist.broadcast(t, src=self._src(), group=group)
+
+    def _src(self):
+        return dist.get_global_rank(self.group, 0) if self.group is not None else 0
+
+    def _layout(self, order: List[int]):
+        """Flat buffer, .grad views and buckets for `order` (parameter indices, first-finished first)."""
+        size = [(p.numel() + 3) // 4 * 4 for p in self.params]     # 16-byte aligned slices
+        offs, total = [0] * len(self.params), 0
+        for i in order:
+            offs[i] = total
+            total += size[i]
+        self.order = list(order)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, self.params)]
+        # the tail bucket: as many of the last-finished parameters as fit in tail_limit (at least one)
+        k, acc = len(order), 0
+        while k > 0 and (k == len(order) or acc + size[order[k - 1]] <= self.tail_limit):
+            acc += size[order[k - 1]]
+            k -= 1
+        self.buckets, self.bucket_of = [], {}
+
+        def close(members):
+            if members:
+                s = offs[members[0]]
+                self.buckets.append({"range": (s, offs[members[-1]] + size[members[-1]]), "members": members, "pending": 0,
+                                     "launched": False})
+                for m in members:
+                    self.bucket_of[m] = len(self.buckets) - 1
+
+        members: List[int] = []
+        for i in order[:k]:
+            members.append(i)
+            if sum(size[m] for m in members) >= self.limit:
+                close(members)
+                members = []
+        close(members)
+        close(list(order[k:]))
+        self._attach()
         self._reset()
 
     def _attach(self):
@@ -147,9 +180,29 @@ class GradBuckets:
         for b in self.buckets:
             b["pending"], b["launched"] = len(b["members"]), False
         self.works = []
+        self._fired = []
+
+    def _maybe_reorder(self):
+        """Once, at the first zero_grad after a complete backward pass (the gradients are about to be cleared, so nothing
+        has to be carried over): lay the buffer out in the observed completion order.  Every rank uses rank 0's order."""
+        if self.reordered or self._observed is None or (self.cuda and torch.cuda.is_current_stream_capturing()):
+            return
+        seen = set(self._observed)
+        order = self._observed + [i for i in self.order if i not in seen]       # never-fired parameters keep their place at the end
+        t = torch.tensor(order, dtype=torch.int64, device=self.dev)
+        dist.broadcast(t, src=self._src(), group=self.group)
+        order = [int(i) for i in t.tolist()]
+        if sorted(order) != list(range(len(self.params))):
+            raise RuntimeError("GradBuckets: rank 0 observed an inconsistent gradient order")
+        self.reordered = True
+        if order != self.order:
+            if self.comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+            self._layout(order)
 
     def zero_grad(self):
         """Replaces module.zero_grad(): one memset of the flat buffer; the .grad views stay attached."""
+        self._maybe_reorder()
         self.flat.zero_()
         self._attach()
 
@@ -168,6 +221,7 @@ class GradBuckets:
             chunk.div_(self.world)
 
     def _ready(self, i: int):
+        self._fired.append(i)
         b = self.buckets[self.bucket_of[i]]
         b["pending"] -= 1
         if b["pending"] == 0 and not b["launched"]:
@@ -182,6 +236,8 @@ class GradBuckets:
                     self._launch(b)
             if self.comm_stream is not None:
                 torch.cuda.current_stream().wait_stream(self.comm_stream)
+            if not self.reordered and self._observed is None and self._fired:
+                self._observed = list(dict.fromkeys(self._fired))
         self._reset()
 
     __call__ = finish
@@ -270,8 +326,11 @@ class GraphedTrainStep:
                        "z_im": z_im.clone()}
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        # eager steps before the capture: they build every lazily created table / workspace, and (data parallel) the
+        # second one re-cuts the gradient buckets in the completion order the first one observed
+        warmup = max(2 if self.sync_d.world > 1 else 1, warmup)
         with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):       # builds every lazily created table / workspace outside the capture
+            for _ in range(warmup):
                 self._step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
@@ -281,7 +340,7 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.out = self._step()
         self.kernels_per_replay = lib().l2i_launch_count(1)      # libl2i kernel nodes recorded in the graph
-        self.warmup_steps = max(1, warmup)        # eager steps already applied to the networks (capture itself executes nothing)
+        self.warmup_steps = warmup                # eager steps already applied to the networks (capture itself executes nothing)
 
     def _step(self):
         s = self.static

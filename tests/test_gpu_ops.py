@@ -727,3 +727,20 @@ def test_class_mix_matches_composition(dev, B, O, h, C):
     close(conv.bias.grad, conv_r.bias.grad, 1e-3, 1e-5 * max(1.0, conv_r.bias.grad.abs().max().item()), "d conv bias")
     close(ag.grad, ar.grad, 1e-3, 1e-5 * max(1.0, ar.grad.abs().max().item()), "d alpha")
     close(bg.grad, br.grad, 1e-3, 1e-5, "d bmask")
+
+
+@pytest.mark.gpu
+def test_conv_tile_queue_variants_match():
+    """The convolution kernel's tile order is a launch-time switch read once per process (L2I_CONV_DYNAMIC: tiles handed
+    out by a device-wide counter instead of a static stride; L2I_CONV_NCAT=0: three-instruction product form).  Re-run
+    the convolution parity tests in child processes with the non-default settings."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for var, val in (("L2I_CONV_DYNAMIC", "1"), ("L2I_CONV_NCAT", "0")):
+        env = dict(os.environ, **{var: val})
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_ops.py"), "-q", "-x", "-k",
+                            "test_conv_fwd_dgrad_wgrad or test_conv_epilogue_mask_pool_residual_pair"],
+                           cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, f"{var}={val}:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"

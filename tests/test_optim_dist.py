@@ -29,8 +29,10 @@ def _worker(rank, world, port, q):
     buckets = GradBuckets(net, bucket_mb=1e-4)                  # tiny buckets: several all-reduces per backward
     params0 = [p.detach().clone() for p in net.parameters()]
     x = torch.arange(10, dtype=torch.float32).view(2, 5) / 10.0
-    for _ in range(2):                                          # two iterations: views stay attached, counters reset
-        buckets.zero_grad()
+    layouts = []
+    for _ in range(3):                                          # views stay attached, counters reset; the second zero_grad
+        buckets.zero_grad()                                     # re-cuts the buckets in the completion order seen in the first pass
+        layouts.append((list(buckets.order), [tuple(b["members"]) for b in buckets.buckets], buckets.reordered))
         ((rank + 1.0) * net[1](net[0](x))).sum().backward()
         buckets.finish()
     grads = [p.grad.clone() for p in net.parameters()]
@@ -45,7 +47,7 @@ def _worker(rank, world, port, q):
     gw = w.grad.clone()
     dist.all_reduce(gw)
     gw /= world                                                 # what the gradient average over the ranks yields
-    q.put((rank, params0, grads, is_view, gw))
+    q.put((rank, params0, grads, is_view, gw, layouts))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -74,6 +76,15 @@ def test_grad_buckets_world2_gloo():
         assert res[r][2], "gradients must be views into the flat buffer"
         for got, w in zip(res[r][1], want):
             assert torch.allclose(got, w, rtol=1e-5, atol=1e-6), (r, got, w)
+    # bucket layout: reverse registration order at first; from the second iteration on the observed completion order
+    # (net[1] before net[0], bias before weight as autograd finishes them; the unused layer keeps its place at the end),
+    # identical on both ranks, the tail bucket holding the last-finished parameters
+    for r in range(world):
+        first, second, third = res[r][4]
+        assert first[0] == [5, 4, 3, 2, 1, 0] and first[2] is False
+        assert second[2] is True and second == third == res[0][4][1]
+        assert set(second[0][:2]) == {2, 3} and set(second[0][2:4]) == {0, 1} and second[0][4:] == [5, 4]
+        assert sorted(m for b in second[1] for m in b) == [0, 1, 2, 3, 4, 5]
     # K-weighted object loss: equals the gradient of ONE mean over all 8 valid objects of both ranks
     w = torch.nn.Parameter(torch.tensor([0.5, -0.25]))
     allf = torch.arange(16, dtype=torch.float32).view(8, 2) / 7.0
