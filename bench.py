@@ -496,9 +496,10 @@ def run_ours(args, rank, local_rank, world):
             "tensor_pipe_active_pct_ncu": prof.get("sm__pipe_tensor_cycles_active_pct"),
             "all_conv_fwd_dgrad_launches": {"achieved": tf(conv), "frac": tf(conv) / peak if conv["ms"] else None,
                                             "launches_per_step": conv["calls"], "ms_per_step": conv["ms"],
-                                            "share_of_step": conv["ms"] / step_ms if step_ms else None},
+                                            "share_of_step": conv["ms"] / (ms / args.steps)},
             "all_conv_wgrad_launches": {"achieved": tf(wg), "frac": tf(wg) / peak if wg["ms"] else None,
-                                        "launches_per_step": wg["calls"], "ms_per_step": wg["ms"]},
+                                        "launches_per_step": wg["calls"], "ms_per_step": wg["ms"],
+                                        "share_of_step": wg["ms"] / (ms / args.steps)},
         }
         breakdown = {k: {"calls": v["calls"], "ms": round(v["ms"], 3)} for k, v in
                      sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}

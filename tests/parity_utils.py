@@ -20,6 +20,19 @@ def close(got, want, rtol=RTOL, atol=ATOL, what=""):
                            f"(ref max {want.abs().max().item():.3e})")
 
 
+def close_modulo_kinks(got, want, rtol, atol, what=""):
+    """`close` for two runs of OUR path whose summation order differs (atomics, different tile compositions): a
+    pre-activation within rounding distance of zero can land on either side of a ReLU, which moves the few gradient
+    elements it feeds by a visible amount.  At most max(2, 0.1 %) of the elements may miss (rtol, atol), none by more than
+    5 % of the tensor's maximum."""
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    err = (got - want).abs()
+    bad = err > atol + rtol * want.abs()
+    m = want.abs().max().item()
+    assert int(bad.sum()) <= max(2, bad.numel() // 1000) and err.max().item() <= max(atol, 5e-2 * m), \
+        (f"{what}: {int(bad.sum())}/{bad.numel()} outside tol, max err {err.max().item():.3e} (ref max {m:.3e})")
+
+
 def oracle_step(schema_g, schema_d, seed_g, seed_d, data, keep, dtype, device="cpu"):
     """One oracle iteration in `dtype` on `device`; returns grads ("d.<name>" after d_loss.backward, "g.<name>" after
     g_loss.backward), losses, fake and the post-step states.  On a CUDA device this is the same restatement running
