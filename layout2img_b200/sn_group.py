@@ -12,6 +12,7 @@ consumers through functional.take_prepared(weight).
 """
 from __future__ import annotations
 
+import weakref
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -25,12 +26,24 @@ _ENTRY = np.dtype([("W", "<u8"), ("u", "<u8"), ("v", "<u8"), ("f32_off", "<i8"),
                    ("pad", "<i4")])
 assert _ENTRY.itemsize == 72
 
-# id(weight tensor) -> (SNState | None, WeightPair | None); filled by SNGroup.prepare, consumed once by the autograd nodes
+# id(weight tensor) -> (weakref to the tensor, its version counter, SNState | None, WeightPair | None); filled by
+# SNGroup.prepare, consumed once by the autograd nodes.  An entry is only honoured for the very tensor it was made
+# from, unmodified since: ids are recycled once a network is freed, and an entry that nobody consumed (a module the
+# forward did not reach) must not be picked up after an optimizer step.
 PREPARED: Dict[int, tuple] = {}
 
 
+def _valid(entry, weight: torch.Tensor) -> bool:
+    return entry is not None and entry[0]() is weight and entry[1] == weight._version
+
+
 def take_prepared(weight: torch.Tensor):
-    return PREPARED.pop(id(weight), None)
+    entry = PREPARED.pop(id(weight), None)
+    return (entry[2], entry[3]) if _valid(entry, weight) else None
+
+
+def has_prepared(weight: torch.Tensor) -> bool:
+    return _valid(PREPARED.get(id(weight)), weight)
 
 
 def _pad4(n: int) -> int:
@@ -169,6 +182,8 @@ class SNGroup:
         bv = torch.split_with_sizes(bf[:self.bf_elems], self.bf_sizes) if self.bf_elems else ()
         for k in self._keys:                   # entries of the previous call that nobody consumed
             PREPARED.pop(k, None)
+        for k in [k for k, e in PREPARED.items() if e[0]() is None]:      # ... and of networks that no longer exist
+            del PREPARED[k]
         self._keys = []
         bi = 0
         for i, d in enumerate(self.mods):
@@ -178,9 +193,9 @@ class SNGroup:
                 wp = WeightPair(bv[bi], bv[bi + 1], bv[bi + 2] if need_dgrad else None, bv[bi + 3] if need_dgrad else None,
                                 d["R"], d["cin"], d["taps"])
                 bi += 4
-            key = id(self._weights(d)[0])
-            PREPARED[key] = (st, wp)
-            self._keys.append(key)
+            w = self._weights(d)[0]
+            PREPARED[id(w)] = (weakref.ref(w), w._version, st, wp)
+            self._keys.append(id(w))
 
 
 def prepare_network(net: torch.nn.Module):

@@ -277,7 +277,7 @@ def test_grouped_spectral_norm_equals_per_module_path():
         sum(o.sum() for o in out2).backward()
     finally:
         dmod.prepare_network = orig
-    assert not sn_group.PREPARED or all(k not in sn_group.PREPARED for k in [id(p) for p in D2.parameters()])
+    assert not any(sn_group.has_prepared(p) for p in D2.parameters())      # D2 really took the per-module path
     for a, b in zip(out1, out2):
         close(a, b, 1e-5, 1e-6, "D output grouped vs per-module")
     sd1, sd2 = D.state_dict(), D2.state_dict()
