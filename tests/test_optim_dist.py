@@ -47,7 +47,9 @@ def _worker(rank, world, port, q):
     gw = w.grad.clone()
     dist.all_reduce(gw)
     gw /= world                                                 # what the gradient average over the ranks yields
-    q.put((rank, params0, grads, is_view, gw, layouts))
+    # by value (numpy), not as shared-memory handles: a torch tensor in an mp queue must outlive its receiver's unpickling,
+    # and this process exits right after the barrier
+    q.put((rank, [t.numpy() for t in params0], [t.numpy() for t in grads], is_view, gw.numpy(), layouts))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -59,7 +61,10 @@ def test_grad_buckets_world2_gloo():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = {r: rest for r, *rest in (q.get(timeout=120) for _ in range(world))}
+    res = {}
+    for _ in range(world):
+        r, params0, grads, is_view, gw, layouts = q.get(timeout=120)
+        res[r] = [[torch.from_numpy(a) for a in params0], [torch.from_numpy(a) for a in grads], is_view, torch.from_numpy(gw), layouts]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -101,3 +106,30 @@ def test_shards_are_disjoint_and_deterministic():
     assert torch.equal(a["z"], a2["z"]) and torch.equal(a["bbox"], a2["bbox"])
     assert not torch.equal(a["z"], b["z"])
     assert a["bbox"].shape == (4, 8, 4) and a["label"].min() >= 1
+
+
+def test_bucket_layout_follows_the_given_order():
+    """GradBuckets._layout: the flat buffer follows the completion order, every bucket is one contiguous range of it,
+    buckets close at the size limit, and the last-finished parameters (<= tail_mb) form their own final bucket."""
+    from layout2img_b200.train import GradBuckets
+    net = torch.nn.Sequential(*[torch.nn.Linear(16, 16, bias=False) for _ in range(6)])     # 6 x 1 KiB gradients
+    b = GradBuckets(net, bucket_mb=2.5 / 1024, tail_mb=1.5 / 1024)                           # 2.5 KiB buckets, 1.5 KiB tail
+    assert b.order == [5, 4, 3, 2, 1, 0] and b.reordered                                      # single process: nothing to learn
+    assert [bk["members"] for bk in b.buckets] == [[5, 4, 3], [2, 1], [0]]
+    order = [2, 0, 5, 1, 4, 3]
+    b._layout(order)
+    assert [bk["members"] for bk in b.buckets] == [[2, 0, 5], [1, 4], [3]]
+    pos = 0
+    for bk in b.buckets:
+        s, e = bk["range"]
+        assert s == pos and e - s == 256 * len(bk["members"])
+        for k, m in enumerate(bk["members"]):                     # member k of a bucket sits at its k-th slice
+            assert b.views[m].data_ptr() == b.flat.data_ptr() + 4 * (s + 256 * k)
+        pos = e
+    assert pos == b.flat.numel() == 6 * 256
+    for p, v in zip(net.parameters(), b.views):
+        assert p.grad is v
+    net(torch.ones(1, 16)).sum().backward()                       # autograd accumulates into the views in place
+    assert all(p.grad is v and float(v.abs().sum()) > 0 for p, v in zip(net.parameters(), b.views))
+    b.zero_grad()
+    assert float(b.flat.abs().sum()) == 0.0 and all(p.grad is v for p, v in zip(net.parameters(), b.views))
