@@ -911,8 +911,14 @@ int conv_fwd_tc(const ConvFwdArgs& a, cudaStream_t stream) {
   static const int dynamic_enabled = env_int("L2I_CONV_DYNAMIC", 0);
   static std::atomic<unsigned> next_slot{0};
   p.sched_slot = dynamic_enabled ? static_cast<int>(next_slot.fetch_add(1, std::memory_order_relaxed) % kSchedSlots) : -1;
-  const int BN = (a.cout > 64) ? 128 : 64;
   p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+  int BN = (a.cout > 64) ? 128 : 64;
+  // few pixels, many channels (1024 -> 1024 at 4 x 4: 8 x 8 tiles of 128 x 128 for 148 SMs; the 308-wide linears):
+  // with 128-wide tiles less than half of the SMs would get a tile, each with the whole K loop; 64-wide tiles double
+  // the CTAs that work (measured: 96 -> 78 us on 1024 -> 1024 at 4 x 4, 89.2 -> 87.8 ms per step;
+  // L2I_CONV_NARROW_TILES=0 restores the 128-wide tiles)
+  static const int narrow_enabled = env_int("L2I_CONV_NARROW_TILES", 1);
+  if (narrow_enabled && BN == 128 && 2LL * p.m_tiles * ((a.cout + 127) / 128) <= sm_count()) BN = 64;
   p.n_tiles = (a.cout + BN - 1) / BN;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
