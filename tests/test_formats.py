@@ -86,3 +86,22 @@ def test_drop_in_import_path():
             "for n in ('conv2d', 'bbox_mask', 'batched_index_select', 'BatchNorm'): assert n in globals(), n\n")
     r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_prepared_weight_entries_are_tied_to_the_live_unmodified_tensor():
+    """sn_group.PREPARED hands the grouped spectral-norm results to the autograd nodes keyed by id(weight); an entry must
+    not be honoured for another tensor that recycled the id, nor after the weight was modified (optimizer step)."""
+    import weakref
+    from layout2img_b200 import sn_group
+    w = torch.nn.Parameter(torch.ones(4, 4))
+    sn_group.PREPARED[id(w)] = (weakref.ref(w), w._version, "state", "pairs")
+    assert sn_group.has_prepared(w)
+    assert sn_group.take_prepared(w) == ("state", "pairs") and not sn_group.has_prepared(w)     # consumed once
+    sn_group.PREPARED[id(w)] = (weakref.ref(w), w._version, "state", "pairs")
+    with torch.no_grad():
+        w.add_(1.0)                                                                              # version counter moves
+    assert not sn_group.has_prepared(w) and sn_group.take_prepared(w) is None
+    other = torch.nn.Parameter(torch.zeros(4, 4))
+    sn_group.PREPARED[id(other)] = (weakref.ref(w), other._version, "state of w", "pairs of w")  # a recycled id
+    assert not sn_group.has_prepared(other) and sn_group.take_prepared(other) is None
+    assert id(other) not in sn_group.PREPARED
