@@ -37,6 +37,15 @@ def _worker(rank, world, port, q):
         buckets.finish()
     grads = [p.grad.clone() for p in net.parameters()]
     is_view = all(p.grad.untyped_storage().data_ptr() == buckets.flat.untyped_storage().data_ptr() for p in net.parameters())
+    # ---- 1b. the one-call set-up of a rank: buckets for both networks + global-batch BN statistics switched on
+    from layout2img_b200 import ops
+    from layout2img_b200.train import setup_data_parallel
+    gA, gB = torch.nn.Linear(3, 3), torch.nn.Linear(3, 2)
+    sA, sB = setup_data_parallel(gA, gB)
+    dp_ok = (sA.world == sB.world == world and ops._SYNC_BN["world"] == world and sA.params[0] is gA.weight
+             and sB.params[0] is gB.weight)
+    ops.set_sync_bn(False)
+    dp_ok = dp_ok and ops._SYNC_BN["world"] == 1
     # ---- 2. object-loss normalisation over the GLOBAL object count (ranks hold different numbers of valid objects)
     k_r = 3 if rank == 0 else 5
     label = torch.cat([torch.ones(k_r, dtype=torch.long), torch.zeros(8 - k_r, dtype=torch.long)]).view(1, 8)
@@ -49,7 +58,7 @@ def _worker(rank, world, port, q):
     gw /= world                                                 # what the gradient average over the ranks yields
     # by value (numpy), not as shared-memory handles: a torch tensor in an mp queue must outlive its receiver's unpickling,
     # and this process exits right after the barrier
-    q.put((rank, [t.numpy() for t in params0], [t.numpy() for t in grads], is_view, gw.numpy(), layouts))
+    q.put((rank, [t.numpy() for t in params0], [t.numpy() for t in grads], is_view and dp_ok, gw.numpy(), layouts))
     dist.barrier()
     dist.destroy_process_group()
 
